@@ -1,0 +1,18 @@
+// Library identification and error strings for the C ABI (include/unidistill_b200.h).
+#include "common.cuh"
+
+extern "C" {
+
+const char* ud_version(void) { return "unidistill_b200 sm_100a " __DATE__; }
+
+const char* ud_error_string(int code) {
+    switch (code) {
+        case UD_OK: return "ok";
+        case UD_ERR_INVALID_ARG: return "unidistill_b200: invalid argument";
+        case UD_ERR_WORKSPACE: return "unidistill_b200: workspace missing or too small";
+        case UD_ERR_UNSUPPORTED: return "unidistill_b200: unsupported shape or size";
+        default: return cudaGetErrorString((cudaError_t)code);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// Row-matrix BatchNorm1d (+residual, +ReLU) and the sparse->dense BEV scatter.
+//
+// BatchNorm: reference spconv_backbone.py:255 builds nn.BatchNorm1d(eps=1e-3, momentum=0.01) after every
+// sparse conv and applies it to the (N_active, C) feature matrix (post_act_block :10-58,
+// SparseBasicBlock.forward :97-113).  Here one statistics pass + one fused apply pass
+// (scale/shift, optional residual add, optional ReLU) replaces 3-4 elementwise passes.
+//
+// Scatter: reference layers/blocks_2d/det3d/map_to_bev/height_compression.py:11-22
+// (`sp_tensor.dense()` -> (B, C, D, H, W) -> view(B, C*D, H, W)); channel index = c*D + z.
+#include "common.cuh"
+
+namespace {
+
+// ---- statistics: per-channel sum and sum of squares over the active rows ----------------------
+// block = 256 threads = (256/C) row lanes x C channels, C in {16,32,64,128}
+__global__ void __launch_bounds__(256)
+k_bn_stats(const float* __restrict__ x, int n, int C, double* __restrict__ sum, double* __restrict__ sqsum) {
+    __shared__ float s_sum[256];
+    __shared__ float s_sq[256];
+    const int c = threadIdx.x % C;
+    const int rl = threadIdx.x / C;
+    const int RL = blockDim.x / C;
+    float a = 0.f, b = 0.f;
+    for (long long r = (long long)blockIdx.x * RL + rl; r < n; r += (long long)gridDim.x * RL) {
+        float v = x[r * C + c];
+        a += v;
+        b = fmaf(v, v, b);
+    }
+    s_sum[threadIdx.x] = a;
+    s_sq[threadIdx.x] = b;
+    __syncthreads();
+    if (rl == 0) {
+        double da = 0.0, db = 0.0;
+        for (int j = 0; j < RL; ++j) {
+            da += (double)s_sum[j * C + c];
+            db += (double)s_sq[j * C + c];
+        }
+        atomicAdd(sum + c, da);
+        atomicAdd(sqsum + c, db);
+    }
+}
+
+// scale = gamma * invstd, shift = beta - mean * scale; optional running-stat update (training).
+__global__ void k_bn_finalize(const double* __restrict__ sum, const double* __restrict__ sqsum, int n, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                              float momentum, float* running_mean, float* running_var,
+                              float* __restrict__ scale, float* __restrict__ shift,
+                              float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double cnt = n > 0 ? (double)n : 1.0;
+    double mean = sum[c] / cnt;
+    double var = sqsum[c] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f;
+    float bt = beta ? beta[c] : 0.f;
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = bt - (float)mean * sc;
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = invstd;
+    if (running_mean && running_var) {
+        double unbiased = n > 1 ? var * cnt / (cnt - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// eval-mode scale/shift from running statistics
+__global__ void k_bn_eval_coeffs(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 int C, float* __restrict__ scale, float* __restrict__ shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float invstd = 1.f / sqrtf(running_var[c] + eps);
+    float sc = (gamma ? gamma[c] : 1.f) * invstd;
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - running_mean[c] * sc;
+}
+
+// y = relu?( x*scale[c] + shift[c] (+ residual) ), float4 vectorised; C % 4 == 0
+__global__ void __launch_bounds__(256)
+k_bn_apply(const float4* x, long long n4, int C4, const float4* __restrict__ scale,
+           const float4* __restrict__ shift, const float4* residual, int relu, float4* y) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4;
+         t += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(t % C4);
+        float4 v = x[t];
+        float4 sc = __ldg(scale + c4), sh = __ldg(shift + c4);
+        v.x = fmaf(v.x, sc.x, sh.x);
+        v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z);
+        v.w = fmaf(v.w, sc.w, sh.w);
+        if (residual) {
+            float4 r = residual[t];
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        y[t] = v;
+    }
+}
+
+// ---- BN backward (training) ---------------------------------------------------------------------
+// g = dy * (y > 0) if relu else dy.   sum_g[c] = sum g, sum_gx[c] = sum g * xhat, xhat = (x-mean)*invstd
+__global__ void __launch_bounds__(256)
+k_bn_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, int n,
+                int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                double* __restrict__ sum_g, double* __restrict__ sum_gx) {
+    __shared__ float s_a[256];
+    __shared__ float s_b[256];
+    const int c = threadIdx.x % C;
+    const int rl = threadIdx.x / C;
+    const int RL = blockDim.x / C;
+    const float m = mean[c], is = invstd[c];
+    float a = 0.f, b = 0.f;
+    for (long long r = (long long)blockIdx.x * RL + rl; r < n; r += (long long)gridDim.x * RL) {
+        float g = dy[r * C + c];
+        if (relu && !(y[r * C + c] > 0.f)) g = 0.f;
+        a += g;
+        b = fmaf(g, (x[r * C + c] - m) * is, b);
+    }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+    __syncthreads();
+    if (rl == 0) {
+        double da = 0.0, db = 0.0;
+        for (int j = 0; j < RL; ++j) {
+            da += (double)s_a[j * C + c];
+            db += (double)s_b[j * C + c];
+        }
+        atomicAdd(sum_g + c, da);
+        atomicAdd(sum_gx + c, db);
+    }
+}
+
+// dx = gamma*invstd * (g - sum_g/n - xhat * sum_gx/n);  dres = g (optional)
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+               long long total, int C, int n, const float* __restrict__ mean, const float* __restrict__ invstd,
+               const float* __restrict__ gamma, const double* __restrict__ sum_g,
+               const double* __restrict__ sum_gx, int relu, float* __restrict__ dx, float* __restrict__ dres) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(t % C);
+        float g = dy[t];
+        if (relu && !(y[t] > 0.f)) g = 0.f;
+        float is = invstd[c];
+        float xhat = (x[t] - mean[c]) * is;
+        float inv_n = 1.f / (float)n;
+        float mg = (float)sum_g[c] * inv_n;
+        float mgx = (float)sum_gx[c] * inv_n;
+        float gm = gamma ? gamma[c] : 1.f;
+        dx[t] = gm * is * (g - mg - xhat * mgx);
+        if (dres) dres[t] = g;
+    }
+}
+
+// ---- scatter to BEV ---------------------------------------------------------------------------
+// CTA = 32 consecutive rows (rows of one conv output are sorted by (b,z,y,x), so they are mostly
+// x-adjacent) x all C channels, staged through smem so that both the row reads (C contiguous floats)
+// and the NCHW writes (x contiguous) coalesce.
+__global__ void __launch_bounds__(256)
+k_scatter_bev(const float* __restrict__ feat, const int4* __restrict__ coords, int n, int C, int D, int H,
+              int W, float* __restrict__ out) {
+    extern __shared__ float tile[];   // [32][C+1]
+    __shared__ long long base_off[32];
+    const int row0 = blockIdx.x * 32;
+    const int rows = min(32, n - row0);
+    for (int e = threadIdx.x; e < 32 * C; e += blockDim.x) {
+        int r = e / C, c = e - r * C;
+        tile[r * (C + 1) + c] = r < rows ? feat[(size_t)(row0 + r) * C + c] : 0.f;
+    }
+    if (threadIdx.x < 32) {
+        long long off = -1;
+        if (threadIdx.x < rows) {
+            int4 q = coords[row0 + threadIdx.x];   // b, z, y, x
+            off = (((long long)q.x * C * D + q.y) * H + q.z) * W + q.w;
+        }
+        base_off[threadIdx.x] = off;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const long long off = base_off[lane];
+    const long long cstride = (long long)D * H * W;
+    if (off >= 0)
+        for (int c = wid; c < C; c += nw) out[off + c * cstride] = tile[lane * (C + 1) + c];
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_bev(const float* __restrict__ dense, const int4* __restrict__ coords, int n, int C, int D, int H,
+             int W, float* __restrict__ feat) {
+    extern __shared__ float tile[];   // [32][C+1]
+    __shared__ long long base_off[32];
+    const int row0 = blockIdx.x * 32;
+    const int rows = min(32, n - row0);
+    if (threadIdx.x < 32) {
+        long long off = -1;
+        if (threadIdx.x < rows) {
+            int4 q = coords[row0 + threadIdx.x];
+            off = (((long long)q.x * C * D + q.y) * H + q.z) * W + q.w;
+        }
+        base_off[threadIdx.x] = off;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const long long off = base_off[lane];
+    const long long cstride = (long long)D * H * W;
+    for (int c = wid; c < C; c += nw) tile[lane * (C + 1) + c] = off >= 0 ? dense[off + c * cstride] : 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * C; e += blockDim.x) {
+        int r = e / C, c = e - r * C;
+        feat[(size_t)(row0 + r) * C + c] = tile[r * (C + 1) + c];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// sum/sqsum: (C) f64 device scratch (zeroed here).  C must divide 256.
+int ud_bn_stats(const float* x, int n, int C, double* sum, double* sqsum, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x || !sum || !sqsum || n < 0 || C < 1 || C > 256 || 256 % C != 0) return UD_ERR_INVALID_ARG;
+    UD_CUDA_TRY(cudaMemsetAsync(sum, 0, sizeof(double) * C, stream));
+    UD_CUDA_TRY(cudaMemsetAsync(sqsum, 0, sizeof(double) * C, stream));
+    if (n == 0) return UD_OK;
+    int RL = 256 / C;
+    long long want = ((long long)n + RL - 1) / RL;
+    int grid = (int)(want < UD_NUM_SMS * 8 ? want : UD_NUM_SMS * 8);
+    k_bn_stats<<<grid, 256, 0, stream>>>(x, n, C, sum, sqsum);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+int ud_bn_finalize(const double* sum, const double* sqsum, int n, int C, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sum || !sqsum || !scale || !shift || C < 1) return UD_ERR_INVALID_ARG;
+    k_bn_finalize<<<ud_blocks(C, 128), 128, 0, stream>>>(sum, sqsum, n, C, gamma, beta, eps, momentum,
+                                                         running_mean, running_var, scale, shift, save_mean,
+                                                         save_invstd);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+int ud_bn_eval_coeffs(const float* running_mean, const float* running_var, const float* gamma,
+                      const float* beta, float eps, int C, float* scale, float* shift, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!running_mean || !running_var || !scale || !shift || C < 1) return UD_ERR_INVALID_ARG;
+    k_bn_eval_coeffs<<<ud_blocks(C, 128), 128, 0, stream>>>(running_mean, running_var, gamma, beta, eps, C,
+                                                            scale, shift);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// y may alias x.  residual may be NULL.  C % 4 == 0.
+int ud_bn_apply(const float* x, int n, int C, const float* scale, const float* shift, const float* residual,
+                int relu, float* y, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x || !y || !scale || !shift || n < 0 || C < 4 || C % 4 != 0) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    long long n4 = (long long)n * C / 4;
+    long long want = (n4 + 255) / 256;
+    int grid = (int)(want < UD_NUM_SMS * 16 ? want : UD_NUM_SMS * 16);
+    k_bn_apply<<<grid, 256, 0, stream>>>((const float4*)x, n4, C / 4, (const float4*)scale,
+                                         (const float4*)shift, (const float4*)residual, relu, (float4*)y);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// sum_g/sum_gx: (C) f64 scratch (zeroed here); dx: (n,C); dres nullable (n,C).
+int ud_bn_backward(const float* dy, const float* y, const float* x, int n, int C, const float* mean,
+                   const float* invstd, const float* gamma, int relu, double* sum_g, double* sum_gx,
+                   float* dx, float* dres, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!dy || !x || !mean || !invstd || !sum_g || !sum_gx || !dx || n < 0 || C < 1 || C > 256 || 256 % C != 0)
+        return UD_ERR_INVALID_ARG;
+    if (relu && !y) return UD_ERR_INVALID_ARG;
+    UD_CUDA_TRY(cudaMemsetAsync(sum_g, 0, sizeof(double) * C, stream));
+    UD_CUDA_TRY(cudaMemsetAsync(sum_gx, 0, sizeof(double) * C, stream));
+    if (n == 0) return UD_OK;
+    int RL = 256 / C;
+    long long want = ((long long)n + RL - 1) / RL;
+    int grid = (int)(want < UD_NUM_SMS * 8 ? want : UD_NUM_SMS * 8);
+    k_bn_bwd_reduce<<<grid, 256, 0, stream>>>(dy, y, x, n, C, mean, invstd, relu, sum_g, sum_gx);
+    UD_LAUNCH_CHECK();
+    long long total = (long long)n * C;
+    long long want2 = (total + 255) / 256;
+    int grid2 = (int)(want2 < UD_NUM_SMS * 16 ? want2 : UD_NUM_SMS * 16);
+    k_bn_bwd_apply<<<grid2, 256, 0, stream>>>(dy, y, x, total, C, n, mean, invstd, gamma, sum_g, sum_gx, relu,
+                                              dx, dres);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// feat: (n, C); coords: (n,4) [b,z,y,x]; out: (B, C*D, H, W) f32.  zero_fill != 0 clears `out` first.
+int ud_scatter_to_bev(const float* feat, const int* coords, int n, int batch_size, int C, int D, int H,
+                      int W, int zero_fill, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!feat || !coords || !out || n < 0 || C < 1 || C > 1024) return UD_ERR_INVALID_ARG;
+    if (zero_fill)
+        UD_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)batch_size * C * D * H * W * sizeof(float), stream));
+    if (n == 0) return UD_OK;
+    size_t smem = (size_t)32 * (C + 1) * sizeof(float);
+    k_scatter_bev<<<ud_blocks(n, 32), 256, smem, stream>>>(feat, (const int4*)coords, n, C, D, H, W, out);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// backward of the scatter: feat_grad[o, c] = dense_grad[b, c*D + z, y, x]
+int ud_gather_from_bev(const float* dense, const int* coords, int n, int batch_size, int C, int D, int H,
+                       int W, float* feat, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)batch_size;
+    if (!dense || !coords || !feat || n < 0 || C < 1 || C > 1024) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    size_t smem = (size_t)32 * (C + 1) * sizeof(float);
+    k_gather_bev<<<ud_blocks(n, 32), 256, smem, stream>>>(dense, (const int4*)coords, n, C, D, H, W, feat);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+}  // extern "C"

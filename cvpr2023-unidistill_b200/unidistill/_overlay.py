@@ -1,0 +1,18 @@
+"""Overlay support: lets this package sit *on top of* a reference checkout.
+
+When UNIDISTILL_REFERENCE_ROOT points at a CVPR2023-UniDistill checkout, every sub-package of this
+mirror appends the matching reference directory to its __path__.  Modules that exist here (the hot
+path: layers, voxelization, ...) win; everything else (exps/, data/multisensorfusion/, ...) resolves to
+the reference's own files, so its experiment scripts run unchanged on the sm_100a kernels.
+Without the variable the mirror is self-contained.
+"""
+import os
+
+
+def extend(path_list, package_name):
+    root = os.environ.get("UNIDISTILL_REFERENCE_ROOT")
+    if not root:
+        return
+    sub = os.path.join(root, *package_name.split("."))
+    if os.path.isdir(sub) and sub not in path_list:
+        path_list.append(sub)

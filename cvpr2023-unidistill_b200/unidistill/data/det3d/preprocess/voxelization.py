@@ -1,0 +1,40 @@
+"""Voxelization module -- same constructor / forward contract as the reference
+(unidistill/data/det3d/preprocess/voxelization.py:8-73), one batched GPU launch sequence instead of a
+per-sample Python loop over spconv's PointToVoxel with three clones and a cat per sample."""
+import numpy as np
+import torch
+from torch import nn
+
+from unidistill_b200.voxelize import hard_voxelize
+
+
+class Voxelization(nn.Module):
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels, num_point_features,
+                 device=None):
+        super().__init__()
+        if len(voxel_size) != 3 or len(point_cloud_range) != 6:
+            raise ValueError("voxel_size needs 3 entries and point_cloud_range 6")
+        self.voxel_size = np.array(voxel_size)
+        self.point_cloud_range = np.array(point_cloud_range)
+        self.max_num_points = int(max_num_points)
+        self.num_point_features = int(num_point_features)
+        if isinstance(max_voxels, tuple):
+            # a freshly constructed nn.Module is in training mode, so the reference always picks the
+            # first (train) entry here (voxelization.py:25-30); kept on purpose.
+            max_voxels = max_voxels[0] if self.training else max_voxels[1]
+        self.max_voxels = int(max_voxels)
+        extent = (self.point_cloud_range[3:6] - self.point_cloud_range[0:3]) / np.array(voxel_size)
+        self.grid_size = np.round(extent).astype(np.int64)
+        self.device = device
+
+    def forward(self, points):
+        """points: Tensor (N,C) or list of them -> (voxels (M,P,C), voxel_coords (M,4) int32 [b,z,y,x],
+        voxel_num_points (M,) int32).  The fused per-voxel mean rides along as `voxels._ud_mean`."""
+        if not isinstance(points, (list, tuple)):
+            points = [points]
+        voxels, coords, num, mean, _ = hard_voxelize(
+            list(points), self.voxel_size.tolist(), self.point_cloud_range.tolist(), self.grid_size.tolist(),
+            self.max_num_points, self.max_voxels, want_voxels=True, want_mean=True)
+        voxels._ud_mean = mean
+        voxels._ud_num_features = self.num_point_features
+        return voxels, coords, num

@@ -1,0 +1,317 @@
+"""Sparse-tensor operators on top of the C ABI: rulebooks, sparse convolution, fused BatchNorm+ReLU,
+dense()/scatter-to-BEV.  These are the primitives the `spconv` shim and the mirrored
+`unidistill.layers` modules are made of (reference: layers/blocks_3d/det3d/spconv_backbone.py).
+"""
+import torch
+from torch.autograd import Function
+
+from . import native
+
+_WS_RULEBOOK = 1  # workspace slot that must survive between conv_count and conv_fill
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+class Rulebook:
+    """Kernel map of one sparse convolution (see csrc/rulebook.cu for the conventions)."""
+
+    def __init__(self, subm, ksize, stride, padding, dilation, in_shape, out_shape, n_in, n_out,
+                 nbr_out, nbr_in, out_coords, batch_size):
+        self.subm = subm
+        self.ksize, self.stride, self.padding, self.dilation = ksize, stride, padding, dilation
+        self.in_shape, self.out_shape = list(in_shape), list(out_shape)
+        self.n_in, self.n_out = n_in, n_out
+        self.nbr_out, self.nbr_in = nbr_out, nbr_in
+        self.out_coords = out_coords
+        self.batch_size = batch_size
+        self.K = ksize[0] * ksize[1] * ksize[2]
+        self._pairs = None
+        self.in_coords_for_inverse = None
+
+    def num_pairs(self):
+        """Number of (input,output) pairs == rulebook size P (host sync; for reporting only)."""
+        return int((self.nbr_out >= 0).sum().item())
+
+    def spconv_pairs(self):
+        """spconv-shaped (indice_pairs (2,K,N_in) int32, indice_pair_num (K,) int32)."""
+        if self._pairs is None:
+            lib = native.load()
+            table = self.nbr_out if self.subm else self.nbr_in
+            dev = table.device
+            pairs = torch.empty((2, self.K, self.n_in), dtype=torch.int32, device=dev)
+            pair_num = torch.empty((self.K,), dtype=torch.int32, device=dev)
+            nbytes = native.query_bytes("ud_rulebook_pairs_workspace_bytes", self.n_in, self.K)
+            ws = native.WORKSPACE.get(nbytes, dev)
+            rc = lib.ud_rulebook_pairs(native.ptr(table), self.n_in, self.K, 1 if self.subm else 0,
+                                       native.ptr(pairs), native.ptr(pair_num), native.ptr(ws), ws.numel(),
+                                       native.stream_ptr(dev))
+            native.check(rc, "ud_rulebook_pairs")
+            self._pairs = (pairs, pair_num)
+        return self._pairs
+
+
+def conv_out_shape(in_shape, ksize, stride, padding, dilation):
+    return [
+        (in_shape[d] + 2 * padding[d] - dilation[d] * (ksize[d] - 1) - 1) // stride[d] + 1
+        for d in range(3)
+    ]
+
+
+def build_subm_rulebook(coords, batch_size, spatial_shape, ksize, dilation=1):
+    native.require_cuda(coords)
+    lib = native.load()
+    ksize, dilation = _triple(ksize), _triple(dilation)
+    assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
+    n = int(coords.shape[0])
+    K = ksize[0] * ksize[1] * ksize[2]
+    dev = coords.device
+    nbr = torch.empty((n, K), dtype=torch.int32, device=dev)
+    nbytes = native.query_bytes("ud_rulebook_subm_workspace_bytes", n)
+    ws = native.WORKSPACE.get(nbytes, dev)
+    shp, ks, dl = native.host_ints(spatial_shape), native.host_ints(ksize), native.host_ints(dilation)
+    rc = lib.ud_rulebook_subm(native.ptr(coords), n, int(batch_size), native.host_ptr(shp), native.host_ptr(ks),
+                              native.host_ptr(dl), native.ptr(nbr), native.ptr(ws), ws.numel(),
+                              native.stream_ptr(dev))
+    native.check(rc, "ud_rulebook_subm")
+    return Rulebook(True, ksize, [1, 1, 1], [k // 2 for k in ksize], dilation, spatial_shape, spatial_shape,
+                    n, n, nbr, None, coords, batch_size)
+
+
+def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, padding, dilation=1):
+    native.require_cuda(coords)
+    lib = native.load()
+    ksize, stride, padding, dilation = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    assert coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
+    n_in = int(coords.shape[0])
+    K = ksize[0] * ksize[1] * ksize[2]
+    dev = coords.device
+    out_shape = conv_out_shape(list(spatial_shape), ksize, stride, padding, dilation)
+    ish, osh = native.host_ints(spatial_shape), native.host_ints(out_shape)
+    ks, st, pd, dl = (native.host_ints(ksize), native.host_ints(stride), native.host_ints(padding),
+                      native.host_ints(dilation))
+    nbytes = native.query_bytes("ud_rulebook_conv_workspace_bytes", int(batch_size), native.host_ptr(osh))
+    ws = native.WORKSPACE.get(nbytes, dev, slot=_WS_RULEBOOK)
+    n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+    sp = native.stream_ptr(dev)
+    rc = lib.ud_rulebook_conv_count(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
+                                    native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
+                                    native.host_ptr(pd), native.host_ptr(dl), native.ptr(n_out_dev),
+                                    native.ptr(ws), ws.numel(), sp)
+    native.check(rc, "ud_rulebook_conv_count")
+    n_out = int(n_out_dev.item())   # host sync: output row count sizes the tables
+    out_coords = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
+    nbr_in = torch.empty((n_in, K), dtype=torch.int32, device=dev)
+    nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
+    rc = lib.ud_rulebook_conv_fill(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
+                                   native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
+                                   native.host_ptr(pd), native.host_ptr(dl), n_out, native.ptr(out_coords),
+                                   native.ptr(nbr_in), native.ptr(nbr_out), native.ptr(ws), ws.numel(), sp)
+    native.check(rc, "ud_rulebook_conv_fill")
+    return Rulebook(False, ksize, stride, padding, dilation, spatial_shape, out_shape, n_in, n_out,
+                    nbr_out, nbr_in, out_coords, batch_size)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout):
+    lib = native.load()
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
+    rc = lib.ud_sparse_conv_forward(native.ptr(feats), native.ptr(w_k), native.ptr(bias), native.ptr(table),
+                                    n_out, K, cin, cout, native.ptr(out), native.stream_ptr(feats.device))
+    native.check(rc, "ud_sparse_conv_forward")
+    return out
+
+
+def weight_to_taps(weight):
+    """spconv-2 parameter layout (Cout, kz, ky, kx, Cin) -> kernel layout (K, Cin, Cout)."""
+    cout, cin = weight.shape[0], weight.shape[-1]
+    return weight.reshape(cout, -1, cin).permute(1, 2, 0).contiguous()
+
+
+class SparseConvFunction(Function):
+    """out = sparse_conv(features, weight, bias) for a given Rulebook; custom dgrad/wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, features, weight, bias, rulebook, inverse=False):
+        native.require_cuda(features, weight)
+        features = features.contiguous().float()
+        rb = rulebook
+        cout, cin = int(weight.shape[0]), int(weight.shape[-1])
+        w_k = weight_to_taps(weight.detach().float())
+        if not inverse:
+            table, n_out = rb.nbr_out, rb.n_out
+        else:  # SparseInverseConv3d: roles of the paired strided conv swapped
+            table, n_out = rb.nbr_in, rb.n_in
+        assert features.shape[1] == cin, "feature width %d != conv in_channels %d" % (features.shape[1], cin)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        out = _conv_forward_raw(features, w_k, b, table, n_out, rb.K, cin, cout)
+        ctx.rb, ctx.inverse = rb, inverse
+        ctx.has_bias = bias is not None
+        ctx.wshape = tuple(weight.shape)
+        ctx.save_for_backward(features, w_k)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, w_k = ctx.saved_tensors
+        rb, inverse = ctx.rb, ctx.inverse
+        lib = native.load()
+        grad_out = grad_out.contiguous().float()
+        K, cin, cout = w_k.shape
+        dfeat = dweight = dbias = None
+        if ctx.needs_input_grad[0]:
+            if rb.subm:
+                w_t = w_k.flip(0).transpose(1, 2).contiguous()   # (K, cout, cin), taps mirrored
+                table, n_in = rb.nbr_out, rb.n_in
+            elif not inverse:
+                w_t = w_k.transpose(1, 2).contiguous()
+                table, n_in = rb.nbr_in, rb.n_in
+            else:
+                w_t = w_k.transpose(1, 2).contiguous()
+                table, n_in = rb.nbr_out, rb.n_out
+            dfeat = _conv_forward_raw(grad_out, w_t, None, table, n_in, K, cout, cin)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((K, cin, cout), dtype=torch.float32, device=grad_out.device)
+            if not inverse:
+                table, n_rows = rb.nbr_out, rb.n_out
+            else:
+                table, n_rows = rb.nbr_in, rb.n_in
+            rc = lib.ud_sparse_conv_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table),
+                                          n_rows, K, cin, cout, native.ptr(dw),
+                                          native.stream_ptr(grad_out.device))
+            native.check(rc, "ud_sparse_conv_wgrad")
+            dweight = dw.permute(2, 0, 1).reshape(ctx.wshape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dbias = grad_out.sum(0)
+        return dfeat, dweight, dbias, None, None
+
+
+def sparse_conv(features, weight, bias, rulebook, inverse=False):
+    return SparseConvFunction.apply(features, weight, bias, rulebook, inverse)
+
+
+# ---------------------------------------------------------------------------------------------------
+class BatchNormActFunction(Function):
+    """y = relu?(batch_norm(x) (+ residual)) over the rows of an (N, C) matrix; two kernels forward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, training, momentum, eps, relu):
+        native.require_cuda(x)
+        lib = native.load()
+        x = x.contiguous()
+        n, C = int(x.shape[0]), int(x.shape[1])
+        dev = x.device
+        sp = native.stream_ptr(dev)
+        scale = torch.empty((C,), dtype=torch.float32, device=dev)
+        shift = torch.empty((C,), dtype=torch.float32, device=dev)
+        res = residual.contiguous() if residual is not None else None
+        if training:
+            sums = torch.empty((2, C), dtype=torch.float64, device=dev)
+            save_mean = torch.empty((C,), dtype=torch.float32, device=dev)
+            save_invstd = torch.empty((C,), dtype=torch.float32, device=dev)
+            rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums[0]), native.ptr(sums[1]), sp)
+            native.check(rc, "ud_bn_stats")
+            rc = lib.ud_bn_finalize(native.ptr(sums[0]), native.ptr(sums[1]), n, C, native.ptr(gamma),
+                                    native.ptr(beta), float(eps), float(momentum), native.ptr(running_mean),
+                                    native.ptr(running_var), native.ptr(scale), native.ptr(shift),
+                                    native.ptr(save_mean), native.ptr(save_invstd), sp)
+            native.check(rc, "ud_bn_finalize")
+        else:
+            save_mean = save_invstd = None
+            rc = lib.ud_bn_eval_coeffs(native.ptr(running_mean), native.ptr(running_var), native.ptr(gamma),
+                                       native.ptr(beta), float(eps), C, native.ptr(scale), native.ptr(shift), sp)
+            native.check(rc, "ud_bn_eval_coeffs")
+        y = torch.empty_like(x)
+        rc = lib.ud_bn_apply(native.ptr(x), n, C, native.ptr(scale), native.ptr(shift), native.ptr(res),
+                             1 if relu else 0, native.ptr(y), sp)
+        native.check(rc, "ud_bn_apply")
+        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        ctx.has_affine = gamma is not None
+        if training:
+            ctx.save_for_backward(x, y, gamma, save_mean, save_invstd)
+        else:
+            ctx.save_for_backward(y, scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = native.load()
+        dy = dy.contiguous()
+        dev = dy.device
+        if ctx.training:
+            x, y, gamma, mean, invstd = ctx.saved_tensors
+            n, C = int(x.shape[0]), int(x.shape[1])
+            sums = torch.empty((2, C), dtype=torch.float64, device=dev)
+            dx = torch.empty_like(x)
+            dres = torch.empty_like(x) if ctx.has_res else None
+            rc = lib.ud_bn_backward(native.ptr(dy), native.ptr(y), native.ptr(x), n, C, native.ptr(mean),
+                                    native.ptr(invstd), native.ptr(gamma), 1 if ctx.relu else 0,
+                                    native.ptr(sums[0]), native.ptr(sums[1]), native.ptr(dx), native.ptr(dres),
+                                    native.stream_ptr(dev))
+            native.check(rc, "ud_bn_backward")
+            dgamma = sums[1].float() if ctx.has_affine else None
+            dbeta = sums[0].float() if ctx.has_affine else None
+            return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+        y, scale = ctx.saved_tensors
+        g = dy * (y > 0).to(dy.dtype) if ctx.relu else dy
+        dx = g * scale
+        dres = g if ctx.has_res else None
+        # eval-mode BN: parameters are treated as constants (frozen-teacher use)
+        return dx, None, None, dres, None, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, relu=True, residual=None):
+    """Fused replacement for `relu(bn(x) + residual)` with an nn.BatchNorm1d module `bn`."""
+    training = bn.training or (bn.running_mean is None)
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = bn.momentum if bn.momentum is not None else 0.1
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    if not training and torch.is_grad_enabled() and bn.weight is not None and bn.weight.requires_grad:
+        # eval-mode BN with trainable affine parameters: keep exact autograd semantics
+        y = torch.nn.functional.batch_norm(x, rm, rv, bn.weight, bn.bias, False, momentum, bn.eps)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+    return BatchNormActFunction.apply(x, bn.weight, bn.bias, residual, rm, rv, training, momentum, bn.eps, relu)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ScatterToBEVFunction(Function):
+    """(N, C) rows + (N,4) [b,z,y,x] -> dense (B, C, D, H, W) (== (B, C*D, H, W) memory)."""
+
+    @staticmethod
+    def forward(ctx, features, coords, batch_size, spatial_shape):
+        native.require_cuda(features, coords)
+        lib = native.load()
+        features = features.contiguous().float()
+        n, C = int(features.shape[0]), int(features.shape[1])
+        D, H, W = [int(s) for s in spatial_shape]
+        out = torch.empty((batch_size, C, D, H, W), dtype=torch.float32, device=features.device)
+        rc = lib.ud_scatter_to_bev(native.ptr(features), native.ptr(coords), n, int(batch_size), C, D, H, W, 1,
+                                   native.ptr(out), native.stream_ptr(features.device))
+        native.check(rc, "ud_scatter_to_bev")
+        ctx.save_for_backward(coords)
+        ctx.dims = (n, C, D, H, W, int(batch_size))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (coords,) = ctx.saved_tensors
+        n, C, D, H, W, B = ctx.dims
+        lib = native.load()
+        grad = grad.contiguous()
+        dfeat = torch.empty((n, C), dtype=torch.float32, device=grad.device)
+        rc = lib.ud_gather_from_bev(native.ptr(grad), native.ptr(coords), n, B, C, D, H, W, native.ptr(dfeat),
+                                    native.stream_ptr(grad.device))
+        native.check(rc, "ud_gather_from_bev")
+        return dfeat, None, None, None
+
+
+def scatter_to_dense(features, coords, batch_size, spatial_shape):
+    return ScatterToBEVFunction.apply(features, coords, batch_size, spatial_shape)

@@ -1,0 +1,124 @@
+/*
+ * unidistill_b200.h -- C ABI of the Blackwell (sm_100a) BEV feature-extraction + distillation path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers, sizes and a CUDA stream
+ * (passed as void* == cudaStream_t) and returns 0 on success, a cudaError_t value when a CUDA call
+ * failed, or one of the UD_ERR_* codes below.  Nothing synchronises the stream, nothing allocates:
+ * scratch comes from the caller (`*_workspace_bytes` tells how much).  "HOST" marks the few small
+ * arrays that are read on the host at call time.
+ *
+ * The reference (megvii-research/CVPR2023-UniDistill) exposes no C ABI of its own for this path; its
+ * native arithmetic lives in the spconv wheel and in the prebuilt voxel_pooling_ext .so.  Each
+ * declaration cites the reference call site (file:line under /root/reference) whose native callee it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ */
+#ifndef UNIDISTILL_B200_H
+#define UNIDISTILL_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UD_OK 0
+#define UD_ERR_INVALID_ARG 1001
+#define UD_ERR_WORKSPACE 1002
+#define UD_ERR_UNSUPPORTED 1003
+
+/* library / build identification ("unidistill_b200 sm_100a <date>") */
+const char* ud_version(void);
+/* human-readable text for a return code of this library (static storage) */
+const char* ud_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hard voxelization + mean VFE.
+ * Replaces spconv.pytorch.utils.PointToVoxel.__call__ as driven by
+ *   unidistill/data/det3d/preprocess/voxelization.py:31-38,53-68   (per-sample loop + clones + cat)
+ * and the reduction of unidistill/layers/blocks_3d/det3d/vfe/mean_vfe.py:25-32.
+ * points (N_total,C) f32: the batch's clouds concatenated; sample_offsets HOST int[batch_size+1].
+ * voxel_size HOST float[3] (x,y,z); pc_range HOST float[6]; grid_size HOST int[3] (x,y,z).
+ * Outputs (row capacity out_capacity): voxels (cap,max_points,C) f32 or NULL; coords (cap,4) int32
+ * [b,z,y,x]; num_points (cap) int32; mean (cap,C) f32 or NULL; counts (1+batch_size) int32 device =
+ * [total rows, rows of sample 0, ...].  Deterministic first-come order (see oracle/voxelize_ref.c).
+ * ------------------------------------------------------------------------------------------- */
+int ud_voxelize_workspace_bytes(int num_points_total, size_t* bytes);
+int ud_hard_voxelize(const float* points, const int* sample_offsets, int batch_size, int num_features,
+                     const float* voxel_size, const float* pc_range, const int* grid_size,
+                     int max_points, int max_voxels, int out_capacity, float* voxels, int* coords,
+                     int* num_points, float* mean, int* counts, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rulebooks.  Replace spconv's get_indice_pairs, implicit in every SubMConv3d/SparseConv3d of
+ *   unidistill/layers/blocks_3d/det3d/spconv_backbone.py:259-340
+ * (operator API visible at layers/blocks_3d/det3d/centernet_backbone.py:221-251).
+ * coords (n,4) int32 [b,z,y,x]; shapes/ksize/stride/padding/dilation are HOST int[3] in (z,y,x).
+ * Tables are int32 with -1 == absent, K = kz*ky*kx (<= 32), tap index k = (kz*KY+ky)*KX+kx:
+ *   nbr_out (n_out,K): input row feeding output row o through tap k
+ *   nbr_in  (n_in, K): output row fed by input row i through tap k
+ * Strided conv outputs are ordered ascending by linear (b,z,y,x) index.
+ * ------------------------------------------------------------------------------------------- */
+int ud_rulebook_subm_workspace_bytes(int n, size_t* bytes);
+int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatial_shape, const int* ksize,
+                     const int* dilation, int* nbr_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, size_t* bytes);
+/* phase 1: n_out_dev (device int) <- number of output rows; keep the workspace for phase 2 */
+int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const int* in_shape,
+                           const int* out_shape, const int* ksize, const int* stride, const int* padding,
+                           const int* dilation, int* n_out_dev, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* phase 2: out_coords (n_out,4), nbr_in (n_in,K), nbr_out (n_out,K) */
+int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int* in_shape,
+                          const int* out_shape, const int* ksize, const int* stride, const int* padding,
+                          const int* dilation, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* spconv-shaped export: pairs (2,K,n_in) int32 (-1 padded), pair_num (K); mirror=1 reads a SubM nbr_out */
+int ud_rulebook_pairs_workspace_bytes(int n_in, int K, size_t* bytes);
+int ud_rulebook_pairs(const int* nbr_in, int n_in, int K, int mirror, int* pairs, int* pair_num,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution.  Replaces spconv.pytorch.functional.indice_conv / indice_subm_conv
+ * (ConvAlgo.Native) behind spconv_backbone.py:21-48,70-92 and their backward.
+ *   forward: out[o,:] = bias + sum_k in[nbr[o][k],:] @ w[k]     w (K,cin,cout) f32, bias (cout)|NULL
+ *   dgrad  : the same call with in:=dout, nbr:=nbr_in, w:=W^T as (K,cout,cin) (SubM: nbr_out and the
+ *            taps reversed), cin/cout swapped
+ *   wgrad  : dw[k] += in[nbr[o][k],:]^T dout[o,:]                dw (K,cin,cout), caller zeroes it
+ * ------------------------------------------------------------------------------------------- */
+int ud_sparse_conv_forward(const float* in, const float* w, const float* bias, const int* nbr, int n_out,
+                           int K, int cin, int cout, float* out, void* stream);
+int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int n_out, int K, int cin,
+                         int cout, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /
+ * replace_feature passes of spconv_backbone.py:50-56,97-113,255.
+ * ------------------------------------------------------------------------------------------- */
+int ud_bn_stats(const float* x, int n, int C, double* sum, double* sqsum, void* stream);
+int ud_bn_finalize(const double* sum, const double* sqsum, int n, int C, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int ud_bn_eval_coeffs(const float* running_mean, const float* running_var, const float* gamma,
+                      const float* beta, float eps, int C, float* scale, float* shift, void* stream);
+int ud_bn_apply(const float* x, int n, int C, const float* scale, const float* shift, const float* residual,
+                int relu, float* y, void* stream);
+int ud_bn_backward(const float* dy, const float* y, const float* x, int n, int C, const float* mean,
+                   const float* invstd, const float* gamma, int relu, double* sum_g, double* sum_gx,
+                   float* dx, float* dres, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Scatter to BEV.  Replaces SparseConvTensor.dense() + view of
+ *   unidistill/layers/blocks_2d/det3d/map_to_bev/height_compression.py:19-21
+ * out (B, C*D, H, W) f32, channel = c*D + z.  ud_gather_from_bev is its backward.
+ * ------------------------------------------------------------------------------------------- */
+int ud_scatter_to_bev(const float* feat, const int* coords, int n, int batch_size, int C, int D, int H,
+                      int W, int zero_fill, float* out, void* stream);
+int ud_gather_from_bev(const float* dense, const int* coords, int n, int batch_size, int C, int D, int H,
+                       int W, float* feat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIDISTILL_B200_H */

@@ -1,0 +1,376 @@
+"""GPU parity of the LiDAR-branch kernels against the CPU oracle (all through the C ABI).
+
+Bit-exact for voxel indices / counts / kept points / rulebooks; fp32 features within 1e-3 relative
+(north_star tolerance) -- in practice ~1e-6 because accumulation is fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lidar as O
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3   # north_star: "within 1e-3 rel for fp32 features/losses"
+
+
+def _rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+def _random_sparse(rng, B, shape, n, C):
+    lin = rng.choice(B * shape[0] * shape[1] * shape[2], n, replace=False)
+    x = lin % shape[2]; lin //= shape[2]
+    y = lin % shape[1]; lin //= shape[1]
+    z = lin % shape[0]; b = lin // shape[0]
+    coords = np.stack([b, z, y, x], 1).astype(np.int32)
+    feat = rng.standard_normal((n, C)).astype(np.float32)
+    return coords, feat
+
+
+def _clustered_sparse(rng, B, shape, n, C):
+    """Surface-like occupancy (dense neighbourhoods), closer to LiDAR data than uniform noise."""
+    pts = []
+    per = n // B
+    for b in range(B):
+        yy = rng.integers(0, shape[1], per * 2)
+        xx = rng.integers(0, shape[2], per * 2)
+        zz = np.clip((shape[0] // 3 + 2 * np.sin(yy / 7.0) + rng.integers(0, 2, per * 2)).astype(np.int64), 0,
+                     shape[0] - 1)
+        pts.append(np.stack([np.full_like(yy, b), zz, yy, xx], 1))
+    coords = np.unique(np.concatenate(pts, 0), axis=0)
+    rng.shuffle(coords)
+    coords = coords[:n].astype(np.int32)
+    feat = rng.standard_normal((coords.shape[0], C)).astype(np.float32)
+    return coords, feat
+
+
+# ---------------------------------------------------------------------------------------------------
+def _check_voxelize(cuda, clouds, vs, rng_, grid, max_points, max_voxels):
+    from unidistill_b200.voxelize import hard_voxelize
+
+    v, c, n, m, counts = hard_voxelize([torch.from_numpy(p).to(cuda) for p in clouds], vs, rng_, grid,
+                                       max_points, max_voxels)
+    rv, rc, rn, rm = O.voxelize(clouds, vs, rng_, grid, max_points, max_voxels)
+    assert c.shape[0] == rc.shape[0], "voxel count %d != oracle %d" % (c.shape[0], rc.shape[0])
+    assert np.array_equal(c.cpu().numpy(), rc), "voxel coordinates / order differ"
+    assert np.array_equal(n.cpu().numpy(), rn), "points-per-voxel differ"
+    assert np.array_equal(v.cpu().numpy(), rv), "kept points differ"
+    assert np.array_equal(m.cpu().numpy(), rm), "fused mean differs from sequential fp32 mean"
+    assert sum(counts) == rc.shape[0]
+    return v, c, n, m
+
+
+def test_voxelize_known_answers(cuda, native_lib):
+    vs, rg, grid = [0.5, 0.5, 1.0], [0.0, 0.0, 0.0, 4.0, 4.0, 2.0], [8, 8, 2]
+    # bounds, first-come order, 11 points in one voxel
+    pts = np.array([[4.0, 1.0, 1.0, 0, 0], [1.0, 4.0, 1.0, 0, 0], [1.0, 1.0, 2.0, 0, 0], [-1e-6, 1.0, 1.0, 0, 0],
+                    [0.0, 0.0, 0.0, 0, 0], [3.999, 3.999, 1.999, 0, 0]], np.float32)
+    v, c, n, m = _check_voxelize(cuda, [pts], vs, rg, grid, 10, 100)
+    assert c.cpu().tolist() == [[0, 0, 0, 0], [0, 1, 7, 7]]
+    many = np.zeros((11, 5), np.float32)
+    many[:, :3] = [1.1, 1.1, 0.5]
+    many[:, 3] = np.arange(11)
+    v, c, n, m = _check_voxelize(cuda, [many], vs, rg, grid, 10, 100)
+    assert n.cpu().tolist() == [10] and v[0, :, 3].cpu().tolist() == list(range(10))
+
+
+def test_voxelize_cap_and_order(cuda, native_lib):
+    vs, rg, grid = [0.5, 0.5, 1.0], [0.0, 0.0, 0.0, 4.0, 4.0, 2.0], [8, 8, 2]
+    A, B, C = [0.1, 0.1, 0.1], [1.1, 0.1, 0.1], [2.1, 0.1, 0.1]
+    pts = np.array([A + [0, 0], B + [1, 0], C + [2, 0], A + [3, 0], C + [4, 0], B + [5, 0]], np.float32)
+    v, c, n, m = _check_voxelize(cuda, [pts, pts[::-1].copy()], vs, rg, grid, 10, 2)
+    assert c.cpu().tolist() == [[0, 0, 0, 0], [0, 0, 0, 2], [1, 0, 0, 2], [1, 0, 0, 4]]
+
+
+def test_voxelize_empty_and_all_rejected(cuda, native_lib):
+    vs, rg, grid = [0.5, 0.5, 1.0], [0.0, 0.0, 0.0, 4.0, 4.0, 2.0], [8, 8, 2]
+    from unidistill_b200.voxelize import hard_voxelize
+
+    out_of_range = np.full((7, 5), 100.0, np.float32)
+    v, c, n, m, counts = hard_voxelize([torch.from_numpy(out_of_range).to(cuda)], vs, rg, grid, 10, 50)
+    assert c.shape[0] == 0 and counts == [0]
+    empty = np.zeros((0, 5), np.float32)
+    some = np.array([[0.3, 0.3, 0.3, 1, 2]], np.float32)
+    _check_voxelize(cuda, [empty, some, empty], vs, rg, grid, 10, 50)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_voxelize_random_ragged_batch(cuda, native_lib, seed):
+    rng = np.random.default_rng(seed)
+    vs, rg, grid = [0.2, 0.2, 0.25], [-4.0, -4.0, -1.0, 4.0, 4.0, 1.0], [40, 40, 8]
+    clouds = []
+    for nn in (5000, 1, 777, 12000):
+        p = (rng.standard_normal((nn, 5)) * [2.5, 2.5, 0.7, 1, 1]).astype(np.float32)
+        p[rng.integers(0, nn, nn // 10)] = 0.0          # zero padding rows (quirk 1)
+        clouds.append(p)
+    _check_voxelize(cuda, clouds, vs, rg, grid, 10, 1500)     # the cap binds for the big clouds
+    _check_voxelize(cuda, clouds, vs, rg, grid, 3, 100000)
+
+
+def test_voxelize_full_size_sample(cuda, native_lib):
+    """BASELINE config sizes: 40k x 10 sweeps, 0.1 m grid, cap 120000 (binds)."""
+    from unidistill_b200 import synthetic as S
+
+    batch = S.lidar_batch(2, seed=3)
+    clouds = [batch["points"][b].numpy() for b in range(2)]
+    v, c, n, m = _check_voxelize(cuda, clouds, S.VOXEL_SIZE_128, S.PC_RANGE_128, S.GRID_SIZE_128, 10, 120000)
+    assert c.shape[0] > 150000
+    # size-independent properties: unique cells, counts within [1, 10], every kept point inside its cell
+    cc = c.cpu().numpy().astype(np.int64)
+    lin = ((cc[:, 0] * 40 + cc[:, 1]) * 1024 + cc[:, 2]) * 1024 + cc[:, 3]
+    assert np.unique(lin).size == lin.size
+    nn = n.cpu().numpy()
+    assert nn.min() >= 1 and nn.max() <= 10
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_subm_rulebook_bit_exact(cuda, native_lib):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(0)
+    for (B, shape, n) in [(2, [9, 20, 24], 1500), (1, [3, 5, 5], 1), (3, [41, 64, 64], 20000)]:
+        coords, _ = _clustered_sparse(rng, B, shape, n, 1)
+        rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+        pairs, pn = rb.spconv_pairs()
+        rp, rpn = O.rulebook_subm(coords, shape, 3)
+        assert np.array_equal(pn.cpu().numpy(), rpn)
+        assert np.array_equal(pairs.cpu().numpy(), rp), "pair lists differ (content or canonical order)"
+        # symmetry property of SubM tables: nbr[o][k] = i  <=>  nbr[i][K-1-k] = o
+        t = rb.nbr_out.cpu().numpy()
+        o_idx, k_idx = np.nonzero(t >= 0)
+        assert np.array_equal(t[t[o_idx, k_idx], 26 - k_idx], o_idx)
+
+
+@pytest.mark.parametrize("ksize,stride,pad", [(3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)])
+def test_strided_rulebook_bit_exact(cuda, native_lib, ksize, stride, pad):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(1)
+    B, shape, n = 2, [11, 30, 28], 4000
+    coords, _ = _clustered_sparse(rng, B, shape, n, 1)
+    rb = sparse.build_conv_rulebook(torch.from_numpy(coords).to(cuda), B, shape, ksize, stride, pad)
+    oc, rp, rpn, osh = O.rulebook_conv(coords, shape, ksize, stride, pad)
+    assert rb.out_shape == osh
+    assert np.array_equal(rb.out_coords.cpu().numpy(), oc), "output coordinates / order differ"
+    pairs, pn = rb.spconv_pairs()
+    assert np.array_equal(pn.cpu().numpy(), rpn)
+    assert np.array_equal(pairs.cpu().numpy(), rp)
+    # the two table forms describe the same pair set
+    t_out, t_in = rb.nbr_out.cpu().numpy(), rb.nbr_in.cpu().numpy()
+    o_idx, k_idx = np.nonzero(t_out >= 0)
+    assert np.array_equal(t_in[t_out[o_idx, k_idx], k_idx], o_idx)
+    assert (t_in >= 0).sum() == (t_out >= 0).sum() == rpn.sum()
+
+
+def test_rulebook_empty_input(cuda, native_lib):
+    from unidistill_b200 import sparse
+
+    coords = torch.zeros((0, 4), dtype=torch.int32, device=cuda)
+    rb = sparse.build_conv_rulebook(coords, 1, [8, 8, 8], 3, 2, 1)
+    assert rb.n_out == 0
+    rb = sparse.build_subm_rulebook(coords, 1, [8, 8, 8], 3)
+    assert rb.n_out == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+CHANNELS = [(5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (7, 9)]
+
+
+@pytest.mark.parametrize("cin,cout", CHANNELS)
+def test_subm_conv_forward_parity(cuda, native_lib, cin, cout):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(cin * 131 + cout)
+    B, shape, n = 2, [9, 24, 24], 2500
+    coords, feat = _clustered_sparse(rng, B, shape, n, cin)
+    n = coords.shape[0]
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    bias = rng.standard_normal((cout,)).astype(np.float32)
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    out = sparse.sparse_conv(torch.from_numpy(feat).to(cuda), torch.from_numpy(w).to(cuda),
+                             torch.from_numpy(bias).to(cuda), rb)
+    rp, rpn = O.rulebook_subm(coords, shape, 3)
+    ref = O.sparse_conv_c(feat, w, bias, rp, rpn, n)
+    err = _rel_err(out.cpu().numpy(), ref)
+    assert err < 1e-5, "fp32 SIMT path should agree to ~1e-6, got %g" % err
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(16, 32, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
+                                                       (128, 128, (3, 1, 1), (2, 1, 1), 0)])
+def test_strided_conv_forward_parity(cuda, native_lib, cin, cout, ksize, stride, pad):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(5)
+    B, shape, n = 2, [11, 26, 22], 3000
+    coords, feat = _clustered_sparse(rng, B, shape, n, cin)
+    ks = O._t3(ksize)
+    w = (rng.standard_normal((cout, ks[0], ks[1], ks[2], cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    rb = sparse.build_conv_rulebook(torch.from_numpy(coords).to(cuda), B, shape, ksize, stride, pad)
+    out = sparse.sparse_conv(torch.from_numpy(feat).to(cuda), torch.from_numpy(w).to(cuda), None, rb)
+    oc, rp, rpn, osh = O.rulebook_conv(coords, shape, ksize, stride, pad)
+    ref = O.sparse_conv_c(feat, w, None, rp, rpn, oc.shape[0])
+    assert _rel_err(out.cpu().numpy(), ref) < 1e-5
+
+
+def _torch_ref_conv(feat, w, bias, pairs, pn, n_out):
+    """Differentiable torch-CPU restatement (gather-mm-index_add) for gradient parity."""
+    cout, cin = w.shape[0], w.shape[-1]
+    w_k = w.reshape(cout, -1, cin).permute(1, 2, 0)
+    out = torch.zeros((n_out, cout), dtype=torch.float32)
+    if bias is not None:
+        out = out + bias
+    p = torch.from_numpy(np.asarray(pairs)).long()
+    for k in range(w_k.shape[0]):
+        m = int(pn[k])
+        if m:
+            out = out.index_add(0, p[1, k, :m], feat.index_select(0, p[0, k, :m]) @ w_k[k])
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,strided", [(16, 16, False), (32, 64, True), (64, 64, False), (128, 128, False),
+                                              (5, 16, False), (64, 128, True)])
+def test_conv_backward_parity(cuda, native_lib, cin, cout, strided):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(cin + cout)
+    B, shape, n = 2, [9, 20, 20], 1800
+    coords, feat = _clustered_sparse(rng, B, shape, n, cin)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    bias = None if strided else rng.standard_normal((cout,)).astype(np.float32)
+    if strided:
+        rb = sparse.build_conv_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3, 2, 1)
+        oc, rp, rpn, _ = O.rulebook_conv(coords, shape, 3, 2, 1)
+        n_out = oc.shape[0]
+    else:
+        rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+        rp, rpn = O.rulebook_subm(coords, shape, 3)
+        n_out = coords.shape[0]
+    gout = rng.standard_normal((n_out, cout)).astype(np.float32)
+
+    f_g = torch.from_numpy(feat).to(cuda).requires_grad_(True)
+    w_g = torch.from_numpy(w).to(cuda).requires_grad_(True)
+    b_g = torch.from_numpy(bias).to(cuda).requires_grad_(True) if bias is not None else None
+    out = sparse.sparse_conv(f_g, w_g, b_g, rb)
+    out.backward(torch.from_numpy(gout).to(cuda))
+
+    f_c = torch.from_numpy(feat).requires_grad_(True)
+    w_c = torch.from_numpy(w).requires_grad_(True)
+    b_c = torch.from_numpy(bias).requires_grad_(True) if bias is not None else None
+    ref = _torch_ref_conv(f_c, w_c, b_c, rp, rpn, n_out)
+    ref.backward(torch.from_numpy(gout))
+
+    assert _rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert _rel_err(f_g.grad.cpu().numpy(), f_c.grad.numpy()) < 1e-4, "dgrad"
+    assert _rel_err(w_g.grad.cpu().numpy(), w_c.grad.numpy()) < 1e-4, "wgrad"
+    if bias is not None:
+        assert _rel_err(b_g.grad.cpu().numpy(), b_c.grad.numpy()) < 1e-4, "bias grad"
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,relu,with_res", [(16, True, False), (32, True, True), (64, False, False),
+                                             (128, True, True)])
+def test_fused_batchnorm_matches_torch(cuda, native_lib, C, relu, with_res):
+    from unidistill_b200.sparse import batch_norm_act
+
+    torch.manual_seed(C)
+    n = 5000
+    x = (torch.randn(n, C) * 3 + 1.5)
+    res = torch.randn(n, C) if with_res else None
+    gout = torch.randn(n, C)
+    for training in (True, False):
+        bn_ref = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01)
+        with torch.no_grad():
+            bn_ref.weight.uniform_(0.5, 1.5)
+            bn_ref.bias.uniform_(-0.5, 0.5)
+            bn_ref.running_mean.normal_()
+            bn_ref.running_var.uniform_(0.5, 2.0)
+        bn_gpu = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01)
+        bn_gpu.load_state_dict(bn_ref.state_dict())
+        bn_gpu.to(cuda)
+        bn_ref.train(training)
+        bn_gpu.train(training)
+        xr = x.clone().requires_grad_(True)
+        rr = res.clone().requires_grad_(True) if with_res else None
+        y_ref = bn_ref(xr)
+        if with_res:
+            y_ref = y_ref + rr
+        if relu:
+            y_ref = torch.relu(y_ref)
+        xg = x.to(cuda).requires_grad_(True)
+        rg = res.to(cuda).requires_grad_(True) if with_res else None
+        if not training:
+            for p in bn_gpu.parameters():
+                p.requires_grad_(False)   # frozen-teacher configuration takes the fused eval path
+        y = batch_norm_act(xg, bn_gpu, relu=relu, residual=rg)
+        assert _rel_err(y.detach().cpu().numpy(), y_ref.detach().numpy()) < 1e-5
+        y_ref.backward(gout)
+        y.backward(gout.to(cuda))
+        assert _rel_err(xg.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
+        if with_res:
+            assert _rel_err(rg.grad.cpu().numpy(), rr.grad.numpy()) < 1e-5
+        if training:
+            assert _rel_err(bn_gpu.weight.grad.cpu().numpy(), bn_ref.weight.grad.numpy()) < 1e-4
+            assert _rel_err(bn_gpu.bias.grad.cpu().numpy(), bn_ref.bias.grad.numpy()) < 1e-4
+            assert _rel_err(bn_gpu.running_mean.cpu().numpy(), bn_ref.running_mean.numpy()) < 1e-5
+            assert _rel_err(bn_gpu.running_var.cpu().numpy(), bn_ref.running_var.numpy()) < 1e-5
+            assert int(bn_gpu.num_batches_tracked.item()) == int(bn_ref.num_batches_tracked.item())
+
+
+def test_scatter_to_bev_and_backward(cuda, native_lib):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(9)
+    B, shape, n, C = 3, [2, 16, 20], 700, 128
+    coords, feat = _random_sparse(rng, B, shape, n, C)
+    order = np.lexsort((coords[:, 3], coords[:, 2], coords[:, 1], coords[:, 0]))
+    coords, feat = coords[order], feat[order]
+    f = torch.from_numpy(feat).to(cuda).requires_grad_(True)
+    dense = sparse.scatter_to_dense(f, torch.from_numpy(coords).to(cuda), B, shape)
+    ref = O.dense(feat, coords, B, shape)
+    assert np.array_equal(dense.detach().cpu().numpy(), ref), "scatter is a pure copy: must be bit exact"
+    hc = dense.view(B, C * shape[0], shape[1], shape[2])
+    assert np.array_equal(hc.detach().cpu().numpy(), O.height_compression(feat, coords, B, shape))
+    g = rng.standard_normal(ref.shape).astype(np.float32)
+    dense.backward(torch.from_numpy(g).to(cuda))
+    c = coords.astype(np.int64)
+    ref_grad = g[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]]
+    assert np.array_equal(f.grad.cpu().numpy(), ref_grad)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("training", [True, False])
+def test_backbone_forward_parity(cuda, native_lib, training):
+    """VoxelResBackBone8x + HeightCompression on the GPU vs the CPU restatement, same weights."""
+    from unidistill.layers.blocks_2d.det3d import HeightCompression
+    from unidistill.layers.blocks_3d.det3d import VoxelResBackBone8x
+
+    torch.manual_seed(0)
+    rng = np.random.default_rng(11)
+    grid = np.array([64, 64, 16])
+    sparse_shape = [17, 64, 64]
+    net = VoxelResBackBone8x(5, grid)
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.weight.uniform_(0.6, 1.4)
+                mod.bias.uniform_(-0.3, 0.3)
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    coords, feat = _clustered_sparse(rng, 2, sparse_shape, 6000, 5)
+    ref_f, ref_c, ref_shape = O.backbone_forward(sd, feat, coords, 2, sparse_shape, training=training)
+
+    net = net.to(cuda).train(training)
+    with torch.set_grad_enabled(training):   # eval + no_grad == the frozen-teacher configuration
+        out, stride, scales = net(torch.from_numpy(feat).to(cuda), torch.from_numpy(coords).to(cuda), 2)
+    assert stride == 8 and list(out.spatial_shape) == ref_shape
+    assert np.array_equal(out.indices.cpu().numpy(), ref_c)
+    err = _rel_err(out.features.detach().cpu().numpy(), ref_f.numpy())
+    assert err < REL_TOL, "backbone features rel err %g" % err
+    bev, _ = HeightCompression(256)(out, stride)
+    ref_bev = O.height_compression(ref_f.numpy(), ref_c, 2, ref_shape)
+    assert bev.shape == ref_bev.shape
+    assert _rel_err(bev.detach().cpu().numpy(), ref_bev) < REL_TOL
