@@ -244,7 +244,7 @@ int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatia
                      const int* dilation, int* nbr_out, void* workspace, size_t workspace_bytes,
                      void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!coords || !nbr_out || n < 0) return UD_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && (!coords || !nbr_out))) return UD_ERR_INVALID_ARG;
     int ones[3] = {1, 1, 1}, zeros[3] = {0, 0, 0};
     UdConvGeom g = ud_make_geom(batch_size, spatial_shape, spatial_shape, ksize, ones, zeros, dilation);
     if ((g.kD & 1) == 0 || (g.kH & 1) == 0 || (g.kW & 1) == 0) return UD_ERR_UNSUPPORTED;
@@ -314,7 +314,7 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
                            const int* dilation, int* n_out_dev, void* workspace, size_t workspace_bytes,
                            void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!coords || !n_out_dev || n_in < 0) return UD_ERR_INVALID_ARG;
+    if (!n_out_dev || n_in < 0 || (n_in > 0 && !coords)) return UD_ERR_INVALID_ARG;
     UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation);
     int rc = ud_geom_check(g, false);
     if (rc != UD_OK) return rc;
@@ -345,7 +345,9 @@ int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int
                           const int* dilation, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
                           void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!coords || !out_coords || !nbr_in || !nbr_out || n_in < 0 || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (n_in < 0 || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (n_in > 0 && (!coords || !nbr_in)) return UD_ERR_INVALID_ARG;
+    if (n_out > 0 && (!out_coords || !nbr_out)) return UD_ERR_INVALID_ARG;
     UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation);
     int rc = ud_geom_check(g, false);
     if (rc != UD_OK) return rc;
@@ -385,7 +387,7 @@ int ud_rulebook_pairs_workspace_bytes(int n_in, int K, size_t* bytes) {
 int ud_rulebook_pairs(const int* nbr_in, int n_in, int K, int mirror, int* pairs, int* pair_num,
                       void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!nbr_in || !pairs || !pair_num || n_in < 0 || K < 1) return UD_ERR_INVALID_ARG;
+    if (!pair_num || n_in < 0 || K < 1 || (n_in > 0 && (!nbr_in || !pairs))) return UD_ERR_INVALID_ARG;
     if ((long long)n_in * K + 1 > 0x7FFFFFFFll) return UD_ERR_UNSUPPORTED;
     UD_CUDA_TRY(cudaMemsetAsync(pair_num, 0, sizeof(int) * K, stream));
     if (n_in == 0) return UD_OK;

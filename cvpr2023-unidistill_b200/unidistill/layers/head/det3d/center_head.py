@@ -1,0 +1,162 @@
+"""CenterHead / SepHead -- CenterPoint detection head (reference layers/head/det3d/center_head.py:15-171,311-375).
+
+Dense 3x3 convolutions stay on cuDNN; module tree and parameter names are the reference's
+(`shared_conv.{0,1}`, `tasks.<t>.<head>.{0,1,3}`) so checkpoints load by key.
+"""
+import copy
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from unidistill.layers.losses import det3d as loss_utils
+from unidistill.utils.det3d_utils.initialize_utils import kaiming_init
+
+
+class Sequential(nn.Sequential):
+    """nn.Sequential with the reference's `add(module, name=None)` convenience (center_head.py:266-308)."""
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+            if name in self._modules:
+                raise KeyError("name exists")
+        self.add_module(name, module)
+
+
+class SepHead(nn.Module):
+    """One small conv tower per regression / classification target of a task."""
+
+    def __init__(self, in_channels, heads, head_conv=64, name="", final_kernel=1, bn=False, init_bias=-2.19,
+                 directional_classifier=False, **kwargs):
+        super().__init__(**kwargs)
+        assert directional_classifier is False, "directional classifier is not supported (as in the reference)"
+        self.heads = heads
+        pad = final_kernel // 2
+        for head, (classes, num_conv) in self.heads.items():
+            tower = Sequential()
+            for _ in range(num_conv - 1):
+                tower.add(nn.Conv2d(in_channels, head_conv, kernel_size=final_kernel, stride=1, padding=pad,
+                                    bias=True))
+                if bn:
+                    tower.add(nn.BatchNorm2d(head_conv))
+                tower.add(nn.ReLU())
+            tower.add(nn.Conv2d(head_conv, classes, kernel_size=final_kernel, stride=1, padding=pad, bias=True))
+            if "hm" in head:
+                tower[-1].bias.data.fill_(init_bias)
+            else:
+                for m in tower.modules():
+                    if isinstance(m, nn.Conv2d):
+                        kaiming_init(m)
+            self.__setattr__(head, tower)
+
+    def forward(self, x):
+        return {head: self.__getattr__(head)(x) for head in self.heads}
+
+
+class CenterHead(nn.Module):
+    def __init__(self, dataset_name, tasks, target_assigner, proposal_layer, input_channels, grid_size,
+                 point_cloud_range, code_weights, loc_weight, share_conv_channel, common_heads,
+                 upsample_for_pedestrian=False, predict_boxes_when_training=False, mode="3d", init_bias=-2.19,
+                 distill=False):
+        super().__init__()
+        self.in_channels = input_channels
+        self.grid_size = grid_size
+        self.point_cloud_range = point_cloud_range
+        self.predict_boxes_when_training = predict_boxes_when_training
+        self.num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.code_weights = code_weights
+        self.weight = loc_weight
+        self.dataset = dataset_name
+        self.box_n_dim = 9 if self.dataset == "nuscenes" else 7
+        self.encode_background_as_zeros = True
+        self.use_sigmoid_score = True
+        self.no_log = False
+        self.use_direction_classifier = False
+        self.bev_only = mode == "bev"
+        self.distill = distill
+        self.shared_conv = nn.Sequential(
+            nn.Conv2d(self.in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
+            nn.BatchNorm2d(share_conv_channel),
+            nn.ReLU(inplace=True),
+        )
+        self.upsample_for_pedestrian = upsample_for_pedestrian
+        if upsample_for_pedestrian:
+            self.upsample_conv = nn.Sequential(
+                nn.ConvTranspose2d(share_conv_channel, share_conv_channel, 2, stride=2, bias=False),
+                nn.BatchNorm2d(share_conv_channel),
+                nn.ReLU(),
+            )
+        self.common_heads = common_heads
+        self.init_bias = init_bias
+        self.tasks = nn.ModuleList()
+        for num_cls in self.num_classes:
+            heads = copy.deepcopy(dict(self.common_heads))
+            heads.update(dict(hm=(num_cls, 2)))
+            self.tasks.append(SepHead(share_conv_channel, OrderedDict(heads), bn=True, init_bias=init_bias,
+                                      final_kernel=3, directional_classifier=False))
+        self.target_assigner = target_assigner
+        self.proposal_layer = proposal_layer
+        self.build_losses()
+
+    def train(self, mode: bool = True):
+        super().train(mode=mode)
+        self.proposal_layer.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def assign_targets(self, gt_boxes):
+        return self.target_assigner.assign_targets(gt_boxes)
+
+    def forward(self, spatial_features_2d, gt_boxes=None):
+        ret = {}
+        x = self.shared_conv(spatial_features_2d)
+        if self.upsample_for_pedestrian:
+            x = self.upsample_conv(x)
+        ret["multi_head_features"] = [task(x) for task in self.tasks]
+        if self.training or self.distill:
+            ret.update(self.assign_targets(gt_boxes))
+            return ret
+        return self.proposal_layer.generate_predicted_boxes(ret, {})
+
+    def build_losses(self):
+        self.add_module("crit", loss_utils.CenterNetFocalLoss())
+        self.add_module("crit_reg", loss_utils.CenterNetRegLoss())
+
+    def _sigmoid(self, x):
+        return torch.clamp(x.sigmoid(), min=1e-4, max=1 - 1e-4)
+
+    def _box_codes(self, pred_dict, with_iou=False):
+        names = ["reg", "height", "dim", "rot"] + (["vel"] if self.dataset == "nuscenes" else [])
+        if with_iou:
+            names.append("iou")
+        return torch.cat([pred_dict[n] for n in names], dim=1).contiguous()
+
+    def get_loss(self, forward_ret_dict):
+        """hm focal loss + weighted L1 box loss per task (reference center_head.py:171-263).
+        tb_dict values are 0-dim tensors (no host sync); call float() on them to log."""
+        tb_dict = {}
+        losses = []
+        forward_ret_dict["pred_box_encoding"] = {}
+        code_w = None
+        for task_id, pred_dict in enumerate(forward_ret_dict["multi_head_features"]):
+            pred_dict["hm"] = self._sigmoid(pred_dict["hm"])
+            hm_loss = self.crit(pred_dict["hm"], forward_ret_dict["heatmap"][task_id])
+            target = forward_ret_dict["box_encoding"][task_id]
+            pred = self._box_codes(pred_dict)
+            forward_ret_dict["pred_box_encoding"][task_id] = pred
+            box_loss = self.crit_reg(pred, forward_ret_dict["mask"][task_id], forward_ret_dict["ind"][task_id],
+                                     target)
+            if code_w is None:
+                code_w = box_loss.new_tensor(self.code_weights)
+            loc_loss = (box_loss * code_w).sum()
+            loss = hm_loss + self.weight * loc_loss
+            key = "task_%d/" % task_id
+            tb_dict.update({key + "loss": loss.detach(), key + "hm_loss": hm_loss.detach(),
+                            key + "loc_loss": loc_loss.detach(),
+                            key + "num_positive": forward_ret_dict["mask"][task_id].float().sum()})
+            losses.append(loss)
+        return sum(losses), tb_dict

@@ -1,0 +1,3 @@
+from unidistill._overlay import extend as _extend
+
+_extend(__path__, __name__)

@@ -1,0 +1,267 @@
+"""BEVFusion model assembly for the benchmark / tests.
+
+Mirrors the classes the reference defines inside its experiment scripts
+(exps/multisensor_fusion/nuscenes/BEVFusion/BEVFusion_nuscenes_base_exp.py:40-260 and
+BEVFusion_nuscenes_centerhead_fusion_exp.py:44-175): same sub-module names, so a state_dict of the
+reference's BEVFusionCenterHead loads by key.  The reference scripts themselves can run unchanged on top of
+the `unidistill` mirror; this module exists because those scripts cannot be shipped
+here and the bench needs the same model without pytorch-lightning / mmcv.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from unidistill.data.det3d.preprocess.voxelization import Voxelization
+from unidistill.layers.blocks_2d.det3d import BaseBEVBackbone, HeightCompression
+from unidistill.layers.blocks_3d.det3d import MeanVFE, VoxelResBackBone8x
+from unidistill.layers.blocks_3d.mmdet3d.lss_fpn import LSSFPN
+from unidistill.layers.head.det3d import CenterHeadIouAware, FCOSAssigner, IouAwareGenProposals
+from unidistill.layers.losses.det3d import CenterNetRegLoss, FocalLoss
+from unidistill.models.multisensor_fusion import BaseEncoder, BaseMultiSensorFusion
+
+from . import synthetic as S
+
+
+class AttrDict(dict):
+    """Minimal stand-in for mmcv.Config: nested dicts with attribute access."""
+
+    def __init__(self, d=None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = self._wrap(v)
+
+    @classmethod
+    def _wrap(cls, v):
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            return cls(v)
+        if isinstance(v, list):
+            return [cls._wrap(x) for x in v]
+        return v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = self._wrap(v)
+
+
+CLASS_NAMES = S.CLASS_NAMES
+DENSE_TASKS = [
+    dict(num_class=1, class_names=["car"]),
+    dict(num_class=2, class_names=["truck", "construction_vehicle"]),
+    dict(num_class=2, class_names=["bus", "trailer"]),
+    dict(num_class=1, class_names=["barrier"]),
+    dict(num_class=2, class_names=["motorcycle", "bicycle"]),
+    dict(num_class=2, class_names=["pedestrian", "traffic_cone"]),
+]
+
+
+def make_model_cfg(bev=128, lidar=True, camera=True, img_depth=50):
+    """Model config with the reference's structure (_base_/base_nuscenes_cfg.py:105-283 +
+    ..._centerhead_fusion_exp.py:24-41) for the 128^2 benchmark grid or the 180^2 reference default."""
+    if bev == 128:
+        pc_range, voxel, grid = S.PC_RANGE_128, S.VOXEL_SIZE_128, S.GRID_SIZE_128
+    elif bev == 180:
+        pc_range, voxel, grid = S.PC_RANGE_180, S.VOXEL_SIZE_180, S.GRID_SIZE_180
+    else:
+        raise ValueError("bev must be 128 or 180")
+    osf = 8
+    res_ch = {18: [64, 128, 256, 512], 34: [64, 128, 256, 512], 50: [256, 512, 1024, 2048]}[img_depth]
+    cfg = dict(
+        class_names=CLASS_NAMES,
+        lidar_encoder=dict(point_cloud_range=pc_range, voxel_size=voxel, grid_size=grid, max_num_points=10,
+                           max_voxels=(120000, 160000), src_num_point_features=5, use_num_point_features=5,
+                           map_to_bev_num_features=256) if lidar else None,
+        camera_encoder=dict(
+            x_bound=[pc_range[0], pc_range[3], voxel[0] * osf], y_bound=[pc_range[1], pc_range[4], voxel[1] * osf],
+            z_bound=[pc_range[2], pc_range[5], pc_range[5] - pc_range[2]], d_bound=[2.0, 58.0, 0.5],
+            final_dim=(256, 704), output_channels=256, downsample_factor=16,
+            img_backbone_conf=dict(type="ResNet", depth=img_depth, frozen_stages=0, out_indices=[0, 1, 2, 3],
+                                   norm_eval=False, init_cfg=None),
+            img_neck_conf=dict(type="SECONDFPN", in_channels=res_ch, upsample_strides=[0.25, 0.5, 1, 2],
+                               out_channels=[128, 128, 128, 128]),
+            depth_net_conf=dict(in_channels=512, mid_channels=512)) if camera else None,
+        bev_encoder=dict(backbone2d_layer_nums=[5, 5], backbone2d_layer_strides=[1, 2],
+                         backbone2d_num_filters=[128, 256], backbone2d_upsample_strides=[1, 2],
+                         backbone2d_num_upsample_filters=[256, 256], num_bev_features=256,
+                         backbone2d_use_scconv=False),
+        det_head=dict(
+            class_name=CLASS_NAMES,
+            target_assigner=dict(
+                densehead_out_size_factor=osf, densehead_tasks=DENSE_TASKS, target_assigner_dense_reg=1,
+                target_assigner_gaussian_overlap=0.1, target_assigner_max_objs=2500, target_assigner_min_radius=2,
+                target_assigner_mapping={n: i + 1 for i, n in enumerate(CLASS_NAMES)}, grid_size=grid,
+                pc_range=pc_range[0:2], voxel_size=voxel[0:2], target_assigner_topk=9,
+                target_assigner_no_log=False, with_velocity=True),
+            proposal_layer=dict(
+                densehead_dataset_name="nuscenes", densehead_tasks=DENSE_TASKS,
+                proposal_post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+                proposal_score_threshold=0.1, proposal_pc_range=pc_range[0:2], densehead_out_size_factor=osf,
+                proposal_voxel_size=voxel[0:2], no_log=False, proposal_iou_aware_list=[0.65] * 10,
+                nms_iou_threshold_train=0.8, nms_pre_max_size_train=1500, nms_post_max_size_train=80,
+                nms_iou_threshold_test=0.1, nms_pre_max_size_test=1500, nms_post_max_size_test=100),
+            dense_head=dict(
+                densehead_dataset_name="nuscenes", densehead_tasks=DENSE_TASKS, densehead_out_size_factor=osf,
+                input_channels=512, grid_size=grid, point_cloud_range=pc_range,
+                densehead_loss_code_weights=[1.0] * 8 + [0.2, 0.2], densehead_loss_loc_weight=0.25,
+                densehead_loss_iou_weight=5.0, densehead_share_conv_channel=64,
+                densehead_common_heads={"iou": [1, 2], "reg": [2, 2], "height": [1, 2], "dim": [3, 2],
+                                        "rot": [2, 2], "vel": [2, 2]},
+                densehead_upsample_for_pedestrian=False, densehead_mode="3d", densehead_init_bias=-2.19),
+            target_assigner_alpha=0.25, target_assigner_gamma=2),
+    )
+    cfg["geometry"] = dict(pc_range=pc_range, voxel_size=voxel, grid_size=grid, out_size_factor=osf)
+    return AttrDict(copy.deepcopy(cfg))
+
+
+class LidarEncoder(BaseEncoder):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        self.cfg = cfg
+        self.voxelizer = Voxelization(voxel_size=cfg.voxel_size, point_cloud_range=cfg.point_cloud_range,
+                                      max_num_points=cfg.max_num_points, max_voxels=tuple(cfg.max_voxels)
+                                      if isinstance(cfg.max_voxels, (list, tuple)) else cfg.max_voxels,
+                                      num_point_features=cfg.src_num_point_features, device=torch.device("cuda"))
+        self.vfe = MeanVFE(num_point_features=cfg.use_num_point_features)
+        self.backbone_3d = VoxelResBackBone8x(input_channels=self.vfe.get_output_feature_dim(),
+                                              grid_size=np.array(cfg.grid_size), last_pad=0)
+        self.map_to_bev = HeightCompression(num_bev_features=cfg.map_to_bev_num_features)
+
+    def forward(self, lidar_points):
+        voxels, coords, num = self.voxelizer(lidar_points)
+        feats = self.vfe(voxels, num)
+        sp, stride, _ = self.backbone_3d(feats, coords, len(lidar_points))
+        bev, _ = self.map_to_bev(sp, stride)
+        return bev
+
+
+class CameraEncoder(BaseEncoder):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        self.backbone = LSSFPN(**cfg)
+
+    def forward(self, imgs, mats_dict, is_return_depth=False):
+        # NB the reference passes is_return_depth positionally into the `timestamps` slot (quirk 12)
+        return self.backbone(imgs, mats_dict, is_return_depth)
+
+
+class FusionEncoder(nn.Module):
+    def __init__(self, use_elementwise=True, input_channel=512, output_channel=256, reduction=2):
+        super().__init__()
+        self.use_elementwise = use_elementwise
+        if not use_elementwise:
+            self.att = nn.Sequential(nn.AdaptiveAvgPool2d(1),
+                                     nn.Conv2d(input_channel, input_channel, kernel_size=1, stride=1),
+                                     nn.Sigmoid())
+            self.reduce_conv = nn.Sequential(nn.Conv2d(input_channel, output_channel, 3, padding=1, bias=False),
+                                             nn.BatchNorm2d(output_channel), nn.ReLU(True))
+
+    def forward(self, x1, x2):
+        assert x1.shape == x2.shape, f"shape: {x1.shape} != {x2.shape}"
+        if self.use_elementwise:
+            return x1 + x2
+        x = torch.cat((x1, x2), dim=1)
+        return self.reduce_conv(x * self.att(x))
+
+
+class BevEncoder(nn.Module):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        self.bev_encoder_cfg = cfg
+        self.backbone_2d = BaseBEVBackbone(
+            layer_nums=cfg.backbone2d_layer_nums, layer_strides=cfg.backbone2d_layer_strides,
+            num_filters=cfg.backbone2d_num_filters, upsample_strides=cfg.backbone2d_upsample_strides,
+            num_upsample_filters=cfg.backbone2d_num_upsample_filters, input_channels=cfg.num_bev_features,
+            use_scconv=cfg.get("backbone2d_use_scconv", False),
+            upsample_output=cfg.get("backbone2d_upsample_output", False))
+
+    def forward(self, x):
+        return self.backbone_2d(x)
+
+
+class DetHead(nn.Module):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        self.det_head_cfg = cfg
+        t, p, h = cfg.target_assigner, cfg.proposal_layer, cfg.dense_head
+        assigner = FCOSAssigner(
+            out_size_factor=t.densehead_out_size_factor, tasks=t.densehead_tasks,
+            dense_reg=t.target_assigner_dense_reg, gaussian_overlap=t.target_assigner_gaussian_overlap,
+            max_objs=t.target_assigner_max_objs, min_radius=t.target_assigner_min_radius,
+            mapping=t.target_assigner_mapping, grid_size=t.grid_size, pc_range=t.pc_range,
+            voxel_size=t.voxel_size, assign_topk=t.target_assigner_topk, no_log=t.target_assigner_no_log,
+            with_velocity=t.with_velocity)
+        proposals = IouAwareGenProposals(
+            dataset_name=p.densehead_dataset_name, class_names=[x["class_names"] for x in p.densehead_tasks],
+            post_center_limit_range=p.proposal_post_center_limit_range, score_threshold=p.proposal_score_threshold,
+            pc_range=p.proposal_pc_range, out_size_factor=p.densehead_out_size_factor,
+            voxel_size=p.proposal_voxel_size, no_log=p.no_log, iou_aware_list=p.proposal_iou_aware_list,
+            nms_iou_threshold_train=p.nms_iou_threshold_train, nms_pre_max_size_train=p.nms_pre_max_size_train,
+            nms_post_max_size_train=p.nms_post_max_size_train, nms_iou_threshold_test=p.nms_iou_threshold_test,
+            nms_pre_max_size_test=p.nms_pre_max_size_test, nms_post_max_size_test=p.nms_post_max_size_test)
+        self.dense_head = CenterHeadIouAware(
+            dataset_name=h.densehead_dataset_name, tasks=h.densehead_tasks, target_assigner=assigner,
+            proposal_layer=proposals, out_size_factor=h.densehead_out_size_factor, input_channels=h.input_channels,
+            grid_size=h.grid_size, point_cloud_range=h.point_cloud_range,
+            code_weights=h.densehead_loss_code_weights, loc_weight=h.densehead_loss_loc_weight,
+            iou_weight=h.densehead_loss_iou_weight, share_conv_channel=h.densehead_share_conv_channel,
+            common_heads=h.densehead_common_heads, upsample_for_pedestrian=h.densehead_upsample_for_pedestrian,
+            mode=h.densehead_mode, init_bias=h.densehead_init_bias, predict_boxes_when_training=False)
+        self.dense_head.add_module("crit", FocalLoss(cfg.target_assigner_alpha, cfg.target_assigner_gamma))
+        self.dense_head.add_module("crit_reg", CenterNetRegLoss())
+        self.dense_head.add_module("crit_iou_aware", CenterNetRegLoss())
+
+    def forward(self, x, gt_boxes):
+        ret = self.dense_head(x, gt_boxes)
+        if self.training:
+            for _, enc in ret["box_encoding"].items():
+                enc[torch.isinf(enc)] = 0       # log(0) of padded boxes (quirk 10)
+        return ret
+
+
+class BEVFusionCenterHead(BaseMultiSensorFusion):
+    """forward(lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False) with the reference's return
+    conventions (..._centerhead_fusion_exp.py:134-171)."""
+
+    def __init__(self, model_cfg):
+        super().__init__()
+        self.cfg = model_cfg
+        self.class_names = model_cfg.class_names
+        self.num_class = len(self.class_names)
+        self.lidar_encoder = LidarEncoder(model_cfg.lidar_encoder) if model_cfg.get("lidar_encoder") else None
+        self.camera_encoder = CameraEncoder(model_cfg.camera_encoder) if model_cfg.get("camera_encoder") else None
+        both = self.with_lidar_encoder and self.with_camera_encoder
+        self.fusion_encoder = FusionEncoder(use_elementwise=False) if both else None
+        self.bev_encoder = BevEncoder(model_cfg.bev_encoder)
+        self.det_head = DetHead(model_cfg.det_head)
+
+    def extract_bev(self, lidar_points, cameras_imgs, metas):
+        out = None
+        if self.with_lidar_encoder:
+            lidar_out = self.lidar_encoder(lidar_points)
+            out = lidar_out
+        if self.with_camera_encoder:
+            camera_out = self.camera_encoder(cameras_imgs, metas)
+            out = camera_out
+        if self.with_fusion_encoder:
+            out = self.fusion_encoder(lidar_out, camera_out)
+        return out
+
+    def forward(self, lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False, **kwargs):
+        model_output = self.extract_bev(lidar_points, cameras_imgs, metas)
+        x = self.bev_encoder(model_output)
+        ret = self.det_head(x[0], gt_boxes)
+        if return_feature:
+            return model_output, x[0], ret["multi_head_features"]
+        if self.training:
+            for _, enc in ret["box_encoding"].items():
+                enc[torch.isinf(enc)] = 0
+            loss_rpn, tb_dict = self.det_head.dense_head.get_loss(ret)
+            tb_dict.update({"loss_rpn": loss_rpn.detach()})
+            return {"loss": loss_rpn}, tb_dict, model_output, x[0], ret["multi_head_features"], {}
+        return ret

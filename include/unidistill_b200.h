@@ -118,6 +118,44 @@ int ud_scatter_to_bev(const float* feat, const int* coords, int n, int batch_siz
 int ud_gather_from_bev(const float* dense, const int* coords, int n, int batch_size, int C, int D, int H,
                        int W, float* feat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Camera branch: frustum -> BEV pooling.  Replaces the prebuilt voxel_pooling_ext extension
+ * (voxel_pooling_forward_wrapper -> voxel_pooling_forward_kernel_launcher, binary only) called from
+ *   unidistill/layers/blocks_3d/mmdet3d/lss_fpn.py:48-59 (forward) and restates :64-79 (backward).
+ * Argument order of ud_voxel_pooling_forward == the reference launcher's
+ *   (batch_size, num_points, num_channels, num_voxel_x, num_voxel_y, num_voxel_z, geom_xyz,
+ *    input_features, output_features, pos_memo, stream) + workspace.
+ * geom_xyz (B,N,3) int32; input_features (B,N,C) f32; output_features (B,ny,nx,C) f32 and pos_memo
+ * (B,N,3) int32 are fully written (no pre-zero / pre-fill needed); pos_memo may be NULL.
+ * Deterministic (sorted segmented reduction, no atomics).
+ * ------------------------------------------------------------------------------------------- */
+int ud_voxel_pooling_workspace_bytes(int batch_size, int num_points, int num_channels, int num_voxel_x,
+                                     int num_voxel_y, size_t* bytes);
+int ud_voxel_pooling_forward(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
+                             int num_voxel_z, const int* geom_xyz, const float* input_features,
+                             float* output_features, int* pos_memo, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* grad_output (B,C,ny,nx) contiguous -> grad_input (B,N,C), fully written */
+int ud_voxel_pooling_backward(int batch_size, int num_points, int num_channels, int num_voxel_x, int num_voxel_y,
+                              const float* grad_output, const int* pos_memo, float* grad_input, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused LSS lift-splat: out[b,:,y,x] = sum over frustum points p in cell (y,x) of depth[p] * ctx[pix(p),:].
+ * Replaces the materialised outer product + permute + pooling of lss_fpn.py:289-316 (484 MB/sample x2).
+ * geom_xyz (B, ncam*D*H*W, 3) int32 (lss_fpn.py:311-313); depth (B*ncam,D,H,W) f32 (already softmaxed);
+ * ctx (B*ncam,C,H,W) f32; out (B,C,ny,nx) f32.  C in {128,256}.  `state` (state_bytes from
+ * ud_lift_splat_sizes) carries what the backward needs.
+ * ------------------------------------------------------------------------------------------- */
+int ud_lift_splat_sizes(int batch_size, int num_cams, int D, int H, int W, int C, int nx, int ny,
+                        size_t* workspace_bytes, size_t* state_bytes);
+int ud_lift_splat_forward(int batch_size, int num_cams, int D, int H, int W, int C, int nx, int ny, int nz,
+                          const int* geom_xyz, const float* depth, const float* ctx, float* out, void* state,
+                          size_t state_bytes, void* workspace, size_t workspace_bytes, void* stream);
+int ud_lift_splat_backward(int batch_size, int num_cams, int D, int H, int W, int C, int nx, int ny,
+                           const float* grad_out, const float* depth, const void* state, size_t state_bytes,
+                           float* d_depth, float* d_ctx, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

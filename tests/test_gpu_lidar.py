@@ -349,8 +349,8 @@ def test_backbone_forward_parity(cuda, native_lib, training):
 
     torch.manual_seed(0)
     rng = np.random.default_rng(11)
-    grid = np.array([64, 64, 16])
-    sparse_shape = [17, 64, 64]
+    grid = np.array([64, 64, 40])          # z must survive 41 -> 21 -> 11 -> 5 -> 2 (spconv_backbone.py:279-340)
+    sparse_shape = [41, 64, 64]
     net = VoxelResBackBone8x(5, grid)
     with torch.no_grad():
         for mod in net.modules():
