@@ -156,6 +156,34 @@ int ud_lift_splat_backward(int batch_size, int num_cams, int D, int H, int W, in
                            const float* grad_out, const float* depth, const void* state, size_t state_bytes,
                            float* d_depth, float* d_ctx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused distillation losses.  Replace the module-level functions of the reference's distill scripts
+ *   exps/multisensor_fusion/nuscenes/BEVFusion/BEVFusion_nuscenes_centerhead_camera_exp_distill_lidar.py
+ *     :73-97 center_to_corner_box2d (+ :478-483 cell units)   -> ud_box_corners_bev
+ *     :196-245 FeatureDistillLoss (mode 0), :248-323 BEVDistillLoss (mode 1) -> ud_box_distill_*
+ *     :326-385 ResponseDistillLoss + :100-128 calculate_box_mask_gaussian    -> ud_response_distill_*
+ * (identical in the three sibling scripts; camera_exp_distill_fusion uses clamp_lo = 1e-3).
+ * Maps are (B,C,H,W) f32; corners (B,M,4,2) f32 in BEV cells; valid (B,M) u8.  Per-box / per-block partial
+ * results are returned so the caller applies the (all-reduced) normalisers; backward entry points give
+ * gradients w.r.t. the student tensors only.
+ * ------------------------------------------------------------------------------------------- */
+int ud_box_corners_bev(const float* boxes, int n, int stride, float x_min, float y_min, float cell_x,
+                       float cell_y, float* corners, void* stream);
+int ud_box_distill_forward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
+                           const float* corners, const unsigned char* valid, int M, float* out, void* stream);
+int ud_box_distill_backward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
+                            const float* corners, const unsigned char* valid, int M, const float* upstream,
+                            float* grad_s, void* stream);
+int ud_response_distill_forward(const float* cls_s, const float* cls_t, const float* reg_s, const float* reg_t,
+                                int B, int n_cls, int n_reg, int H, int W, const float* boxes, int M, int stride,
+                                const int* n_rows, float x_min, float y_min, float cell_x, float cell_y,
+                                float clamp_lo, float* partial, float* mask_out, void* stream);
+int ud_response_distill_backward(const float* cls_s, const float* cls_t, const float* reg_s, const float* reg_t,
+                                 int B, int n_cls, int n_reg, int H, int W, const float* boxes, int M, int stride,
+                                 const int* n_rows, float x_min, float y_min, float cell_x, float cell_y,
+                                 float clamp_lo, float g_cls, float g_reg, float* d_cls, float* d_reg,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""GPU parity of the fused distillation kernels: against golden vectors of the real reference functions
+(tests/golden/distill.npz) and against the CPU oracle at benchmark shapes.  Tolerance 1e-3 rel (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import distill as OD
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "distill.npz")
+OSF = 8
+_HEADS = ("reg", "height", "dim", "rot", "vel", "iou", "hm")
+REL = 1e-3
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+def test_glue_on_device_matches_reference(cuda, native_lib):
+    from unidistill.layers.losses.distill import gt_boxes_bev_corners, gt_boxes_valid_prefix
+
+    g = np.load(GOLD)
+    gt = torch.from_numpy(g["gt_boxes"]).to(cuda)
+    ind = gt_boxes_valid_prefix(gt[:, :, :9])
+    assert np.array_equal(ind.cpu().numpy(), g["indice"])
+    c = gt_boxes_bev_corners(gt, g["pc_range"].tolist(), g["voxel"].tolist(), OSF)
+    assert np.allclose(c.cpu().numpy(), g["coords"], rtol=1e-6, atol=2e-5)
+
+
+def test_feature_and_relation_match_reference_golden(cuda, native_lib):
+    from unidistill.layers.losses.distill import BEVDistillLoss, FeatureDistillLoss
+
+    g = np.load(GOLD)
+    coords, ind = torch.from_numpy(g["coords"]).to(cuda), torch.from_numpy(g["indice"]).to(cuda)
+    fs = torch.from_numpy(g["fs"]).to(cuda).requires_grad_(True)
+    loss = FeatureDistillLoss(fs, torch.from_numpy(g["ft"]).to(cuda), coords, ind)
+    assert abs(float(loss) - float(g["loss_feat"])) < 1e-5 * abs(float(g["loss_feat"]))
+    loss.backward()
+    assert _rel(fs.grad.cpu().numpy(), g["g_fs"]) < REL
+    bs = torch.from_numpy(g["bs"]).to(cuda).requires_grad_(True)
+    loss = BEVDistillLoss(bs, torch.from_numpy(g["bt"]).to(cuda), coords, ind)
+    assert abs(float(loss) - float(g["loss_rel"])) < 1e-5 * abs(float(g["loss_rel"]))
+    loss.backward()
+    assert _rel(bs.grad.cpu().numpy(), g["g_bs"]) < REL
+
+
+def _resp(g, prefix, dev, grad=False):
+    out = []
+    for t in range(6):
+        d = {}
+        for k in _HEADS:
+            x = torch.from_numpy(g["%s_%s_%d" % (prefix, k, t)]).to(dev)
+            d[k] = x.requires_grad_(True) if grad else x
+        out.append(d)
+    return out
+
+
+def test_response_matches_reference_golden(cuda, native_lib):
+    from unidistill.layers.losses.distill import ResponseDistillLoss
+    from unidistill_b200.distill import response_mask
+
+    g = np.load(GOLD)
+    gt = torch.from_numpy(g["gt_boxes"]).to(cuda)
+    mask = response_mask(gt, (32, 32), g["pc_range"].tolist(), g["voxel"].tolist(), OSF)
+    assert np.array_equal(mask.cpu().numpy(), g["gaussian_mask"]), "Gaussian box mask differs from the reference"
+    rs, rt = _resp(g, "rs", cuda, grad=True), _resp(g, "rt", cuda)
+    lc, lr = ResponseDistillLoss(rs, rt, gt, g["pc_range"].tolist(), g["voxel"].tolist(), OSF)
+    assert abs(float(lc) - float(g["loss_cls"])) < 1e-5 * abs(float(g["loss_cls"]))
+    assert abs(float(lr) - float(g["loss_reg"])) < 1e-5 * abs(float(g["loss_reg"]))
+    (lc + lr).backward()
+    for t in range(6):
+        for k in _HEADS:
+            ref = g["grs_%s_%d" % (k, t)]
+            got = rs[t][k].grad.cpu().numpy()
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= REL * max(1e-12, np.abs(ref).max()), (k, t)
+
+
+@pytest.mark.parametrize("C,mode", [(256, 0), (512, 1), (64, 1)])
+def test_box_distill_benchmark_shapes_vs_oracle(cuda, native_lib, C, mode):
+    """128 x 128 BEV maps, 40 GT rows/sample incl. padded rows and boxes whose centre leaves the map."""
+    from unidistill.layers.losses.distill import BEVDistillLoss, FeatureDistillLoss, gt_boxes_bev_corners
+    from unidistill_b200 import synthetic as S
+
+    torch.manual_seed(C)
+    B = 2
+    batch = S.lidar_batch(B, seed=4, points_per_sweep=10, sweeps=1)
+    gt = batch["gt_boxes"]
+    ind = OD.valid_prefix(gt)
+    coords = OD.bev_corners(gt, S.PC_RANGE_128, S.VOXEL_SIZE_128, 8)
+    s = torch.randn(B, C, 128, 128)
+    t = torch.randn(B, C, 128, 128)
+    fn_o = OD.feature_distill_loss if mode == 0 else OD.bev_distill_loss
+    fn_g = FeatureDistillLoss if mode == 0 else BEVDistillLoss
+    so = s.clone().requires_grad_(True)
+    lo = fn_o(so, t, coords, ind)
+    lo.backward()
+    sg = s.to(cuda).requires_grad_(True)
+    cg = gt_boxes_bev_corners(gt.to(cuda), S.PC_RANGE_128, S.VOXEL_SIZE_128, 8)
+    assert np.allclose(cg.cpu().numpy(), coords.numpy(), rtol=1e-6, atol=5e-5)
+    lg = fn_g(sg, t.to(cuda), cg, ind.to(cuda))
+    assert abs(float(lg) - float(lo)) < 1e-4 * abs(float(lo))
+    lg.backward()
+    assert _rel(sg.grad.cpu().numpy(), so.grad.numpy()) < REL
+
+
+def test_identical_maps_give_zero(cuda, native_lib):
+    from unidistill.layers.losses.distill import BEVDistillLoss, FeatureDistillLoss
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, 16, 16, device=cuda)
+    coords = torch.tensor([[[[3.2, 4.1], [3.2, 9.7], [8.8, 9.7], [8.8, 4.1]]]], device=cuda)
+    ind = torch.ones((1, 1), dtype=torch.bool, device=cuda)
+    assert float(FeatureDistillLoss(x, x.clone(), coords, ind)) == 0.0
+    assert float(BEVDistillLoss(x, x.clone(), coords, ind)) == 0.0
+
+
+def test_constant_maps_hand_value(cuda, native_lib):
+    """Single box well inside constant maps: every bilinear sample equals the constant, so the feature loss is
+    |a - b| * (1 / (1 + 1e-4)); quirk 5 (column swap) is exercised with a map that varies along one axis."""
+    from unidistill.layers.losses.distill import FeatureDistillLoss
+
+    a = torch.full((1, 4, 16, 16), 2.0, device=cuda)
+    b = torch.full((1, 4, 16, 16), -1.0, device=cuda)
+    coords = torch.tensor([[[[4.0, 5.0], [4.0, 8.0], [7.0, 8.0], [7.0, 5.0]]]], device=cuda)
+    ind = torch.ones((1, 1), dtype=torch.bool, device=cuda)
+    assert abs(float(FeatureDistillLoss(a, b, coords, ind)) - 3.0 / (1 + 1e-4)) < 1e-6
+    # map value = row index; the sample row comes from the x cell coordinate (row = x - 0.5)
+    ramp = torch.arange(16.0, device=cuda).view(1, 1, 16, 1).expand(1, 1, 16, 16).contiguous()
+    zero = torch.zeros_like(ramp)
+    pt = torch.tensor([[[[6.0, 2.0]] * 4]], device=cuda)        # all 9 key-points at x = 6, y = 2
+    assert abs(float(FeatureDistillLoss(ramp, zero, pt, ind)) - 5.5 / (1 + 1e-4)) < 1e-5
