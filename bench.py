@@ -1,0 +1,546 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200 BEV feature-extraction / distillation path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference path
+
+Workload at N=1 (BASELINE.json configs[1]): BEVFusion-LiDAR forward = hard voxelization -> mean VFE ->
+VoxelResBackBone8x sparse encoder -> scatter to a 128x128 BEV -> BaseBEVBackbone -> CenterHead towers
+(+ the target assignment CenterHead.forward performs in training mode), bs=4 per GPU, every sample =
+10 sweeps x 40k synthetic ring-LiDAR points.  N>1: every rank runs its own batch (samples are independent;
+a forward has no exchange step) -> weak scaling.  `--workload camera|distill` select configs[2] / [3].
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cvpr2023-unidistill_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "samples/sec BEVFusion fwd+distill (128x128 BEV)"
+UNIT = "samples/s"
+BS_PER_GPU = 4
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tensor_tflops": float(p.get("bf16_tflops_sustained",
+                                                                             p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json; sustained bf16 cuBLAS figure, kernel timed inside a step)"}
+    return {"hbm_gbs": 6650.0, "tensor_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            if self._nvml is not None:
+                try:
+                    n = self._nvml
+                    self.samples.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for name, bit in (("gpu_idle", 0x1), ("applications_clocks_setting", 0x2),
+                                      ("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sync_boost", 0x10),
+                                      ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                                      ("hw_power_brake_slowdown", 0x80)):
+                        if r & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            else:
+                self._smi_once()
+            self._stop_evt.wait(0.1)
+
+    def _smi_once(self):
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+            f = [x.strip() for x in out.strip().split(",")]
+            self.samples.append(int(f[0]))
+            self.max_mhz = int(f[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def _dist_setup(n_gpus):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def _barrier(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(x, world, device):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x, world, device):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed steps."""
+
+    def __init__(self, device, mib=256):
+        import torch
+
+        self.buf = torch.empty(mib << 20, dtype=torch.uint8, device=device)
+        self.v = 0
+
+    def __call__(self):
+        self.v = (self.v + 1) & 0x7F
+        self.buf.fill_(self.v)
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads of this repo's arm
+def _gt_with_labels(batch):
+    import torch
+
+    # reference training_step: gt_boxes (B,M,9) + (label+1) -> (B,M,10)  (..._fusion_exp.py:208-212)
+    return torch.cat([batch["gt_boxes"], (batch["gt_labels"].float() + 1).unsqueeze(-1)], dim=-1)
+
+
+class LidarForward:
+    """configs[1]: BEVFusion-LiDAR SparseEncoder + CenterHead fwd, synthetic 40k pts x 10 sweeps, bs=4."""
+
+    name = "BEVFusion-LiDAR SparseEncoder+CenterHead fwd, 40k pts x10 sweeps, bs=4/GPU, 128x128x5 BEV"
+
+    def __init__(self, device, rank, seed=0):
+        import torch
+
+        from unidistill_b200 import models, synthetic as S
+
+        torch.manual_seed(0)
+        self.device = device
+        cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+        self.model = models.BEVFusionCenterHead(cfg).to(device).train()   # BN on batch statistics (student and
+        batch = S.lidar_batch(BS_PER_GPU, seed=seed + rank)               # teacher both run so)
+        self.points_host = batch["points"].pin_memory()                   # (B, Nmax, 5) zero padded (collate_fn)
+        self.gt_host = _gt_with_labels(batch).pin_memory()
+        self.points_dev = self.points_host.to(device)
+        self.gt_dev = self.gt_host.to(device)
+        self.h2d = self.points_host.numel() * 4 + self.gt_host.numel() * 4
+        self.d2h = 0
+        self.samples = BS_PER_GPU
+
+    def _forward(self, points, gt):
+        import torch
+
+        with torch.no_grad():
+            pts = [points[b] for b in range(points.shape[0])]     # training_step splits the padded batch
+            bev, feat, heads = self.model(pts, None, None, gt, return_feature=True)
+        return bev, feat, heads
+
+    def step(self):
+        return self._forward(self.points_dev, self.gt_dev)
+
+    def step_e2e(self):
+        import torch
+
+        pts = self.points_host.to(self.device, non_blocking=True)
+        gt = self.gt_host.to(self.device, non_blocking=True)
+        _, _, heads = self._forward(pts, gt)
+        hm = torch.cat([h["hm"] for h in heads], dim=1)          # (B, 10, 128, 128) class heat-maps
+        out = hm.cpu()
+        self.d2h = out.numel() * 4
+        return out
+
+
+class CameraForward:
+    """configs[2]: BEVFusion-camera LSS (fused lift-splat) + CenterHead fwd, 6 x 256x704, bs=4."""
+
+    name = "BEVFusion-camera LSS lift-splat+CenterHead fwd, 6 cams 256x704, bs=4/GPU, 128x128 BEV"
+
+    def __init__(self, device, rank, seed=0):
+        import torch
+
+        from unidistill_b200 import models, synthetic as S
+
+        torch.manual_seed(0)
+        self.device = device
+        cfg = models.make_model_cfg(bev=128, lidar=False, camera=True)
+        self.model = models.BEVFusionCenterHead(cfg).to(device).train()
+        cam = S.camera_batch(BS_PER_GPU, seed=seed + rank)
+        lid = S.lidar_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=64, sweeps=1)
+        self.imgs_host = cam["imgs"].pin_memory()
+        self.mats_host = {k: v.pin_memory() for k, v in cam["mats_dict"].items()}
+        self.gt_host = _gt_with_labels(lid).pin_memory()
+        self.imgs_dev = self.imgs_host.to(device)
+        self.mats_dev = {k: v.to(device) for k, v in self.mats_host.items()}
+        self.gt_dev = self.gt_host.to(device)
+        self.h2d = (self.imgs_host.numel() + sum(v.numel() for v in self.mats_host.values())
+                    + self.gt_host.numel()) * 4
+        self.d2h = 0
+        self.samples = BS_PER_GPU
+
+    def _forward(self, imgs, mats, gt):
+        import torch
+
+        with torch.no_grad():
+            return self.model(None, imgs, mats, gt, return_feature=True)
+
+    def step(self):
+        return self._forward(self.imgs_dev, self.mats_dev, self.gt_dev)
+
+    def step_e2e(self):
+        import torch
+
+        imgs = self.imgs_host.to(self.device, non_blocking=True)
+        mats = {k: v.to(self.device, non_blocking=True) for k, v in self.mats_host.items()}
+        gt = self.gt_host.to(self.device, non_blocking=True)
+        _, _, heads = self._forward(imgs, mats, gt)
+        out = torch.cat([h["hm"] for h in heads], dim=1).cpu()
+        self.d2h = out.numel() * 4
+        return out
+
+
+WORKLOADS = {"lidar": LidarForward, "camera": CameraForward}
+
+
+# ---------------------------------------------------------------------------------------------------
+def _roofline_from_records(records, peaks):
+    """Groups the live per-launch timings of ud_sparse_conv_forward by (cin, cout, K) and reports the
+    group with the largest total time (the dominant kernel of the step)."""
+    groups = {}
+    for key, meta, ms in records:
+        if key != "sparse_conv_forward":
+            continue
+        g = groups.setdefault((meta["cin"], meta["cout"], meta["K"]), {"ms": 0.0, "launches": 0, "metas": []})
+        g["ms"] += ms
+        g["launches"] += 1
+        g["metas"].append((meta, ms))
+    if not groups:
+        return None, 0.0
+    total_conv_ms = sum(g["ms"] for g in groups.values())
+    (cin, cout, K), g = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    pairs_cache = {}
+    flops = byts = 0.0
+    for meta, ms in g["metas"]:
+        t = meta["table"]
+        pk = (t.data_ptr(), tuple(t.shape))
+        if pk not in pairs_cache:
+            pairs_cache[pk] = int((t >= 0).sum().item())
+        P = pairs_cache[pk]
+        flops += 2.0 * P * cin * cout
+        byts += 4.0 * (meta["n_in"] * cin + meta["n_out"] * cout + meta["n_out"] * K + K * cin * cout)
+    avg_ms = g["ms"] / g["launches"]
+    tflops = flops / g["launches"] / avg_ms / 1e9
+    gbs = byts / g["launches"] / avg_ms / 1e6
+    tensor_bound = cin >= 32           # C<=16 is gather-bandwidth bound, C>=32 tensor-pipe bound
+    roof = {
+        "kernel": "k_spconv_gather_gemm<%d,%d> (ud_sparse_conv_forward, K=%d)" % (cin, cout, K),
+        "bound": "tensor" if tensor_bound else "hbm",
+        "achieved": round(tflops if tensor_bound else gbs, 3),
+        "peak": peaks["tensor_tflops"] if tensor_bound else peaks["hbm_gbs"],
+        "unit": "TFLOP/s" if tensor_bound else "GB/s",
+        "frac": round((tflops / peaks["tensor_tflops"]) if tensor_bound else (gbs / peaks["hbm_gbs"]), 5),
+        "traffic": None,
+        "avg_launch_ms": round(avg_ms, 4),
+        "launches_per_step_group": g["launches"],
+        "algorithmic_gflop_per_launch": round(flops / g["launches"] / 1e9, 3),
+        "algorithmic_mb_per_launch": round(byts / g["launches"] / 1e6, 3),
+        "achieved_gbs_algorithmic": round(gbs, 1),
+        "peak_source": peaks["source"],
+    }
+    return roof, total_conv_ms
+
+
+def run_ours(args):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference)")
+    from unidistill_b200 import native
+
+    native.load()
+    world, rank, local = _dist_setup(args.gpus)
+    device = torch.device("cuda", local if world > 1 else 0)
+    wl = WORKLOADS[args.workload](device, rank)
+    flush = L2Flusher(device)
+    peaks = _peaks()
+
+    for _ in range(max(args.warmup, 3)):
+        wl.step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps ----------
+    sampler = ClockSampler(local if world > 1 else 0)
+    native.TIMER.enabled = True
+    native.TIMER.records = []
+    events = []
+    _barrier(world)
+    sampler.start()
+    native.launch_count(reset=True)
+    wall0 = time.perf_counter()
+    if args.profile:                      # ncu --profile-from-start off: capture exactly the timed steps
+        torch.cuda.cudart().cudaProfilerStart()
+    for _ in range(args.steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        wl.step()
+        e1.record()
+        events.append((e0, e1))
+    _barrier(world)
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStop()
+    wall = time.perf_counter() - wall0
+    launches = native.launch_count(reset=True)
+    clocks = sampler.stop()
+    native.TIMER.enabled = False
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    records = native.TIMER.drain()
+    total_ms = _max_over_ranks(sum(step_ms), world, device)
+    samples_all = _sum_over_ranks(wl.samples * args.steps, world, device)
+    value = samples_all / (total_ms / 1e3)
+
+    # ---- end-to-end: pinned host -> device copy + step + result read-back, every step -------------
+    for _ in range(0 if args.profile else 2):
+        wl.step_e2e()
+    torch.cuda.synchronize()
+    ev = []
+    _barrier(world)
+    for _ in range(1 if args.profile else args.steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        wl.step_e2e()
+        e1.record()
+        ev.append((e0, e1))
+    _barrier(world)
+    e2e_ms = _max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world, device)
+    e2e_value = samples_all / (e2e_ms / 1e3)
+
+    roof, conv_ms = _roofline_from_records(records, peaks) if args.workload == "lidar" else (None, 0.0)
+
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "global_batch": BS_PER_GPU * world, "per_gpu_batch": BS_PER_GPU,
+                   "bn": "train-mode batch statistics, torch.no_grad", "weights": "random init, seed 0",
+                   "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed",
+                   "dense_convs": "cuDNN fp32 (torch default allow_tf32)", "parallelism": "dp%d" % world},
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d),
+                "d2h_bytes_per_step": int(wl.d2h), "ms_per_step": round(e2e_ms / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "wall_s_timed_region": round(wall, 3),
+        "step_ms_min_med_max": [round(min(step_ms), 3), round(sorted(step_ms)[len(step_ms) // 2], 3),
+                                round(max(step_ms), 3)],
+    }
+    if roof is not None:
+        roof["share_of_step"] = round(conv_ms / max(1e-9, sum(step_ms)), 4)
+        line["roofline"] = roof
+    if args.profile:
+        line["profiled"] = "run under a profiler range: numbers on this line are NOT bench values"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
+        line["cpu_baseline"] = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU restatement of the reference path (oracle/), timed on the host cores.
+class CpuLidarForward:
+    """One sample (one 400k-point cloud) per step through oracle/: C first-come voxelizer + mean VFE,
+    spconv-Native restated with torch CPU ops (gather -> mm -> index_add_ per kernel offset), dense(),
+    then the mirrored BaseBEVBackbone + CenterHead modules on torch CPU (the reference's own CPU path for the
+    dense part)."""
+
+    sample = "1 cloud (10 sweeps x 40k pts) per step, bs=1, same generator and weights as the GPU arm"
+
+    def __init__(self, seed=0):
+        import numpy as np
+        import torch
+
+        from oracle import lidar as O
+        from unidistill.layers.blocks_3d.det3d import VoxelResBackBone8x
+        from unidistill_b200 import models, synthetic as S
+
+        torch.manual_seed(0)
+        self.O, self.S = O, S
+        cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+        self.cfg = cfg
+        bb = VoxelResBackBone8x(5, np.array(cfg.lidar_encoder.grid_size))
+        self.sd = {k: v.detach().clone() for k, v in bb.state_dict().items()}
+        self.bev_encoder = models.BevEncoder(cfg.bev_encoder).train()
+        self.det_head = models.DetHead(cfg.det_head).train()
+        batch = S.lidar_batch(BS_PER_GPU, seed=seed)
+        self.clouds = [batch["points"][b].numpy() for b in range(BS_PER_GPU)]
+        self.gt = _gt_with_labels(batch)
+        self.i = 0
+
+    def step(self):
+        import torch
+
+        O, S = self.O, self.S
+        b = self.i % len(self.clouds)
+        self.i += 1
+        with torch.no_grad():
+            _, coords, num, mean = O.voxelize([self.clouds[b]], S.VOXEL_SIZE_128, S.PC_RANGE_128, S.GRID_SIZE_128,
+                                              10, 120000)
+            f, c, shape = O.backbone_forward(self.sd, mean, coords, 1, [41, 1024, 1024], training=True)
+            bev = torch.from_numpy(O.height_compression(f.numpy(), c, 1, shape))
+            x = self.bev_encoder(bev)
+            ret = self.det_head(x[0], self.gt[b:b + 1])
+        return ret
+
+    samples = 1
+
+
+def cpu_baseline(workload, budget_s=25.0):
+    import torch
+
+    if workload != "lidar":
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "not implemented"}
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = CpuLidarForward()
+    wl.step()                                   # warm-up (builds the C oracle, primes torch's thread pool)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        wl.step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 8:
+            break
+    return {"value": round(n * wl.samples / el, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d x [%s], %.1f s" % (n, wl.sample, el)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (spconv / voxel_pooling_ext are binary wheels that can
+    neither be imported nor compiled here, so this is the oracle port), all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    if args.workload != "lidar":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm implements the lidar workload only"}))
+        return
+    wl = CpuLidarForward()
+    for _ in range(max(1, min(args.warmup, 2))):      # bounded: one CPU step is seconds long
+        wl.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wl.step()
+    el = time.perf_counter() - t0
+    value = args.steps * wl.samples / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": round(el / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": LidarForward.name, "sample_per_step": wl.sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d x [%s]" % (args.steps, wl.sample)},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lidar", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,10 +17,14 @@
         if (_e != cudaSuccess) return (int)_e;     \
     } while (0)
 
+// number of kernels this library launched since the last ud_launch_count(1) (bench.py's gpu_launches)
+extern unsigned long long g_ud_launches;
+
 #define UD_LAUNCH_CHECK()                          \
     do {                                           \
         cudaError_t _e = cudaGetLastError();       \
         if (_e != cudaSuccess) return (int)_e;     \
+        ++g_ud_launches;                           \
     } while (0)
 
 #define UD_MAX_BATCH 64

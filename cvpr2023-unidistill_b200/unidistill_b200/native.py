@@ -139,6 +139,41 @@ class Workspace:
 WORKSPACE = Workspace()
 
 
+def launch_count(reset=False):
+    """Kernels launched by the library since the last reset (every `<<<>>>` of csrc/ counts one)."""
+    return int(load().ud_launch_count(1 if reset else 0))
+
+
+class KernelTimer:
+    """CUDA-event timing of single C-ABI calls on the stream they are launched on (bench.py's roofline
+    numbers are taken live, inside the timed region, through this hook).  Disabled by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def call(self, key, meta, fn, *args):
+        if not self.enabled:
+            return fn(*args)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        self.records.append((key, meta, e0, e1))
+        return rc
+
+    def drain(self):
+        """-> [(key, meta, milliseconds)], after a device synchronize."""
+        torch.cuda.synchronize()
+        out = [(k, m, e0.elapsed_time(e1)) for k, m, e0, e1 in self.records]
+        self.records = []
+        return out
+
+
+TIMER = KernelTimer()
+
+
 def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:

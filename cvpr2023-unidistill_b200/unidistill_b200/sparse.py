@@ -120,8 +120,11 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout):
     lib = native.load()
     out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
-    rc = lib.ud_sparse_conv_forward(native.ptr(feats), native.ptr(w_k), native.ptr(bias), native.ptr(table),
-                                    n_out, K, cin, cout, native.ptr(out), native.stream_ptr(feats.device))
+    meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
+            "table": table} if native.TIMER.enabled else None
+    rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_forward, native.ptr(feats),
+                           native.ptr(w_k), native.ptr(bias), native.ptr(table),
+                           n_out, K, cin, cout, native.ptr(out), native.stream_ptr(feats.device))
     native.check(rc, "ud_sparse_conv_forward")
     return out
 

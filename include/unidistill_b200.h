@@ -30,6 +30,8 @@ extern "C" {
 const char* ud_version(void);
 /* human-readable text for a return code of this library (static storage) */
 const char* ud_error_string(int code);
+/* kernels launched by this library since the last call with reset != 0 (launch accounting for bench.py) */
+int ud_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * Hard voxelization + mean VFE.

@@ -69,6 +69,30 @@ def feature_distill_loss(student, teacher, coords, indices):
     return loss / (indices.float().sum() + 1e-4)
 
 
+def gram_pair(student, teacher, coords):
+    """(B, M, 9, 9) Gram matrices of the normalised key-point features of student and teacher."""
+    h, w = student.shape[-2:]
+    grid = _keypoint_grid(coords, h, w)
+
+    def gram(fmap):
+        s = _sample(fmap, grid)
+        s = s / (torch.norm(s, dim=-1, keepdim=True) + 1e-4)
+        return s @ s.transpose(-1, -2)
+
+    return gram(student), gram(teacher)
+
+
+def well_conditioned_boxes(student, teacher, coords, indices, tol=1e-5):
+    """Boxes whose relation-loss gradient is well defined: the L1 between Gram entries has a sign() in its
+    derivative, so an off-diagonal |G_s - G_t| below fp32 round-off makes the gradient a coin flip (any two
+    fp32 implementations, and the reference on two devices, disagree there).  Evaluated in float64."""
+    gs, gt = gram_pair(student.double(), teacher.double(), coords.double())
+    d = (gs - gt).abs()
+    off = ~torch.eye(d.shape[-1], dtype=torch.bool)
+    risky = ((d < tol) & (d > 0) & off).flatten(2).any(-1)
+    return indices & ~risky
+
+
 def bev_distill_loss(student, teacher, coords, indices):
     h, w = student.shape[-2:]
     grid = _keypoint_grid(coords, h, w)

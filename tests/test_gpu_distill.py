@@ -94,6 +94,11 @@ def test_box_distill_benchmark_shapes_vs_oracle(cuda, native_lib, C, mode):
     coords = OD.bev_corners(gt, S.PC_RANGE_128, S.VOXEL_SIZE_128, 8)
     s = torch.randn(B, C, 128, 128)
     t = torch.randn(B, C, 128, 128)
+    if mode == 1:
+        # d|G_s - G_t|/dG = sign(.): drop the boxes where that sign hangs on fp32 round-off (see the oracle)
+        n_before = int(ind.sum())
+        ind = OD.well_conditioned_boxes(s, t, coords, ind)
+        assert int(ind.sum()) >= n_before - 3
     fn_o = OD.feature_distill_loss if mode == 0 else OD.bev_distill_loss
     fn_g = FeatureDistillLoss if mode == 0 else BEVDistillLoss
     so = s.clone().requires_grad_(True)
