@@ -306,7 +306,7 @@ def _roofline_from_records(records, peaks):
     gbs = byts / g["launches"] / avg_ms / 1e6
     tensor_bound = cin >= 32           # C<=16 is gather-bandwidth bound, C>=32 tensor-pipe bound
     roof = {
-        "kernel": "k_spconv_gather_gemm<%d,%d> (ud_sparse_conv_forward, K=%d)" % (cin, cout, K),
+        "kernel": "%s<%d,%d> (K=%d taps)" % (g["metas"][0][0].get("kernel", "k_spconv"), cin, cout, K),
         "bound": "tensor" if tensor_bound else "hbm",
         "achieved": round(tflops if tensor_bound else gbs, 3),
         "peak": peaks["tensor_tflops"] if tensor_bound else peaks["hbm_gbs"],

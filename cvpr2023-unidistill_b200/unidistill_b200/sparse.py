@@ -2,6 +2,8 @@
 dense()/scatter-to-BEV.  These are the primitives the `spconv` shim and the mirrored
 `unidistill.layers` modules are made of (reference: layers/blocks_3d/det3d/spconv_backbone.py).
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -117,14 +119,35 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 
 
 # ---------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
+# every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
+USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
+
+
 def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout):
     lib = native.load()
-    out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
+    dev = feats.device
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
+    sp = native.stream_ptr(dev)
     meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
             "table": table} if native.TIMER.enabled else None
+    if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout):
+        nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout)
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
+        native.check(rc, "ud_sparse_conv_tc_pack_weights")
+        if meta is not None:
+            meta["kernel"] = "k_spconv_umma"
+        rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
+                               native.ptr(packed), native.ptr(bias), native.ptr(table), n_out, K, cin, cout,
+                               native.ptr(out), sp)
+        native.check(rc, "ud_sparse_conv_tc_forward")
+        return out
+    if meta is not None:
+        meta["kernel"] = "k_spconv_gather_gemm"
     rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_forward, native.ptr(feats),
                            native.ptr(w_k), native.ptr(bias), native.ptr(table),
-                           n_out, K, cin, cout, native.ptr(out), native.stream_ptr(feats.device))
+                           n_out, K, cin, cout, native.ptr(out), sp)
     native.check(rc, "ud_sparse_conv_forward")
     return out
 

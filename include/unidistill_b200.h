@@ -94,6 +94,16 @@ int ud_sparse_conv_forward(const float* in, const float* w, const float* bias, c
 int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int n_out, int K, int cin,
                          int cout, float* dw, void* stream);
 
+/* Tensor-core variant (tcgen05.mma kind::tf32 with a hi/lo operand split == fp32-accurate "3xTF32",
+ * accumulators in TMEM; csrc/sparse_conv_umma.cu).  Same arithmetic contract as ud_sparse_conv_forward for
+ * the (cin, cout) pairs ud_sparse_conv_tc_supported() accepts; the weights are first packed into the
+ * swizzled hi/lo image the kernel's bulk copies read (packed_bytes from ud_sparse_conv_tc_weight_bytes). */
+int ud_sparse_conv_tc_supported(int K, int cin, int cout);
+int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
+int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
+int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr, int n_out,
+                              int K, int cin, int cout, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /
  * replace_feature passes of spconv_backbone.py:50-56,97-113,255.

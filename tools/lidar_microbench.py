@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cvpr2023-unidistill_b200"))
 
-from unidistill_b200 import sparse, synthetic as S  # noqa: E402
+from unidistill_b200 import native, sparse, synthetic as S  # noqa: E402
 from unidistill_b200.voxelize import hard_voxelize  # noqa: E402
 
 
@@ -77,6 +77,13 @@ def main():
             ms, out = timed(lambda: sparse.sparse_conv(x, w, None, rb))
         byt = rb.n_in * cin * 4 + rb.n_out * cout * 4 + rb.n_out * rb.K * 4 + rb.K * cin * cout * 4
         rows.append(("conv %s %d->%d N=%d P=%d" % (kind, cin, cout, rb.n_out, P), ms, byt, 2.0 * P * cin * cout))
+        if sparse.USE_TENSOR_CORES and native.load().ud_sparse_conv_tc_supported(rb.K, cin, cout):
+            sparse.USE_TENSOR_CORES = False
+            with torch.no_grad():
+                ms2, out2 = timed(lambda: sparse.sparse_conv(x, w, None, rb))
+            sparse.USE_TENSOR_CORES = True
+            rows.append(("   (same, fp32 SIMT kernel; max |d| %.2e)" % float((out - out2).abs().max()), ms2, byt,
+                         2.0 * P * cin * cout))
         if cout >= 16:
             bn = torch.nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01).to(dev)
             with torch.no_grad():
