@@ -6,9 +6,10 @@
 //   reference unidistill/layers/blocks_3d/det3d/spconv_backbone.py:21-48,70-92 (+ their dgrad, which is
 //   this same kernel run on the transposed table and weights).
 //
-// Formulation: implicit GEMM, output stationary.  One CTA owns 128 consecutive output rows (UMMA M = 128)
-// and all COUT columns (UMMA N = COUT); the fp32 accumulator lives in TMEM.  For every kernel tap that
-// occurs in the tile, and every 32-channel slice of CIN, a pipeline stage holds
+// Formulation: implicit GEMM, output stationary.  A tile = 128 consecutive output rows (UMMA M = 128) x all
+// COUT columns (UMMA N = COUT) with its fp32 accumulator in TMEM; one CTA owns up to 512/COUT (<= 8) tiles so
+// that every weight slice is fetched once per CTA.  For every kernel tap that occurs in a tile, and every
+// 32-channel slice of CIN, a pipeline stage holds
 //     A  = the gathered input rows   [128 x 32]  K-major, 128-byte swizzle   (written by the gather warps)
 //     B  = W[tap]^T slice            [COUT x 32] K-major, 128-byte swizzle   (one bulk async copy of a
 //                                                                            pre-swizzled weight image)
@@ -56,6 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// One lane of the (converged) warp; nvcc recognises elect.sync and issues the tcgen05 instructions of the guarded
+// region directly instead of wrapping each one in its own election loop.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -131,10 +145,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__host__ __device__ constexpr int stage_bytes(int cout) { return 2 * TILE_M * 128 + 2 * cout * 128; }
-__host__ __device__ constexpr int num_stages(int cout) {
-    return (200 * 1024) / stage_bytes(cout) >= 4 ? 4 : (200 * 1024) / stage_bytes(cout);
-}
+constexpr int A_STAGES = 4;            // ring of gathered A tiles (hi + lo, 32 KB each)
+constexpr int B_STAGES = 2;            // ring of weight slices (hi + lo)
+constexpr int A_STAGE_BYTES = 2 * TILE_M * 128;
+constexpr int MAX_TILES = 8;           // output tiles (TMEM accumulators) per CTA
+constexpr int MAX_SCHED = MAX_TAPS * 4 * 8;   // >= taps * (CIN/32) * tiles for every instantiation
+
+__host__ __device__ constexpr int tiles_max(int cout) { return 512 / cout < MAX_TILES ? 512 / cout : MAX_TILES; }
 
 // ------------------------------------------------------------------------------------------------
 // packed weight image: [tap][CIN/32][hi|lo][COUT rows][32 floats, 16-byte chunks XOR-swizzled by row&7]
@@ -157,105 +174,153 @@ k_pack_weights(const float* __restrict__ w, int K, int cin, int cout, float* __r
     packed[base + (size_t)cout * KC + (size_t)n * KC + pos] = lo;
 }
 
+// [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment
+__global__ void __launch_bounds__(256)
+k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ dst) {
+    __shared__ int tile[32][33];
+    const int r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i;
+        tile[i][tx] = (r < n && tx < K) ? src[(size_t)r * K + tx] : -1;
+    }
+    __syncthreads();
+    for (int k = ty; k < K; k += 8) {
+        const int r = r0 + tx;
+        if (r < n) dst[(size_t)k * n + r] = tile[tx][k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
+// One CTA = `tiles` (<= 512/COUT, <= 8) consecutive 128-row output tiles, one TMEM accumulator each, so that a
+// weight slice W[tap][32-channel chunk] is fetched once per CTA and reused by every tile that has the tap.
+// Schedule (identical in all roles, built once in shared memory):
+//   for tap in taps present in the CTA: for chunk: [B slice]  for tile having the tap: [A stage] -> 12 MMAs
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
-              const int* __restrict__ nbr, int n_out, int K, float* __restrict__ out) {
+              const int* __restrict__ nbr_t, int n_out, int K, int tiles, float* __restrict__ out) {
     constexpr int NCHUNK = CIN / KC;
-    constexpr int S = num_stages(COUT);
     constexpr int A_BYTES = TILE_M * 128;            // one [128 x 32] fp32 operand tile
     constexpr int B_BYTES = COUT * 128;
-    constexpr int STAGE = stage_bytes(COUT);         // A_hi | A_lo | B_hi | B_lo
-    constexpr uint32_t TMEM_COLS = COUT < 32 ? 32 : COUT;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(TILE_M >> 4) << 24);
     static_assert(CIN % KC == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert(MAX_TAPS * NCHUNK * tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
 
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[2 * 4 + 1];
+    __shared__ __align__(8) unsigned long long bars[2 * A_STAGES + 2 * B_STAGES + 1];
     __shared__ uint32_t tmem_base_s;
-    __shared__ unsigned int tile_mask_s;
-    __shared__ int tap_list[MAX_TAPS];
-    __shared__ int n_taps_s;
+    __shared__ unsigned int tile_mask_s[MAX_TILES];
+    __shared__ unsigned short a_sched[MAX_SCHED];          // tap | chunk << 5 | tile << 8
+    __shared__ unsigned short b_sched[MAX_TAPS * 4];       // tap | chunk << 5
+    __shared__ unsigned short b_count[MAX_TAPS * 4];       // A stages that use this weight slice
+    __shared__ int n_a_s, n_b_s;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int row0 = blockIdx.x * TILE_M;
+    const int row0 = blockIdx.x * tiles * TILE_M;
+    const int rows_cta = min(tiles * TILE_M, n_out - row0);
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    int* nbr_s = reinterpret_cast<int*>(smem_al + S * STAGE);          // [TILE_M][K]
-    const uint32_t bar_full = smem_u32(&bars[0]);                      // + 8*s
-    const uint32_t bar_empty = smem_u32(&bars[4]);
-    const uint32_t bar_acc = smem_u32(&bars[8]);
+    const uint32_t smem_b = smem_base + A_STAGES * A_STAGE_BYTES;
+    const uint32_t bar_a_full = smem_u32(&bars[0]);
+    const uint32_t bar_a_empty = smem_u32(&bars[A_STAGES]);
+    const uint32_t bar_b_full = smem_u32(&bars[2 * A_STAGES]);
+    const uint32_t bar_b_empty = smem_u32(&bars[2 * A_STAGES + B_STAGES]);
+    const uint32_t bar_acc = smem_u32(&bars[2 * A_STAGES + 2 * B_STAGES]);
 
     if (tid == 0) {
-        tile_mask_s = 0u;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            mbar_init(bar_full + 8 * s, GATHER_THREADS + 1);
-            mbar_init(bar_empty + 8 * s, 1);
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, GATHER_THREADS);
+            mbar_init(bar_a_empty + 8 * s, 1);
+        }
+#pragma unroll
+        for (int s = 0; s < B_STAGES; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
+    if (tid < MAX_TILES) tile_mask_s[tid] = 0u;
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
     __syncthreads();
-    // ---- neighbour table of the tile + which taps occur in it ----
+    // ---- which taps occur in which tile (one coalesced pass over the CTA's slice of the table) ----
     {
-        const int rows_here = min(TILE_M, n_out - row0);
-        const int total = rows_here * K;
-        const int* src = nbr + (size_t)row0 * K;
-        unsigned int m = 0u;
-        for (int e = tid; e < TILE_M * K; e += NTHREADS) {
-            const int v = e < total ? __ldg(src + e) : -1;
-            nbr_s[e] = v;
-            if (v >= 0) m |= 1u << (e % K);
+        const int segs = (rows_cta + 31) >> 5;                 // 32-row segments
+        for (int w = warp; w < K * segs; w += NTHREADS / 32) {
+            const int k = w / segs, sg = w - k * segs;
+            const int r = sg * 32 + lane;
+            const int v = r < rows_cta ? __ldg(nbr_t + (size_t)k * n_out + row0 + r) : -1;
+            const unsigned any = __ballot_sync(0xffffffffu, v >= 0);
+            if (lane == 0 && any) atomicOr(&tile_mask_s[sg >> 2], 1u << k);
         }
-        m = __reduce_or_sync(0xffffffffu, m);
-        if (lane == 0 && m) atomicOr(&tile_mask_s, m);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        unsigned int m = tile_mask_s;
-        int n = 0;
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            tap_list[n++] = k;
+        unsigned int uni = 0u;
+        for (int t = 0; t < tiles; ++t) uni |= tile_mask_s[t];
+        int na = 0, nb = 0;
+        for (int k = 0; k < K; ++k) {
+            if (!((uni >> k) & 1u)) continue;
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                int cnt = 0;
+                for (int t = 0; t < tiles; ++t)
+                    if ((tile_mask_s[t] >> k) & 1u) {
+                        a_sched[na++] = (unsigned short)(k | (ch << 5) | (t << 8));
+                        ++cnt;
+                    }
+                b_sched[nb] = (unsigned short)(k | (ch << 5));
+                b_count[nb] = (unsigned short)cnt;
+                ++nb;
+            }
         }
-        n_taps_s = n;
+        n_a_s = na;
+        n_b_s = nb;
     }
     __syncthreads();
-    const int n_it = n_taps_s * NCHUNK;
+    const int n_a = n_a_s;
+    const int n_b = n_b_s;
     const uint32_t tmem_acc = tmem_base_s;
 
     if (warp < 8) {
-        // ===================== gather producers: group g fills stages it = g, g+2, ... =====================
+        // ============ gather producers: group g fills A stages it = g, g+2, ... ============
         const int g = warp >> 2;
         const int tg = tid & (GATHER_THREADS - 1);
         const int chunk = tg & 7;                    // 16-byte chunk of the 128-byte row slice
         const int rbase = tg >> 3;                   // rows rbase + 16*j, j = 0..7
         uint4 buf0[8], buf1[8];
+        int idx0[8], idx1[8];
 
-        auto load = [&](uint4(&buf)[8], int it) {
-            const int tap = tap_list[it / NCHUNK];
-            const int c0 = (it % NCHUNK) * KC + chunk * 4;
+        auto load_idx = [&](int(&idx)[8], int it) {
+            const unsigned e = a_sched[it];
+            const int tap = e & 31, tile = e >> 8;
+            const int* col = nbr_t + (size_t)tap * n_out + row0 + tile * TILE_M;
+            const int lim = rows_cta - tile * TILE_M;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int src = nbr_s[(rbase + 16 * j) * K + tap];
+                const int r = rbase + 16 * j;
+                idx[j] = r < lim ? __ldg(col + r) : -1;
+            }
+        };
+        auto load = [&](uint4(&buf)[8], const int(&idx)[8], int it) {
+            const int c0 = ((a_sched[it] >> 5) & 7) * KC + chunk * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
                 buf[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (src >= 0) buf[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)src * CIN + c0));
+                if (idx[j] >= 0) buf[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)idx[j] * CIN + c0));
             }
         };
         auto store = [&](uint4(&buf)[8], int it) {
-            const int slot = it % S;
-            mbar_wait(bar_empty + 8 * slot, (((uint32_t)(it / S)) & 1u) ^ 1u);
-            unsigned char* a_hi = smem_al + slot * STAGE;
+            const int slot = it % A_STAGES;
+            mbar_wait(bar_a_empty + 8 * slot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+            unsigned char* a_hi = smem_al + slot * A_STAGE_BYTES;
             unsigned char* a_lo = a_hi + A_BYTES;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -269,112 +334,484 @@ k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, c
                 *reinterpret_cast<uint4*>(a_lo + off) = l;
             }
             fence_proxy_async();
-            mbar_arrive(bar_full + 8 * slot);
+            mbar_arrive(bar_a_full + 8 * slot);
         };
 
+        // software pipeline per group: indices two stages ahead, data one stage ahead
         int it = g;
-        if (it < n_it) load(buf0, it);
-        while (it < n_it) {
-            if (it + 2 < n_it) load(buf1, it + 2);
+        if (it < n_a) { load_idx(idx0, it); load(buf0, idx0, it); }
+        if (it + 2 < n_a) load_idx(idx1, it + 2);
+        while (it < n_a) {
+            if (it + 2 < n_a) load(buf1, idx1, it + 2);
+            if (it + 4 < n_a) load_idx(idx0, it + 4);
             store(buf0, it);
             it += 2;
-            if (it >= n_it) break;
-            if (it + 2 < n_it) load(buf0, it + 2);
+            if (it >= n_a) break;
+            if (it + 2 < n_a) load(buf0, idx0, it + 2);
+            if (it + 4 < n_a) load_idx(idx1, it + 4);
             store(buf1, it);
             it += 2;
         }
     } else if (warp == 8) {
-        // ===================== MMA issuer =====================
-        for (int it = 0; it < n_it; ++it) {
-            const int slot = it % S;
-            mbar_wait(bar_full + 8 * slot, ((uint32_t)(it / S)) & 1u);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_hi = smem_base + slot * STAGE;
-                const uint32_t a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_lo + A_BYTES;
-                const uint32_t b_lo = b_hi + B_BYTES;
-                const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_lo);
-                const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_lo);
+        // ============ MMA issuer ============
+        unsigned int started = 0u;                   // tiles whose accumulator has been written once
+        int it = 0;
+        for (int ib = 0; ib < n_b; ++ib) {
+            const int bslot = ib % B_STAGES;
+            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / B_STAGES)) & 1u);
+            const uint32_t b_hi = smem_b + bslot * 2 * B_BYTES;
+            const uint32_t b_lo = b_hi + B_BYTES;
+            const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_lo);
+            const int cnt = b_count[ib];
+            for (int c = 0; c < cnt; ++c, ++it) {
+                const int slot = it % A_STAGES;
+                const int tile = a_sched[it] >> 8;
+                mbar_wait(bar_a_full + 8 * slot, ((uint32_t)(it / A_STAGES)) & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_hi = smem_base + slot * A_STAGE_BYTES;
+                    const uint64_t da_hi = umma_desc_sw128(a_hi), da_lo = umma_desc_sw128(a_hi + A_BYTES);
+                    const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
+                    const uint32_t first = (started >> tile) & 1u;
 #pragma unroll
-                for (int ks = 0; ks < KC / 8; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);       // 8 fp32 = 32 B = 2 x 16 B
-                    umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(tmem_acc, da_hi + adv, db_lo + adv, IDESC, 1u);
-                    umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, IDESC, 1u);
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);       // 8 fp32 = 32 B = 2 x 16 B
+                        umma_tf32(d, da_lo + adv, db_hi + adv, IDESC, (first || ks > 0) ? 1u : 0u);
+                        umma_tf32(d, da_hi + adv, db_lo + adv, IDESC, 1u);
+                        umma_tf32(d, da_hi + adv, db_hi + adv, IDESC, 1u);
+                    }
+                    umma_commit(bar_a_empty + 8 * slot);       // frees the A stage when these MMAs retire
                 }
-                umma_commit(bar_empty + 8 * slot);             // frees the stage when these MMAs retire
+                started |= 1u << tile;
+                __syncwarp();
             }
+            if (elect_one_sync()) umma_commit(bar_b_empty + 8 * bslot);
             __syncwarp();
         }
-        if (lane == 0) umma_commit(bar_acc);
+        if (elect_one_sync()) umma_commit(bar_acc);
         __syncwarp();
     } else {
-        // ===================== weight loader =====================
+        // ============ weight loader ============
         if (lane == 0) {
-            for (int it = 0; it < n_it; ++it) {
-                const int slot = it % S;
-                mbar_wait(bar_empty + 8 * slot, (((uint32_t)(it / S)) & 1u) ^ 1u);
-                const int tap = tap_list[it / NCHUNK];
-                const int ch = it % NCHUNK;
+            for (int ib = 0; ib < n_b; ++ib) {
+                const int bslot = ib % B_STAGES;
+                mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / B_STAGES)) & 1u) ^ 1u);
+                const unsigned e = b_sched[ib];
+                const int tap = e & 31, ch = e >> 5;
                 const float* src = wpacked + ((size_t)(tap * NCHUNK + ch) * 2) * COUT * KC;
-                mbar_arrive_expect_tx(bar_full + 8 * slot, 2 * B_BYTES);
-                bulk_g2s(smem_base + slot * STAGE + 2 * A_BYTES, src, 2 * B_BYTES, bar_full + 8 * slot);
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, 2 * B_BYTES);
+                bulk_g2s(smem_b + bslot * 2 * B_BYTES, src, 2 * B_BYTES, bar_b_full + 8 * bslot);
             }
         }
         __syncwarp();
     }
 
-    // ===================== epilogue: TMEM -> registers -> (+bias) -> global =====================
+    // ============ epilogue: TMEM -> registers -> (+bias) -> global ============
     if (warp < 4) {
-        const int row = row0 + warp * 32 + lane;
-        if (n_it > 0) {
+        if (n_a > 0) {
             mbar_wait(bar_acc, 0u);
             tc_fence_after();
         }
         constexpr int CW = COUT >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += CW) {
-            uint32_t v[32];
-            if (n_it > 0) {
-                const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-                if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-                tmem_ld_wait();
-            } else {
+        for (int t = 0; t < tiles; ++t) {
+            if (t * TILE_M >= rows_cta) break;
+            const bool has_acc = tile_mask_s[t] != 0u;       // warp-uniform
+            const int r_local = t * TILE_M + warp * 32 + lane;
+            const int row = row0 + r_local;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                uint32_t v[32];
+                if (has_acc) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * COUT + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int i = 0; i < CW; ++i) v[i] = 0u;
-            }
-            if (row < n_out) {
-                float* dst = out + (size_t)row * COUT + c0;
+                    for (int i = 0; i < CW; ++i) v[i] = 0u;
+                }
+                if (r_local < rows_cta) {
+                    float* dst = out + (size_t)row * COUT + c0;
 #pragma unroll
-                for (int i = 0; i < CW; i += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[i + 0]);
-                    o.y = __uint_as_float(v[i + 1]);
-                    o.z = __uint_as_float(v[i + 2]);
-                    o.w = __uint_as_float(v[i + 3]);
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    for (int i = 0; i < CW; i += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[i + 0]);
+                        o.y = __uint_as_float(v[i + 1]);
+                        o.z = __uint_as_float(v[i + 2]);
+                        o.w = __uint_as_float(v[i + 3]);
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
                     }
-                    *reinterpret_cast<float4*>(dst + i) = o;
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_acc, TMEM_COLS);
+    if (warp == 8) tmem_dealloc(tmem_acc, 512);
 }
 
 template <int CIN, int COUT>
-int launch_umma(const float* in, const float* wpacked, const float* bias, const int* nbr, int n_out, int K,
+int launch_umma(const float* in, const float* wpacked, const float* bias, const int* nbr_t, int n_out, int K,
                 float* out, cudaStream_t stream) {
-    constexpr int S = num_stages(COUT);
-    const size_t smem = (size_t)S * stage_bytes(COUT) + (size_t)TILE_M * K * sizeof(int) + 1024;
+    const size_t smem = (size_t)A_STAGES * A_STAGE_BYTES + (size_t)B_STAGES * 2 * COUT * 128 + 1024;
     auto kern = k_spconv_umma<CIN, COUT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ud_blocks(n_out, TILE_M), NTHREADS, smem, stream>>>(in, wpacked, bias, nbr, n_out, K, out);
+    // tiles per CTA: as many as TMEM holds, but keep the waves over the 148 SMs balanced
+    const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    const int tmax = tiles_max(COUT);
+    const int waves = (n_tiles + UD_NUM_SMS * tmax - 1) / (UD_NUM_SMS * tmax);
+    int tiles = (n_tiles + UD_NUM_SMS * waves - 1) / (UD_NUM_SMS * waves);
+    if (tiles < 1) tiles = 1;
+    if (tiles > tmax) tiles = tmax;
+    const int ctas = (n_tiles + tiles - 1) / tiles;
+    kern<<<ctas, NTHREADS, smem, stream>>>(in, wpacked, bias, nbr_t, n_out, K, tiles, out);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+
+// ================================================================================================
+// Variant "TS": the A operand goes through TMEM instead of shared memory.
+//
+// Shared-memory bandwidth bounds the SS kernel above (per 32-channel stage: 32 KB of hi/lo stores + 72 KB of
+// operand reads by the 12 MMAs).  Here a stage costs 16 KB (cp.async landing the raw fp32 rows) + 16 KB (one read
+// by the transform warps) + 24..48 KB (B reads):
+//   loader warps (4)     : prefetch the row indices, issue 16-byte cp.async (zero-fill for absent rows) into a
+//                          swizzled raw ring; completion is signalled by cp.async.mbarrier.arrive.noinc
+//   transform warps (2x4): thread == row.  Read the 128-byte row slice (conflict-free thanks to the swizzle),
+//                          split hi/lo in registers, tcgen05.st both halves into the stage's 64 TMEM columns
+//   MMA issuer (1 warp)  : tcgen05.mma kind::tf32 with A from TMEM, B (weights) from shared memory
+//   weight loader (1)    : as in the SS kernel
+// TMEM: columns [0, 256) accumulators (256/COUT tiles per CTA), [256, 512) four A stages of 32 hi + 32 lo columns.
+constexpr int TS_THREADS = 448;
+constexpr int TS_RAW_STAGES = 4;
+constexpr int TS_RAW_BYTES = TILE_M * 128;        // one [128 x 32] fp32 tile, raw
+constexpr int TS_A_STAGES = 4;
+constexpr int TS_ACC_COLS = 256;
+
+__host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
+                 const int* __restrict__ nbr_t, int n_out, int K, int tiles, float* __restrict__ out) {
+    constexpr int NCHUNK = CIN / KC;
+    constexpr int B_BYTES = COUT * 128;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                               ((uint32_t)(TILE_M >> 4) << 24);
+    static_assert(CIN % KC == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
+    constexpr int NBAR = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * B_STAGES + 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[NBAR];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int tile_mask_s[MAX_TILES];
+    __shared__ unsigned short a_sched[MAX_SCHED];          // tap | chunk << 5 | tile << 8
+    __shared__ unsigned short b_sched[MAX_TAPS * 4];       // tap | chunk << 5
+    __shared__ unsigned short b_count[MAX_TAPS * 4];       // A stages that use this weight slice
+    __shared__ int n_a_s, n_b_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int row0 = blockIdx.x * tiles * TILE_M;
+    const int rows_cta = min(tiles * TILE_M, n_out - row0);
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_base + TS_RAW_STAGES * TS_RAW_BYTES;
+    const uint32_t bar_raw_full = smem_u32(&bars[0]);
+    const uint32_t bar_raw_empty = smem_u32(&bars[TS_RAW_STAGES]);
+    const uint32_t bar_a_full = smem_u32(&bars[2 * TS_RAW_STAGES]);
+    const uint32_t bar_a_empty = smem_u32(&bars[2 * TS_RAW_STAGES + TS_A_STAGES]);
+    const uint32_t bar_b_full = smem_u32(&bars[2 * TS_RAW_STAGES + 2 * TS_A_STAGES]);
+    const uint32_t bar_b_empty = smem_u32(&bars[2 * TS_RAW_STAGES + 2 * TS_A_STAGES + B_STAGES]);
+    const uint32_t bar_acc = smem_u32(&bars[NBAR - 1]);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TS_RAW_STAGES; ++s) {
+            mbar_init(bar_raw_full + 8 * s, 128);       // one cp.async-completion arrive per loader thread
+            mbar_init(bar_raw_empty + 8 * s, 128);      // one arrive per transform thread
+        }
+#pragma unroll
+        for (int s = 0; s < TS_A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, 128);
+            mbar_init(bar_a_empty + 8 * s, 1);
+        }
+#pragma unroll
+        for (int s = 0; s < B_STAGES; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (tid < MAX_TILES) tile_mask_s[tid] = 0u;
+    if (warp == 12) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    {
+        const int segs = (rows_cta + 31) >> 5;                 // 32-row segments
+        for (int w = warp; w < K * segs; w += TS_THREADS / 32) {
+            const int k = w / segs, sg = w - k * segs;
+            const int r = sg * 32 + lane;
+            const int v = r < rows_cta ? __ldg(nbr_t + (size_t)k * n_out + row0 + r) : -1;
+            const unsigned any = __ballot_sync(0xffffffffu, v >= 0);
+            if (lane == 0 && any) atomicOr(&tile_mask_s[sg >> 2], 1u << k);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        unsigned int uni = 0u;
+        for (int t = 0; t < tiles; ++t) uni |= tile_mask_s[t];
+        int na = 0, nb = 0;
+        for (int k = 0; k < K; ++k) {
+            if (!((uni >> k) & 1u)) continue;
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                int cnt = 0;
+                for (int t = 0; t < tiles; ++t)
+                    if ((tile_mask_s[t] >> k) & 1u) {
+                        a_sched[na++] = (unsigned short)(k | (ch << 5) | (t << 8));
+                        ++cnt;
+                    }
+                b_sched[nb] = (unsigned short)(k | (ch << 5));
+                b_count[nb] = (unsigned short)cnt;
+                ++nb;
+            }
+        }
+        n_a_s = na;
+        n_b_s = nb;
+    }
+    __syncthreads();
+    const int n_a = n_a_s;
+    const int n_b = n_b_s;
+    const uint32_t tmem_acc = tmem_base_s;
+    const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+
+    if (warp < 8) {
+        // ============ transform: raw smem row -> hi/lo -> TMEM.  set g handles stages it = g, g+2, ... ============
+        const int g = warp >> 2;
+        const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                    // row of the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int it = g; it < n_a; it += 2) {
+            const int rslot = it % TS_RAW_STAGES;
+            const int aslot = it % TS_A_STAGES;
+            uint32_t v[32], lo[32];
+            mbar_wait(bar_raw_full + 8 * rslot, ((uint32_t)(it / TS_RAW_STAGES)) & 1u);
+            const unsigned char* rawp = smem_raw + (smem_base - smem_u32(smem_raw)) + rslot * TS_RAW_BYTES;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 x = *reinterpret_cast<const uint4*>(rawp + swz_off(r, c));
+                v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+            }
+            mbar_arrive(bar_raw_empty + 8 * rslot);     // values are in registers: the raw slot may be refilled
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t h = v[i] & 0xffffe000u;
+                lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
+                v[i] = h;
+            }
+            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / TS_A_STAGES)) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_a + lane_addr + (uint32_t)(aslot * 64);
+            tmem_st32(taddr, v);
+            tmem_st32(taddr + 32, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * aslot);
+        }
+    } else if (warp < 12) {
+        // ============ loaders: indices (prefetched one stage ahead) -> cp.async rows into the raw ring ============
+        const int tg = tid - 256;
+        const int chunk = tg & 7;                    // 16-byte chunk of the 128-byte row slice
+        const int rbase = tg >> 3;                   // rows rbase + 16*j, j = 0..7
+        int idx[8], idx_next[8];
+        auto load_idx = [&](int(&dst)[8], int it) {
+            const unsigned e = a_sched[it];
+            const int tap = e & 31, tile = e >> 8;
+            const int* col = nbr_t + (size_t)tap * n_out + row0 + tile * TILE_M;
+            const int lim = rows_cta - tile * TILE_M;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rr = rbase + 16 * j;
+                dst[j] = rr < lim ? __ldg(col + rr) : -1;
+            }
+        };
+        if (n_a > 0) load_idx(idx_next, 0);
+        for (int it = 0; it < n_a; ++it) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) idx[j] = idx_next[j];
+            if (it + 1 < n_a) load_idx(idx_next, it + 1);
+            const int rslot = it % TS_RAW_STAGES;
+            const int c0 = ((a_sched[it] >> 5) & 7) * KC + chunk * 4;
+            mbar_wait(bar_raw_empty + 8 * rslot, (((uint32_t)(it / TS_RAW_STAGES)) & 1u) ^ 1u);
+            const uint32_t dst0 = smem_base + rslot * TS_RAW_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int rr = rbase + 16 * j;
+                const bool ok = idx[j] >= 0;
+                const float* src = in + (ok ? ((size_t)idx[j] * CIN + c0) : 0);
+                cp_async_16(dst0 + swz_off(rr, chunk), src, ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(bar_raw_full + 8 * rslot);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == 12) {
+        // ============ MMA issuer ============
+        unsigned int started = 0u;
+        int it = 0;
+        for (int ib = 0; ib < n_b; ++ib) {
+            const int bslot = ib % B_STAGES;
+            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / B_STAGES)) & 1u);
+            const uint32_t b_hi = smem_b + bslot * 2 * B_BYTES;
+            const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_hi + B_BYTES);
+            const int cnt = b_count[ib];
+            for (int c = 0; c < cnt; ++c, ++it) {
+                const int aslot = it % TS_A_STAGES;
+                const int tile = a_sched[it] >> 8;
+                mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / TS_A_STAGES)) & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_hi = tmem_a + (uint32_t)(aslot * 64);
+                    const uint32_t a_lo = a_hi + 32;
+                    const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
+                    const uint32_t first = (started >> tile) & 1u;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);       // B: 8 fp32 = 32 B = 2 x 16 B
+                        const uint32_t acol = (uint32_t)(ks * 8);      // A: 8 TMEM columns
+                        umma_tf32_ts(d, a_lo + acol, db_hi + adv, IDESC, (first || ks > 0) ? 1u : 0u);
+                        umma_tf32_ts(d, a_hi + acol, db_lo + adv, IDESC, 1u);
+                        umma_tf32_ts(d, a_hi + acol, db_hi + adv, IDESC, 1u);
+                    }
+                    umma_commit(bar_a_empty + 8 * aslot);
+                }
+                started |= 1u << tile;
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(bar_b_empty + 8 * bslot);
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        // ============ weight loader ============
+        if (lane == 0) {
+            for (int ib = 0; ib < n_b; ++ib) {
+                const int bslot = ib % B_STAGES;
+                mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / B_STAGES)) & 1u) ^ 1u);
+                const unsigned e = b_sched[ib];
+                const int tap = e & 31, ch = e >> 5;
+                const float* src = wpacked + ((size_t)(tap * NCHUNK + ch) * 2) * COUT * KC;
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, 2 * B_BYTES);
+                bulk_g2s(smem_b + bslot * 2 * B_BYTES, src, 2 * B_BYTES, bar_b_full + 8 * bslot);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ============ epilogue (warps 0-7: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+2, ...) ============
+    if (warp < 8) {
+        if (n_a > 0) {
+            mbar_wait(bar_acc, 0u);
+            tc_fence_after();
+        }
+        const int q = warp & 3;
+        constexpr int CW = COUT >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int t = warp >> 2; t < tiles; t += 2) {
+            if (t * TILE_M >= rows_cta) break;
+            const bool has_acc = tile_mask_s[t] != 0u;       // warp-uniform
+            const int r_local = t * TILE_M + q * 32 + lane;
+            const int row = row0 + r_local;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                uint32_t v[32];
+                if (has_acc) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = 0u;
+                }
+                if (r_local < rows_cta) {
+                    float* dst = out + (size_t)row * COUT + c0;
+#pragma unroll
+                    for (int i = 0; i < CW; i += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(v[i + 0]);
+                        o.y = __uint_as_float(v[i + 1]);
+                        o.z = __uint_as_float(v[i + 2]);
+                        o.w = __uint_as_float(v[i + 3]);
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_acc, 512);
+}
+
+template <int CIN, int COUT>
+int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t, int n_out, int K,
+                   float* out, cudaStream_t stream) {
+    const size_t smem = (size_t)TS_RAW_STAGES * TS_RAW_BYTES + (size_t)B_STAGES * 2 * COUT * 128 + 1024;
+    auto kern = k_spconv_umma_ts<CIN, COUT>;
+    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    const int tmax = ts_tiles_max(COUT);
+    const int waves = (n_tiles + UD_NUM_SMS * tmax - 1) / (UD_NUM_SMS * tmax);
+    int tiles = (n_tiles + UD_NUM_SMS * waves - 1) / (UD_NUM_SMS * waves);
+    if (tiles < 1) tiles = 1;
+    if (tiles > tmax) tiles = tmax;
+    const int ctas = (n_tiles + tiles - 1) / tiles;
+    kern<<<ctas, TS_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, n_out, K, tiles, out);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -390,8 +827,10 @@ bool tc_shape_ok(int K, int cin, int cout) {
 
 }  // namespace
 
-#define UD_DISPATCH_UMMA(CI, CO) \
-    if (cin == CI && cout == CO) return launch_umma<CI, CO>(in, wpacked, bias, nbr, n_out, K, out, stream);
+#define UD_DISPATCH_UMMA(CI, CO)                                                                          \
+    if (cin == CI && cout == CO)                                                                          \
+        return variant == 1 ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, n_out, K, out, stream)        \
+                            : launch_umma_ts<CI, CO>(in, wpacked, bias, nbr_t, n_out, K, out, stream);
 
 extern "C" {
 
@@ -416,13 +855,24 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     return UD_OK;
 }
 
+// nbr (n, K) int32 row-major gather table -> nbr_t (K, n) tap-major, the form ud_sparse_conv_tc_forward reads.
+int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || K < 1 || K > MAX_TAPS || (n > 0 && (!nbr || !nbr_t))) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    k_transpose_table<<<ud_blocks(n, 32), 256, 0, stream>>>(nbr, n, K, nbr_t);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
 // in (n_in, cin) f32, 16-byte aligned rows; wpacked from ud_sparse_conv_tc_pack_weights; bias (cout)|NULL;
-// nbr (n_out, K) int32; out (n_out, cout) f32.
-int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr, int n_out,
-                              int K, int cin, int cout, float* out, void* stream_) {
+// nbr_t (K, n_out) int32 tap-major gather table (ud_rulebook_transpose); out (n_out, cout) f32.
+// variant: 0 = default (A operand through TMEM, "TS"), 1 = A operand through shared memory ("SS").
+int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t, int n_out,
+                              int K, int cin, int cout, float* out, int variant, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* wpacked = (const float*)wpacked_;
-    if (!in || !wpacked || !nbr || !out || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (!in || !wpacked || !nbr_t || !out || n_out < 0) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
     if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out) & 15u) != 0) return UD_ERR_INVALID_ARG;
     if (n_out == 0) return UD_OK;

@@ -33,7 +33,22 @@ class Rulebook:
         self.batch_size = batch_size
         self.K = ksize[0] * ksize[1] * ksize[2]
         self._pairs = None
+        self._tap_major = {}
         self.in_coords_for_inverse = None
+
+    def tap_major(self, table):
+        """(K, n) transposed copy of one of this rulebook's (n, K) tables, built once and cached
+        (the tensor-core kernel reads the 128 indices of a (tile, tap) as one contiguous segment)."""
+        key = table.data_ptr()
+        t = self._tap_major.get(key)
+        if t is None:
+            n, K = int(table.shape[0]), int(table.shape[1])
+            t = torch.empty((K, n), dtype=torch.int32, device=table.device)
+            rc = native.load().ud_rulebook_transpose(native.ptr(table), n, K, native.ptr(t),
+                                                     native.stream_ptr(table.device))
+            native.check(rc, "ud_rulebook_transpose")
+            self._tap_major[key] = t
+        return t
 
     def num_pairs(self):
         """Number of (input,output) pairs == rulebook size P (host sync; for reporting only)."""
@@ -122,9 +137,10 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 # tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
 # every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
+TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))   # 0: A through TMEM (default), 1: A through smem
 
 
-def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout):
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
     lib = native.load()
     dev = feats.device
     out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
@@ -137,10 +153,11 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout):
         rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
         native.check(rc, "ud_sparse_conv_tc_pack_weights")
         if meta is not None:
-            meta["kernel"] = "k_spconv_umma"
+            meta["kernel"] = "k_spconv_umma_ts" if TC_VARIANT == 0 else "k_spconv_umma"
+        table_t = rb.tap_major(table) if rb is not None else table.t().contiguous()
         rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
-                               native.ptr(packed), native.ptr(bias), native.ptr(table), n_out, K, cin, cout,
-                               native.ptr(out), sp)
+                               native.ptr(packed), native.ptr(bias), native.ptr(table_t), n_out, K, cin, cout,
+                               native.ptr(out), TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_forward")
         return out
     if meta is not None:
@@ -174,7 +191,7 @@ class SparseConvFunction(Function):
             table, n_out = rb.nbr_in, rb.n_in
         assert features.shape[1] == cin, "feature width %d != conv in_channels %d" % (features.shape[1], cin)
         b = bias.detach().float().contiguous() if bias is not None else None
-        out = _conv_forward_raw(features, w_k, b, table, n_out, rb.K, cin, cout)
+        out = _conv_forward_raw(features, w_k, b, table, n_out, rb.K, cin, cout, rb)
         ctx.rb, ctx.inverse = rb, inverse
         ctx.has_bias = bias is not None
         ctx.wshape = tuple(weight.shape)
@@ -199,7 +216,7 @@ class SparseConvFunction(Function):
             else:
                 w_t = w_k.transpose(1, 2).contiguous()
                 table, n_in = rb.nbr_out, rb.n_out
-            dfeat = _conv_forward_raw(grad_out, w_t, None, table, n_in, K, cout, cin)
+            dfeat = _conv_forward_raw(grad_out, w_t, None, table, n_in, K, cout, cin, rb)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros((K, cin, cout), dtype=torch.float32, device=grad_out.device)
             if not inverse:

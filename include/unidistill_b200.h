@@ -101,8 +101,11 @@ int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int
 int ud_sparse_conv_tc_supported(int K, int cin, int cout);
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
 int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
-int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr, int n_out,
-                              int K, int cin, int cout, float* out, void* stream);
+/* nbr (n,K) row-major gather table -> nbr_t (K,n) tap-major, the form the tensor-core kernel reads */
+int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, void* stream);
+/* variant 0 = default kernel (A operand staged through TMEM), 1 = A operand staged through shared memory */
+int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t, int n_out,
+                              int K, int cin, int cout, float* out, int variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /

@@ -195,7 +195,8 @@ def test_subm_conv_forward_parity(cuda, native_lib, cin, cout):
     rp, rpn = O.rulebook_subm(coords, shape, 3)
     ref = O.sparse_conv_c(feat, w, bias, rp, rpn, n)
     err = _rel_err(out.cpu().numpy(), ref)
-    assert err < 1e-5, "fp32 SIMT path should agree to ~1e-6, got %g" % err
+    # fp32 SIMT kernel: ~1e-6; tensor-core (3xTF32, RZ accumulation in the MMA) channel pairs: ~1e-5
+    assert err < 5e-5, "sparse conv forward rel err %g" % err
 
 
 @pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(16, 32, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
@@ -212,7 +213,7 @@ def test_strided_conv_forward_parity(cuda, native_lib, cin, cout, ksize, stride,
     out = sparse.sparse_conv(torch.from_numpy(feat).to(cuda), torch.from_numpy(w).to(cuda), None, rb)
     oc, rp, rpn, osh = O.rulebook_conv(coords, shape, ksize, stride, pad)
     ref = O.sparse_conv_c(feat, w, None, rp, rpn, oc.shape[0])
-    assert _rel_err(out.cpu().numpy(), ref) < 1e-5
+    assert _rel_err(out.cpu().numpy(), ref) < 5e-5
 
 
 def _torch_ref_conv(feat, w, bias, pairs, pn, n_out):
@@ -262,7 +263,7 @@ def test_conv_backward_parity(cuda, native_lib, cin, cout, strided):
     ref = _torch_ref_conv(f_c, w_c, b_c, rp, rpn, n_out)
     ref.backward(torch.from_numpy(gout))
 
-    assert _rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert _rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 5e-5
     assert _rel_err(f_g.grad.cpu().numpy(), f_c.grad.numpy()) < 1e-4, "dgrad"
     assert _rel_err(w_g.grad.cpu().numpy(), w_c.grad.numpy()) < 1e-4, "wgrad"
     if bias is not None:

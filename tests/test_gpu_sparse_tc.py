@@ -1,7 +1,8 @@
 """Tensor-core (tcgen05 / TMEM, 3xTF32) sparse convolution vs the C oracle and vs the fp32 SIMT kernel.
 
 Tolerance: BASELINE.json's north_star allows 1e-3 relative for fp32 features; the hi/lo operand split keeps
-the tensor-core path at ~1e-6, and the bound asserted here is 2e-5 relative to the largest output.
+the tensor-core path at ~1e-5 (the MMA accumulates with truncation), asserted here as 5e-5 relative to the
+largest output.  Both kernel variants (A operand through TMEM / through shared memory) are covered.
 """
 import numpy as np
 import pytest
@@ -10,7 +11,7 @@ import torch
 from oracle import lidar as O
 
 pytestmark = pytest.mark.gpu
-TC_TOL = 2e-5
+TC_TOL = 5e-5
 
 
 def _cloud(rng, B, shape, n, C):
@@ -23,6 +24,16 @@ def _cloud(rng, B, shape, n, C):
     coords = np.stack([b, z, y, x], 1).astype(np.int32)
     feat = rng.standard_normal((n, C)).astype(np.float32)
     return coords, feat
+
+
+@pytest.fixture(params=[0, 1], ids=["A-via-TMEM", "A-via-smem"], autouse=True)
+def tc_variant(request):
+    from unidistill_b200 import sparse
+
+    old = sparse.TC_VARIANT
+    sparse.TC_VARIANT = request.param
+    yield request.param
+    sparse.TC_VARIANT = old
 
 
 def _rel(a, b):

@@ -58,6 +58,8 @@ def main():
             ("subm", 128, 128, None), ("down", 128, 128, ((3, 1, 1), (2, 1, 1), 0))]
     cur_coords, cur_shape = coords, shape
     rb = None
+    only = os.environ.get("UD_MB_ONLY")          # e.g. "64,64": time just that layer, forward only (for ncu)
+    only = tuple(int(v) for v in only.split(",")) if only else None
     for kind, cin, cout, geo in plan:
         if kind == "subm":
             if rb is None or not rb.subm or rb.n_in != cur_coords.shape[0]:
@@ -69,6 +71,11 @@ def main():
             ms, rb = timed(lambda: sparse.build_conv_rulebook(cur_coords, bs, cur_shape, ks, st, pd))
             rows.append(("rulebook conv N=%d->%d" % (rb.n_in, rb.n_out), ms,
                          rb.n_in * 16 + (rb.n_in + rb.n_out) * rb.K * 4 + rb.n_out * 16, 0))
+        if only is not None and (cin, cout) != only:
+            if kind == "down":
+                cur_coords, cur_shape = rb.out_coords, rb.out_shape
+                rb = None
+            continue
         P = rb.num_pairs()
         x = torch.randn((rb.n_in, cin), device=dev)
         ks3 = rb.ksize
@@ -89,6 +96,11 @@ def main():
             with torch.no_grad():
                 ms, _ = timed(lambda: sparse.batch_norm_act(out, bn, relu=True))
             rows.append(("bn+relu(train) N=%d C=%d" % (out.shape[0], cout), ms, out.numel() * 4 * 3, 0))
+        if only is not None:
+            if kind == "down":
+                cur_coords, cur_shape = rb.out_coords, rb.out_shape
+                rb = None
+            continue
         # backward kernels
         xg = x.clone().requires_grad_(True)
         wg = w.clone().requires_grad_(True)
