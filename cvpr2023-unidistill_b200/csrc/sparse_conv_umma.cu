@@ -174,9 +174,10 @@ k_pack_weights(const float* __restrict__ w, int K, int cin, int cout, float* __r
     packed[base + (size_t)cout * KC + (size_t)n * KC + pos] = lo;
 }
 
-// [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment
+// [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
+// tile_masks[row / 128] |= 1 << k for every tap k that occurs in the 128-row tile (zeroed by the launcher).
 __global__ void __launch_bounds__(256)
-k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ dst) {
+k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ dst, unsigned int* __restrict__ tile_masks) {
     __shared__ int tile[32][33];
     const int r0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
@@ -185,10 +186,52 @@ k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ d
         tile[i][tx] = (r < n && tx < K) ? src[(size_t)r * K + tx] : -1;
     }
     __syncthreads();
+    unsigned int m = 0u;
     for (int k = ty; k < K; k += 8) {
         const int r = r0 + tx;
-        if (r < n) dst[(size_t)k * n + r] = tile[tx][k];
+        const int v = tile[tx][k];
+        if (r < n) dst[(size_t)k * n + r] = v;
+        const unsigned any = __ballot_sync(0xffffffffu, r < n && v >= 0);
+        if (any) m |= 1u << k;
     }
+    if (tile_masks && tx == 0 && m) atomicOr(tile_masks + (r0 >> 7), m);
+}
+
+// Builds the stage schedule of a CTA from the tap masks of its tiles (warp 0, lane == tap): for every tap present,
+// for every channel chunk, one weight slice (b_sched) followed by one A stage per tile that has the tap (a_sched).
+template <int NCHUNK>
+__device__ __forceinline__ void build_schedule(const unsigned int* tile_mask_s, int tiles, int K, int lane,
+                                               unsigned short* a_sched, unsigned short* b_sched,
+                                               unsigned short* b_count, int* n_a_s, int* n_b_s) {
+    unsigned int tm = 0u;                                 // bit t: tile t has tap `lane`
+    if (lane < K)
+        for (int t = 0; t < tiles; ++t) tm |= ((tile_mask_s[t] >> lane) & 1u) << t;
+    const int cnt = __popc(tm);
+    const unsigned active = __ballot_sync(0xffffffffu, cnt > 0);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int a_base = (incl - cnt) * NCHUNK;
+    const int b_base = __popc(active & ((1u << lane) - 1u)) * NCHUNK;
+    if (cnt > 0) {
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            b_sched[b_base + ch] = (unsigned short)(lane | (ch << 5));
+            b_count[b_base + ch] = (unsigned short)cnt;
+            unsigned int rem = tm;
+            int j = 0;
+            while (rem) {
+                const int t = __ffs(rem) - 1;
+                rem &= rem - 1;
+                a_sched[a_base + ch * cnt + j] = (unsigned short)(lane | (ch << 5) | (t << 8));
+                ++j;
+            }
+        }
+    }
+    if (lane == 31) *n_a_s = incl * NCHUNK;
+    if (lane == 0) *n_b_s = __popc(active) * NCHUNK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,7 +242,8 @@ k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ d
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
-              const int* __restrict__ nbr_t, int n_out, int K, int tiles, float* __restrict__ out) {
+              const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K, int tiles,
+              float* __restrict__ out) {
     constexpr int NCHUNK = CIN / KC;
     constexpr int A_BYTES = TILE_M * 128;            // one [128 x 32] fp32 operand tile
     constexpr int B_BYTES = COUT * 128;
@@ -246,45 +290,16 @@ k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, c
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (tid < MAX_TILES) tile_mask_s[tid] = 0u;
+    if (tid < MAX_TILES) {
+        const int tile_g = blockIdx.x * tiles + tid;
+        tile_mask_s[tid] = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+    }
     if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
     __syncthreads();
-    // ---- which taps occur in which tile (one coalesced pass over the CTA's slice of the table) ----
-    {
-        const int segs = (rows_cta + 31) >> 5;                 // 32-row segments
-        for (int w = warp; w < K * segs; w += NTHREADS / 32) {
-            const int k = w / segs, sg = w - k * segs;
-            const int r = sg * 32 + lane;
-            const int v = r < rows_cta ? __ldg(nbr_t + (size_t)k * n_out + row0 + r) : -1;
-            const unsigned any = __ballot_sync(0xffffffffu, v >= 0);
-            if (lane == 0 && any) atomicOr(&tile_mask_s[sg >> 2], 1u << k);
-        }
-    }
+    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
-        unsigned int uni = 0u;
-        for (int t = 0; t < tiles; ++t) uni |= tile_mask_s[t];
-        int na = 0, nb = 0;
-        for (int k = 0; k < K; ++k) {
-            if (!((uni >> k) & 1u)) continue;
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                int cnt = 0;
-                for (int t = 0; t < tiles; ++t)
-                    if ((tile_mask_s[t] >> k) & 1u) {
-                        a_sched[na++] = (unsigned short)(k | (ch << 5) | (t << 8));
-                        ++cnt;
-                    }
-                b_sched[nb] = (unsigned short)(k | (ch << 5));
-                b_count[nb] = (unsigned short)cnt;
-                ++nb;
-            }
-        }
-        n_a_s = na;
-        n_b_s = nb;
-    }
-    __syncthreads();
     const int n_a = n_a_s;
     const int n_b = n_b_s;
     const uint32_t tmem_acc = tmem_base_s;
@@ -455,8 +470,8 @@ k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, c
 }
 
 template <int CIN, int COUT>
-int launch_umma(const float* in, const float* wpacked, const float* bias, const int* nbr_t, int n_out, int K,
-                float* out, cudaStream_t stream) {
+int launch_umma(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                const unsigned int* tile_masks, int n_out, int K, float* out, cudaStream_t stream) {
     const size_t smem = (size_t)A_STAGES * A_STAGE_BYTES + (size_t)B_STAGES * 2 * COUT * 128 + 1024;
     auto kern = k_spconv_umma<CIN, COUT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -468,7 +483,7 @@ int launch_umma(const float* in, const float* wpacked, const float* bias, const 
     if (tiles < 1) tiles = 1;
     if (tiles > tmax) tiles = tmax;
     const int ctas = (n_tiles + tiles - 1) / tiles;
-    kern<<<ctas, NTHREADS, smem, stream>>>(in, wpacked, bias, nbr_t, n_out, K, tiles, out);
+    kern<<<ctas, NTHREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -487,7 +502,8 @@ int launch_umma(const float* in, const float* wpacked, const float* bias, const 
 //   MMA issuer (1 warp)  : tcgen05.mma kind::tf32 with A from TMEM, B (weights) from shared memory
 //   weight loader (1)    : as in the SS kernel
 // TMEM: columns [0, 256) accumulators (256/COUT tiles per CTA), [256, 512) four A stages of 32 hi + 32 lo columns.
-constexpr int TS_THREADS = 448;
+constexpr int TS_THREADS = 576;          // 8 transform + 8 loader + MMA + weight-loader warps
+constexpr int TS_LOADER_THREADS = 256;
 constexpr int TS_RAW_STAGES = 4;
 constexpr int TS_RAW_BYTES = TILE_M * 128;        // one [128 x 32] fp32 tile, raw
 constexpr int TS_A_STAGES = 4;
@@ -527,10 +543,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// Optional role-level cycle accounting (development aid): when ud_debug_umma_prof() installed a buffer, every
+// role adds the cycles it spent waiting / working to prof[slot]; nullptr (the default) costs one load per CTA.
+__device__ unsigned long long* g_umma_prof = nullptr;
+enum { PF_MMA_WAIT_A = 0, PF_MMA_WAIT_B, PF_MMA_TOTAL, PF_TR_WAIT_RAW, PF_TR_WAIT_A, PF_TR_TOTAL, PF_LD_WAIT_RAW,
+       PF_LD_TOTAL, PF_PROLOGUE, PF_EPILOGUE, PF_CTA_TOTAL, PF_CTAS, PF_STAGES, PF_COUNT };
+#define PF_T() (prof ? clock64() : 0ll)
+#define PF_ADD(slot, v) do { if (prof && lane == 0) atomicAdd(prof + (slot), (unsigned long long)(v)); } while (0)
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
-                 const int* __restrict__ nbr_t, int n_out, int K, int tiles, float* __restrict__ out) {
+                 const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K, int tiles,
+              float* __restrict__ out) {
     constexpr int NCHUNK = CIN / KC;
     constexpr int B_BYTES = COUT * 128;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
@@ -554,6 +579,8 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     const int row0 = blockIdx.x * tiles * TILE_M;
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
 
+    unsigned long long* const prof = g_umma_prof;
+    const long long t_cta0 = PF_T();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_b = smem_base + TS_RAW_STAGES * TS_RAW_BYTES;
     const uint32_t bar_raw_full = smem_u32(&bars[0]);
@@ -567,7 +594,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < TS_RAW_STAGES; ++s) {
-            mbar_init(bar_raw_full + 8 * s, 128);       // one cp.async-completion arrive per loader thread
+            mbar_init(bar_raw_full + 8 * s, TS_LOADER_THREADS);   // one cp.async-completion arrive per loader thread
             mbar_init(bar_raw_empty + 8 * s, 128);      // one arrive per transform thread
         }
 #pragma unroll
@@ -583,48 +610,22 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (tid < MAX_TILES) tile_mask_s[tid] = 0u;
-    if (warp == 12) tmem_alloc(smem_u32(&tmem_base_s), 512);
-    __syncthreads();
-    {
-        const int segs = (rows_cta + 31) >> 5;                 // 32-row segments
-        for (int w = warp; w < K * segs; w += TS_THREADS / 32) {
-            const int k = w / segs, sg = w - k * segs;
-            const int r = sg * 32 + lane;
-            const int v = r < rows_cta ? __ldg(nbr_t + (size_t)k * n_out + row0 + r) : -1;
-            const unsigned any = __ballot_sync(0xffffffffu, v >= 0);
-            if (lane == 0 && any) atomicOr(&tile_mask_s[sg >> 2], 1u << k);
-        }
+    if (tid < MAX_TILES) {
+        const int tile_g = blockIdx.x * tiles + tid;
+        tile_mask_s[tid] = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
     }
+    if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
-        unsigned int uni = 0u;
-        for (int t = 0; t < tiles; ++t) uni |= tile_mask_s[t];
-        int na = 0, nb = 0;
-        for (int k = 0; k < K; ++k) {
-            if (!((uni >> k) & 1u)) continue;
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                int cnt = 0;
-                for (int t = 0; t < tiles; ++t)
-                    if ((tile_mask_s[t] >> k) & 1u) {
-                        a_sched[na++] = (unsigned short)(k | (ch << 5) | (t << 8));
-                        ++cnt;
-                    }
-                b_sched[nb] = (unsigned short)(k | (ch << 5));
-                b_count[nb] = (unsigned short)cnt;
-                ++nb;
-            }
-        }
-        n_a_s = na;
-        n_b_s = nb;
-    }
-    __syncthreads();
     const int n_a = n_a_s;
     const int n_b = n_b_s;
     const uint32_t tmem_acc = tmem_base_s;
     const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+    const long long t_main0 = PF_T();
+    if (warp == 0) { PF_ADD(PF_PROLOGUE, t_main0 - t_cta0); PF_ADD(PF_CTAS, 1); PF_ADD(PF_STAGES, n_a); }
 
     if (warp < 8) {
         // ============ transform: raw smem row -> hi/lo -> TMEM.  set g handles stages it = g, g+2, ... ============
@@ -632,11 +633,14 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         const int q = warp & 3;                         // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;                    // row of the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        long long w_raw = 0, w_a = 0;
         for (int it = g; it < n_a; it += 2) {
             const int rslot = it % TS_RAW_STAGES;
             const int aslot = it % TS_A_STAGES;
             uint32_t v[32], lo[32];
+            long long tw = PF_T();
             mbar_wait(bar_raw_full + 8 * rslot, ((uint32_t)(it / TS_RAW_STAGES)) & 1u);
+            w_raw += PF_T() - tw;
             const unsigned char* rawp = smem_raw + (smem_base - smem_u32(smem_raw)) + rslot * TS_RAW_BYTES;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -650,7 +654,9 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                 lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
                 v[i] = h;
             }
+            tw = PF_T();
             mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / TS_A_STAGES)) & 1u) ^ 1u);
+            w_a += PF_T() - tw;
             tc_fence_after();
             const uint32_t taddr = tmem_a + lane_addr + (uint32_t)(aslot * 64);
             tmem_st32(taddr, v);
@@ -659,35 +665,51 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             tc_fence_before();
             mbar_arrive(bar_a_full + 8 * aslot);
         }
-    } else if (warp < 12) {
-        // ============ loaders: indices (prefetched one stage ahead) -> cp.async rows into the raw ring ============
+        if (q == 0) { PF_ADD(PF_TR_WAIT_RAW, w_raw); PF_ADD(PF_TR_WAIT_A, w_a); PF_ADD(PF_TR_TOTAL, PF_T() - t_main0); }
+    } else if (warp < 16) {
+        // ============ loaders: indices (L2-prefetched 8 stages ahead, loaded one stage ahead) -> cp.async rows ============
+        constexpr int RPT = TILE_M * 8 / TS_LOADER_THREADS;       // rows per thread and stage
+        constexpr int RSTEP = TS_LOADER_THREADS / 8;
         const int tg = tid - 256;
         const int chunk = tg & 7;                    // 16-byte chunk of the 128-byte row slice
-        const int rbase = tg >> 3;                   // rows rbase + 16*j, j = 0..7
-        int idx[8], idx_next[8];
-        auto load_idx = [&](int(&dst)[8], int it) {
+        const int rbase = tg >> 3;                   // rows rbase + RSTEP*j
+        int idx[RPT], idx_next[RPT];
+        auto seg_ptr = [&](int it) {
             const unsigned e = a_sched[it];
-            const int tap = e & 31, tile = e >> 8;
-            const int* col = nbr_t + (size_t)tap * n_out + row0 + tile * TILE_M;
-            const int lim = rows_cta - tile * TILE_M;
+            return nbr_t + (size_t)(e & 31) * n_out + row0 + (e >> 8) * TILE_M;
+        };
+        auto load_idx = [&](int(&dst)[RPT], int it) {
+            const int* col = seg_ptr(it);
+            const int lim = rows_cta - (a_sched[it] >> 8) * TILE_M;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rr = rbase + 16 * j;
+            for (int j = 0; j < RPT; ++j) {
+                const int rr = rbase + RSTEP * j;
                 dst[j] = rr < lim ? __ldg(col + rr) : -1;
             }
         };
+        auto prefetch_idx = [&](int it) {            // 512-byte index segment = 4 lines: lanes 0..3 of warp 8
+            if (tg < 4 && it < n_a) {
+                const int* p = seg_ptr(it) + tg * 32;
+                if (p < nbr_t + (size_t)K * n_out) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        };
+        for (int it = 0; it < 8; ++it) prefetch_idx(it);
+        long long w_raw = 0;
         if (n_a > 0) load_idx(idx_next, 0);
         for (int it = 0; it < n_a; ++it) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) idx[j] = idx_next[j];
+            for (int j = 0; j < RPT; ++j) idx[j] = idx_next[j];
             if (it + 1 < n_a) load_idx(idx_next, it + 1);
+            prefetch_idx(it + 8);
             const int rslot = it % TS_RAW_STAGES;
             const int c0 = ((a_sched[it] >> 5) & 7) * KC + chunk * 4;
+            const long long tw = PF_T();
             mbar_wait(bar_raw_empty + 8 * rslot, (((uint32_t)(it / TS_RAW_STAGES)) & 1u) ^ 1u);
+            w_raw += PF_T() - tw;
             const uint32_t dst0 = smem_base + rslot * TS_RAW_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int rr = rbase + 16 * j;
+            for (int j = 0; j < RPT; ++j) {
+                const int rr = rbase + RSTEP * j;
                 const bool ok = idx[j] >= 0;
                 const float* src = in + (ok ? ((size_t)idx[j] * CIN + c0) : 0);
                 cp_async_16(dst0 + swz_off(rr, chunk), src, ok ? 16u : 0u);
@@ -695,20 +717,26 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             cp_async_arrive_noinc(bar_raw_full + 8 * rslot);
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 12) {
+        if (warp == 8) { PF_ADD(PF_LD_WAIT_RAW, w_raw); PF_ADD(PF_LD_TOTAL, PF_T() - t_main0); }
+    } else if (warp == 16) {
         // ============ MMA issuer ============
         unsigned int started = 0u;
         int it = 0;
+        long long w_a = 0, w_b = 0;
         for (int ib = 0; ib < n_b; ++ib) {
             const int bslot = ib % B_STAGES;
+            long long tw = PF_T();
             mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / B_STAGES)) & 1u);
+            w_b += PF_T() - tw;
             const uint32_t b_hi = smem_b + bslot * 2 * B_BYTES;
             const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_hi + B_BYTES);
             const int cnt = b_count[ib];
             for (int c = 0; c < cnt; ++c, ++it) {
                 const int aslot = it % TS_A_STAGES;
                 const int tile = a_sched[it] >> 8;
+                tw = PF_T();
                 mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / TS_A_STAGES)) & 1u);
+                w_a += PF_T() - tw;
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t a_hi = tmem_a + (uint32_t)(aslot * 64);
@@ -733,6 +761,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         }
         if (elect_one_sync()) umma_commit(bar_acc);
         __syncwarp();
+        PF_ADD(PF_MMA_WAIT_A, w_a); PF_ADD(PF_MMA_WAIT_B, w_b); PF_ADD(PF_MMA_TOTAL, PF_T() - t_main0);
     } else {
         // ============ weight loader ============
         if (lane == 0) {
@@ -749,6 +778,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         __syncwarp();
     }
 
+    const long long t_epi0 = PF_T();
     // ============ epilogue (warps 0-7: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+2, ...) ============
     if (warp < 8) {
         if (n_a > 0) {
@@ -795,12 +825,13 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_acc, 512);
+    if (warp == 0) { const long long t_end = PF_T(); PF_ADD(PF_EPILOGUE, t_end - t_epi0); PF_ADD(PF_CTA_TOTAL, t_end - t_cta0); }
+    if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
 template <int CIN, int COUT>
-int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t, int n_out, int K,
-                   float* out, cudaStream_t stream) {
+int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                   const unsigned int* tile_masks, int n_out, int K, float* out, cudaStream_t stream) {
     const size_t smem = (size_t)TS_RAW_STAGES * TS_RAW_BYTES + (size_t)B_STAGES * 2 * COUT * 128 + 1024;
     auto kern = k_spconv_umma_ts<CIN, COUT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -811,7 +842,7 @@ int launch_umma_ts(const float* in, const float* wpacked, const float* bias, con
     if (tiles < 1) tiles = 1;
     if (tiles > tmax) tiles = tmax;
     const int ctas = (n_tiles + tiles - 1) / tiles;
-    kern<<<ctas, TS_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, n_out, K, tiles, out);
+    kern<<<ctas, TS_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -829,10 +860,17 @@ bool tc_shape_ok(int K, int cin, int cout) {
 
 #define UD_DISPATCH_UMMA(CI, CO)                                                                          \
     if (cin == CI && cout == CO)                                                                          \
-        return variant == 1 ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, n_out, K, out, stream)        \
-                            : launch_umma_ts<CI, CO>(in, wpacked, bias, nbr_t, n_out, K, out, stream);
+        return variant == 1 ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)    \
+                            : launch_umma_ts<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
 
 extern "C" {
+
+// Development aid: device buffer of 16 uint64 the tensor-core kernel adds role-level cycle counts to (NULL = off).
+int ud_debug_umma_prof(void* buf) {
+    unsigned long long* p = (unsigned long long*)buf;
+    UD_CUDA_TRY(cudaMemcpyToSymbol(g_umma_prof, &p, sizeof(p)));
+    return UD_OK;
+}
 
 // 1 when (K, cin, cout) has a tensor-core instantiation, else 0.
 int ud_sparse_conv_tc_supported(int K, int cin, int cout) { return tc_shape_ok(K, cin, cout) ? 1 : 0; }
@@ -855,24 +893,28 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     return UD_OK;
 }
 
-// nbr (n, K) int32 row-major gather table -> nbr_t (K, n) tap-major, the form ud_sparse_conv_tc_forward reads.
-int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, void* stream_) {
+// nbr (n, K) int32 row-major gather table -> nbr_t (K, n) tap-major + tile_masks (ceil(n/128)) uint32 (bit k set
+// when tap k occurs in the 128-row tile): the two inputs ud_sparse_conv_tc_forward reads.
+int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (n < 0 || K < 1 || K > MAX_TAPS || (n > 0 && (!nbr || !nbr_t))) return UD_ERR_INVALID_ARG;
+    if (n < 0 || K < 1 || K > MAX_TAPS || (n > 0 && (!nbr || !nbr_t || !tile_masks))) return UD_ERR_INVALID_ARG;
     if (n == 0) return UD_OK;
-    k_transpose_table<<<ud_blocks(n, 32), 256, 0, stream>>>(nbr, n, K, nbr_t);
+    UD_CUDA_TRY(cudaMemsetAsync(tile_masks, 0, sizeof(unsigned int) * (size_t)((n + TILE_M - 1) / TILE_M), stream));
+    k_transpose_table<<<ud_blocks(n, 32), 256, 0, stream>>>(nbr, n, K, nbr_t, tile_masks);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
 
 // in (n_in, cin) f32, 16-byte aligned rows; wpacked from ud_sparse_conv_tc_pack_weights; bias (cout)|NULL;
-// nbr_t (K, n_out) int32 tap-major gather table (ud_rulebook_transpose); out (n_out, cout) f32.
+// nbr_t (K, n_out) int32 tap-major gather table and tile_masks (ceil(n_out/128)) from ud_rulebook_transpose;
+// out (n_out, cout) f32.
 // variant: 0 = default (A operand through TMEM, "TS"), 1 = A operand through shared memory ("SS").
-int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t, int n_out,
-                              int K, int cin, int cout, float* out, int variant, void* stream_) {
+int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
+                              const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
+                              int variant, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* wpacked = (const float*)wpacked_;
-    if (!in || !wpacked || !nbr_t || !out || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (!in || !wpacked || !nbr_t || !tile_masks || !out || n_out < 0) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
     if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out) & 15u) != 0) return UD_ERR_INVALID_ARG;
     if (n_out == 0) return UD_OK;

@@ -37,18 +37,28 @@ class Rulebook:
         self.in_coords_for_inverse = None
 
     def tap_major(self, table):
-        """(K, n) transposed copy of one of this rulebook's (n, K) tables, built once and cached
-        (the tensor-core kernel reads the 128 indices of a (tile, tap) as one contiguous segment)."""
+        """((K, n) transposed copy, (ceil(n/128),) per-tile tap masks) of one of this rulebook's (n, K) tables,
+        built once and cached (the tensor-core kernel reads the 128 indices of a (tile, tap) as one contiguous
+        segment and schedules only the taps that occur in a tile)."""
         key = table.data_ptr()
         t = self._tap_major.get(key)
         if t is None:
             n, K = int(table.shape[0]), int(table.shape[1])
-            t = torch.empty((K, n), dtype=torch.int32, device=table.device)
-            rc = native.load().ud_rulebook_transpose(native.ptr(table), n, K, native.ptr(t),
+            tt = torch.empty((K, n), dtype=torch.int32, device=table.device)
+            masks = torch.empty(((n + 127) // 128,), dtype=torch.int32, device=table.device)
+            rc = native.load().ud_rulebook_transpose(native.ptr(table), n, K, native.ptr(tt), native.ptr(masks),
                                                      native.stream_ptr(table.device))
             native.check(rc, "ud_rulebook_transpose")
+            t = (tt, masks)
             self._tap_major[key] = t
         return t
+
+    @classmethod
+    def for_table(cls, table):
+        """Minimal holder for a bare (n, K) gather table (functional API without a Rulebook)."""
+        rb = cls.__new__(cls)
+        rb._tap_major = {}
+        return rb
 
     def num_pairs(self):
         """Number of (input,output) pairs == rulebook size P (host sync; for reporting only)."""
@@ -154,10 +164,10 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
         native.check(rc, "ud_sparse_conv_tc_pack_weights")
         if meta is not None:
             meta["kernel"] = "k_spconv_umma_ts" if TC_VARIANT == 0 else "k_spconv_umma"
-        table_t = rb.tap_major(table) if rb is not None else table.t().contiguous()
+        table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
         rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
-                               native.ptr(packed), native.ptr(bias), native.ptr(table_t), n_out, K, cin, cout,
-                               native.ptr(out), TC_VARIANT, sp)
+                               native.ptr(packed), native.ptr(bias), native.ptr(table_t), native.ptr(masks), n_out, K,
+                               cin, cout, native.ptr(out), TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_forward")
         return out
     if meta is not None:

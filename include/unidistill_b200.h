@@ -101,11 +101,15 @@ int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int
 int ud_sparse_conv_tc_supported(int K, int cin, int cout);
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
 int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
-/* nbr (n,K) row-major gather table -> nbr_t (K,n) tap-major, the form the tensor-core kernel reads */
-int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, void* stream);
+/* development aid: device buffer of 16 uint64 receiving role-level cycle counts of the tensor-core kernel; NULL = off */
+int ud_debug_umma_prof(void* buf);
+/* nbr (n,K) row-major gather table -> nbr_t (K,n) tap-major + tile_masks (ceil(n/128)) uint32 with bit k set when tap k
+ * occurs in that 128-row tile: the two table forms the tensor-core kernel reads */
+int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
 /* variant 0 = default kernel (A operand staged through TMEM), 1 = A operand staged through shared memory */
-int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t, int n_out,
-                              int K, int cin, int cout, float* out, int variant, void* stream);
+int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
+                              const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
+                              int variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /

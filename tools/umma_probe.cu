@@ -1,0 +1,117 @@
+// Micro-probe: cycles per tcgen05.mma (kind::tf32, M=128) as a function of N, of accumulator dependence
+// and of where A lives (smem / TMEM).  Development aid, not part of the library.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe tools/umma_probe.cu && ./umma_probe
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
+    uint64_t d = 0;
+    d |= (uint64_t)((a & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode: 0 = SS same accumulator, 1 = SS alternating 2 accumulators, 2 = TS same, 3 = TS alternating,
+//       4 = SS 4 accumulators round robin, 5 = bf16 SS same accumulator (K=16)
+__global__ void __launch_bounds__(128, 1) probe(int mode, int N, int M, int n_mma, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 0.001f * (i & 63);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t fmt = mode == 5 ? 1u : 2u;      // bf16 : tf32
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    if (warp == 1) {
+        long long t0 = 0, t1 = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            t0 = clock64();
+            if (elect_one_sync()) {
+                const uint64_t da = desc_sw128(base), db = desc_sw128(base + 16384);
+                for (int i = 0; i < n_mma; ++i) {
+                    const uint64_t adv = (uint64_t)((i & 3) * 2);
+                    uint32_t d = tmem;
+                    if (mode == 1 || mode == 3) d = tmem + (uint32_t)((i & 1) * 256);
+                    if (mode == 4) d = tmem + (uint32_t)((i & 3) * 128);
+                    if (mode == 2 || mode == 3) mma_ts(d, tmem + 480 + (i & 3) * 8, db + adv, idesc, 1u);
+                    else if (mode == 5) mma_f16_ss(d, da + adv, db + adv, idesc, 1u);
+                    else mma_ss(d, da + adv, db + adv, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            __syncwarp();
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(smem_u32(&bar)), "r"((uint32_t)(rep & 1)) : "memory");
+            } while (!done);
+            t1 = clock64();
+        }
+        if ((threadIdx.x & 31) == 0) out[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+int main() {
+    long long* d_out;
+    cudaMalloc(&d_out, 148 * sizeof(long long));
+    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc"};
+    const int Ns[] = {16, 32, 64, 128, 256};
+    for (int grid : {1, 148})
+        for (int mode = 0; mode < 6; ++mode)
+            for (int N : Ns) {
+                if ((mode == 1 || mode == 3) && N > 256) continue;
+                if (mode == 4 && N > 128) continue;
+                if ((mode == 2 || mode == 3) && N > 224) continue;   // acc must not overlap the A columns at 480
+                for (int n_mma : {16, 256}) {
+                    probe<<<grid, 128, 64 * 1024>>>(mode, N, 128, n_mma, d_out);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                    long long h[148];
+                    cudaMemcpy(h, d_out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+                    long long mx = 0;
+                    for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+                    printf("grid %3d  %-18s N=%3d  n_mma=%3d  cycles=%7lld  per_mma=%6.1f\n", grid, names[mode], N, n_mma, mx,
+                           (double)mx / n_mma);
+                }
+            }
+    return 0;
+}
