@@ -192,7 +192,8 @@ class LidarForward:
         self.device = device
         cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
         self.model = models.BEVFusionCenterHead(cfg).to(device).train()   # BN on batch statistics (student and
-        batch = S.lidar_batch(BS_PER_GPU, seed=seed + rank)               # teacher both run so)
+        self.model.use_channels_last(os.environ.get("UD_CHANNELS_LAST", "1") != "0")  # teacher both run so, quirk 9)
+        batch = S.lidar_batch(BS_PER_GPU, seed=seed + rank)
         self.points_host = batch["points"].pin_memory()                   # (B, Nmax, 5) zero padded (collate_fn)
         self.gt_host = _gt_with_labels(batch).pin_memory()
         self.points_dev = self.points_host.to(device)
@@ -238,6 +239,7 @@ class CameraForward:
         self.device = device
         cfg = models.make_model_cfg(bev=128, lidar=False, camera=True)
         self.model = models.BEVFusionCenterHead(cfg).to(device).train()
+        self.model.use_channels_last(os.environ.get("UD_CHANNELS_LAST", "1") != "0")
         cam = S.camera_batch(BS_PER_GPU, seed=seed + rank)
         lid = S.lidar_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=64, sweeps=1)
         self.imgs_host = cam["imgs"].pin_memory()
@@ -398,7 +400,7 @@ def run_ours(args):
         "config": {"workload": wl.name, "global_batch": BS_PER_GPU * world, "per_gpu_batch": BS_PER_GPU,
                    "bn": "train-mode batch statistics, torch.no_grad", "weights": "random init, seed 0",
                    "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed",
-                   "dense_convs": "cuDNN fp32 (torch default allow_tf32)", "parallelism": "dp%d" % world},
+                   "dense_convs": "cuDNN fp32 (torch default allow_tf32), NHWC memory format", "parallelism": "dp%d" % world},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d),
                 "d2h_bytes_per_step": int(wl.d2h), "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches),

@@ -239,6 +239,18 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self.fusion_encoder = FusionEncoder(use_elementwise=False) if both else None
         self.bev_encoder = BevEncoder(model_cfg.bev_encoder)
         self.det_head = DetHead(model_cfg.det_head)
+        self._channels_last = False
+
+    def use_channels_last(self, enable=True):
+        """Keeps the dense 2-D part (BEV backbone, fusion conv, detection head, image nets) in NHWC memory so cuDNN's
+        tensor-core convolutions run without an NCHW<->NHWC transpose around every layer.  Shapes, values and
+        state_dict are unchanged (channels_last is a stride convention)."""
+        fmt = torch.channels_last if enable else torch.contiguous_format
+        for m in (self.bev_encoder, self.det_head, self.fusion_encoder, self.camera_encoder):
+            if m is not None:
+                m.to(memory_format=fmt)
+        self._channels_last = bool(enable)
+        return self
 
     def extract_bev(self, lidar_points, cameras_imgs, metas):
         out = None
@@ -254,6 +266,8 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
 
     def forward(self, lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False, **kwargs):
         model_output = self.extract_bev(lidar_points, cameras_imgs, metas)
+        if self._channels_last:
+            model_output = model_output.contiguous(memory_format=torch.channels_last)
         x = self.bev_encoder(model_output)
         ret = self.det_head(x[0], gt_boxes)
         if return_feature:
