@@ -274,7 +274,55 @@ class CameraForward:
         return out
 
 
-WORKLOADS = {"lidar": LidarForward, "camera": CameraForward}
+class DistillTrainStep:
+    """configs[3]: camera-student <- LiDAR-teacher distillation step (det loss + feature/relation/response
+    distillation, backward, one NCCL gradient all-reduce, AdamW), bs=4 per GPU."""
+
+    name = ("camera-student <- LiDAR-teacher distill step (fwd teacher+student, 3 distill losses, bwd, grad "
+            "all-reduce, AdamW), bs=4/GPU, 128x128 BEV")
+
+    def __init__(self, device, rank, seed=0):
+        import torch
+
+        from unidistill_b200 import models, synthetic as S
+        from unidistill_b200.step import DistillStep
+
+        torch.manual_seed(0)
+        self.device = device
+        cl = os.environ.get("UD_CHANNELS_LAST", "1") != "0"
+        t_cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+        s_cfg = models.make_model_cfg(bev=128, lidar=False, camera=True)
+        teacher = models.BEVFusionCenterHead(t_cfg).to(device).use_channels_last(cl)
+        student = models.BEVFusionCenterHead(s_cfg).to(device).use_channels_last(cl)
+        self.step_fn = DistillStep(student, teacher, t_cfg["geometry"])
+        lid = S.lidar_batch(BS_PER_GPU, seed=seed + rank)
+        cam = S.camera_batch(BS_PER_GPU, seed=seed + rank)
+        self.host = {"points": lid["points"].pin_memory(), "imgs": cam["imgs"].pin_memory(),
+                     "gt_boxes": lid["gt_boxes"].pin_memory(), "gt_labels": lid["gt_labels"].pin_memory(),
+                     "mats_dict": {k: v.pin_memory() for k, v in cam["mats_dict"].items()}}
+        self.dev = self._to_device(self.host, False)
+        self.h2d = (self.host["points"].numel() + self.host["imgs"].numel() + self.host["gt_boxes"].numel()
+                    + sum(v.numel() for v in self.host["mats_dict"].values())) * 4 + self.host["gt_labels"].numel() * 8
+        self.d2h = 0
+        self.samples = BS_PER_GPU
+
+    def _to_device(self, h, nb):
+        d = {k: (v.to(self.device, non_blocking=nb) if not isinstance(v, dict) else
+                 {kk: vv.to(self.device, non_blocking=nb) for kk, vv in v.items()}) for k, v in h.items()}
+        d["points"] = [d["points"][b] for b in range(d["points"].shape[0])]
+        return d
+
+    def step(self):
+        return self.step_fn(self.dev)
+
+    def step_e2e(self):
+        terms = self.step_fn(self._to_device(self.host, True))
+        out = terms["loss"].cpu()
+        self.d2h = 4
+        return out
+
+
+WORKLOADS = {"lidar": LidarForward, "camera": CameraForward, "distill": DistillTrainStep}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -264,7 +264,11 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
             out = self.fusion_encoder(lidar_out, camera_out)
         return out
 
-    def forward(self, lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False, **kwargs):
+    def forward(self, lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False, normalisers=None,
+                **kwargs):
+        """`normalisers`: optional callable(ret_dict) run between target assignment and get_loss; it may put
+        pre-reduced `num_pos_reduced` / `num_hm_reduced` tensors into ret_dict (one fused all-reduce per step
+        instead of the reference's per-loss scalar reduce_mean calls; unidistill_b200.step uses it)."""
         model_output = self.extract_bev(lidar_points, cameras_imgs, metas)
         if self._channels_last:
             model_output = model_output.contiguous(memory_format=torch.channels_last)
@@ -275,6 +279,8 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         if self.training:
             for _, enc in ret["box_encoding"].items():
                 enc[torch.isinf(enc)] = 0
+            if normalisers is not None:
+                normalisers(ret)
             loss_rpn, tb_dict = self.det_head.dense_head.get_loss(ret)
             tb_dict.update({"loss_rpn": loss_rpn.detach()})
             return {"loss": loss_rpn}, tb_dict, model_output, x[0], ret["multi_head_features"], {}

@@ -1,0 +1,79 @@
+"""World-size-2 `gloo` tests (CPU) of the data-parallel host logic: flat gradient bucket all-reduce, the fused
+normaliser all-reduce of the distillation step and the torch_dist helpers (reference utils/torch_dist.py:33-43).
+The CUDA kernels are not involved; the N>1 GPU path uses the same code with backend `nccl`."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cvpr2023-unidistill_b200")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from unidistill.utils import torch_dist
+        from unidistill_b200.step import FlatGradBucket, fused_normalisers
+
+        assert torch_dist.get_world_size() == world and torch_dist.get_rank() == rank
+        # reduce_mean == sum / world, input untouched
+        t = torch.tensor([float(rank + 1), 10.0 * (rank + 1)])
+        r = torch_dist.reduce_mean(t)
+        assert torch.allclose(r, torch.tensor([1.5, 15.0])) and t[0] == rank + 1
+
+        # flat bucket: gradients of a tiny model, different data per rank -> identical averaged grads everywhere
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        bucket = FlatGradBucket(net.parameters())
+        assert bucket.numel == sum(p.numel() for p in net.parameters())
+        g = torch.Generator().manual_seed(100 + rank)
+        x = torch.randn(7, 6, generator=g)
+        bucket.zero()
+        net(x).square().sum().backward()
+        local = bucket.flat.clone()
+        for p in net.parameters():                       # backward accumulated INTO the flat views
+            assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+        bucket.all_reduce_mean()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-6)
+
+        # fused normalisers: one all-reduce for 2*T + 2 scalars
+        ret = {"mask": [torch.full((2, 4), float(rank + t)) > 0.5 for t in range(3)],
+               "heatmap": [(torch.arange(8).reshape(1, 1, 2, 4) % (t + 2 + rank) == 0).float() for t in range(3)]}
+        valid = torch.ones(2, 5, dtype=torch.bool)
+        valid[rank, 3:] = False
+        num_pos, num_hm, n_valid, mask_sum = fused_normalisers(ret, valid, torch.tensor(2.0 + rank))
+        exp_pos = [sum(float((torch.full((2, 4), float(r_ + t)) > 0.5).sum()) for r_ in range(world)) / world
+                   for t in range(3)]
+        assert torch.allclose(num_pos, torch.tensor(exp_pos))
+        assert float(n_valid) == pytest.approx((10 - 2) * 2 / 2 / 1.0 if False else 8.0)
+        assert float(mask_sum) == pytest.approx(2.5)
+        assert num_hm.shape == (3,)
+        open(os.path.join(out_dir, "ok_%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok_0") and os.path.exists(tmp_path / "ok_1")

@@ -1,0 +1,89 @@
+"""Distillation training step (unidistill_b200.step.DistillStep == Exp.training_step of the reference's distill
+scripts) on the GPU: every loss term against the CPU oracle evaluated on the same student/teacher tensors, the
+fused-normaliser path against the per-loss reduce_mean path, and one optimiser step."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distill as OD
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(dev, bs=1):
+    from unidistill_b200 import synthetic as S
+
+    lid = S.lidar_batch(bs, seed=5, points_per_sweep=6000, sweeps=2)
+    cam = S.camera_batch(bs, seed=5)
+    b = {"points": [lid["points"][i].to(dev) for i in range(bs)], "imgs": cam["imgs"].to(dev),
+         "mats_dict": {k: v.to(dev) for k, v in cam["mats_dict"].items()},
+         "gt_boxes": lid["gt_boxes"].to(dev), "gt_labels": lid["gt_labels"].to(dev)}
+    return b
+
+
+@pytest.fixture(scope="module")
+def step_and_batch(cuda, native_lib):
+    from unidistill_b200 import models
+    from unidistill_b200.step import DistillStep
+
+    torch.manual_seed(0)
+    t_cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+    s_cfg = models.make_model_cfg(bev=128, lidar=False, camera=True, img_depth=18)
+    teacher = models.BEVFusionCenterHead(t_cfg).to(cuda)
+    student = models.BEVFusionCenterHead(s_cfg).to(cuda)
+    step = DistillStep(student, teacher, t_cfg["geometry"], lr=1e-4)
+    step.keep_features = True
+    return step, _batch(cuda), t_cfg["geometry"]
+
+
+def test_loss_terms_match_oracle(step_and_batch):
+    step, batch, geo = step_and_batch
+    step.bucket.zero()
+    terms = step.losses(batch)
+    L = step.last
+    cpu = lambda t: t.detach().float().cpu().contiguous()  # noqa: E731
+    coords = OD.bev_corners(cpu(L["gt"]), geo["pc_range"], geo["voxel_size"], geo["out_size_factor"])
+    assert np.allclose(cpu(L["corners"]).numpy(), coords.numpy(), rtol=1e-6, atol=5e-5)
+    valid = OD.valid_prefix(cpu(batch["gt_boxes"]))
+    assert torch.equal(valid, L["valid"].cpu())
+    lf = OD.feature_distill_loss(cpu(L["feat_s"]), cpu(L["feat_t"]), coords, valid)
+    lr = OD.bev_distill_loss(cpu(L["bev_s"]), cpu(L["bev_t"]), coords, valid)
+    rs = [{k: cpu(v) for k, v in t.items()} for t in L["resp_s"]]
+    rt = [{k: cpu(v) for k, v in t.items()} for t in L["resp_t"]]
+    lc, lg = OD.response_distill_loss(rs, rt, cpu(L["gt"]), geo["pc_range"], geo["voxel_size"],
+                                      geo["out_size_factor"])
+    for name, ref in (("loss_feature", lf), ("loss_bev_rel", lr), ("loss_resp_cls", lc), ("loss_resp_reg", lg)):
+        got, ref = float(terms[name]), float(ref)
+        assert abs(got - ref) <= 1e-3 * abs(ref) + 1e-7, (name, got, ref)
+    total = float(terms["loss_det"]) + 100 * float(lf) + 40 * float(lr) + 10 * (float(lc) + float(lg))
+    assert abs(float(terms["loss"]) - total) <= 1e-3 * abs(total)
+
+
+def test_fused_normalisers_equal_per_loss_reduce_mean(step_and_batch):
+    """World size 1: the single fused normaliser vector must give exactly the reference's per-loss behaviour."""
+    step, batch, geo = step_and_batch
+    from unidistill_b200.step import gt_with_labels
+
+    gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
+    torch.manual_seed(1)
+    with torch.no_grad():
+        a = step.student(batch["points"], batch["imgs"], batch["mats_dict"], gt)[0]["loss"]
+        step.bucket.zero()
+        b = step.losses(batch)["loss_det"]
+    # BN batch statistics are identical (same batch), running stats do not enter a train-mode forward
+    assert abs(float(a) - float(b)) <= 1e-5 * abs(float(a))
+
+
+def test_one_optimizer_step_changes_student_only(step_and_batch):
+    step, batch, _ = step_and_batch
+    s0 = [p.detach().clone() for p in step.student.parameters()]
+    t0 = [p.detach().clone() for p in step.teacher.parameters()]
+    tb0 = [b.detach().clone() for b in step.teacher.buffers()]
+    terms = step(batch)
+    assert np.isfinite(float(terms["loss"]))
+    assert float(step.bucket.flat.abs().sum()) > 0
+    changed = sum(int(not torch.equal(a, p.detach())) for a, p in zip(s0, step.student.parameters()))
+    assert changed > 0.9 * len(s0)
+    assert all(torch.equal(a, p.detach()) for a, p in zip(t0, step.teacher.parameters()))
+    step._restore_teacher()
+    assert all(torch.equal(a, b) for a, b in zip(tb0, step.teacher.buffers()))
