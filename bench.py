@@ -355,14 +355,20 @@ def _roofline_from_records(records, peaks):
     tflops = flops / g["launches"] / avg_ms / 1e9
     gbs = byts / g["launches"] / avg_ms / 1e6
     tensor_bound = cin >= 32           # C<=16 is gather-bandwidth bound, C>=32 tensor-pipe bound
+    kname = "%s<%d,%d>" % (g["metas"][0][0].get("kernel", "k_spconv"), cin, cout)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")       # dram bytes/launch from the ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = (json.load(f).get(kname) or {}).get("dram_bytes_per_launch")
     roof = {
-        "kernel": "%s<%d,%d> (K=%d taps)" % (g["metas"][0][0].get("kernel", "k_spconv"), cin, cout, K),
+        "kernel": "%s (K=%d taps)" % (kname, K),
         "bound": "tensor" if tensor_bound else "hbm",
         "achieved": round(tflops if tensor_bound else gbs, 3),
         "peak": peaks["tensor_tflops"] if tensor_bound else peaks["hbm_gbs"],
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
         "frac": round((tflops / peaks["tensor_tflops"]) if tensor_bound else (gbs / peaks["hbm_gbs"]), 5),
-        "traffic": None,
+        "traffic": traffic,
         "avg_launch_ms": round(avg_ms, 4),
         "launches_per_step_group": g["launches"],
         "algorithmic_gflop_per_launch": round(flops / g["launches"] / 1e9, 3),

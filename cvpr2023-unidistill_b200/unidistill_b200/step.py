@@ -37,7 +37,8 @@ class FlatGradBucket:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            # same strides as the parameter (NHWC-format conv weights stay NHWC): dense, so the segment is exact
+            p.grad = self.flat[off: off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
         self.numel = n
 
