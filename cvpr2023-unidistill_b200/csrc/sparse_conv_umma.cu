@@ -546,6 +546,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // Optional role-level cycle accounting (development aid): when ud_debug_umma_prof() installed a buffer, every
 // role adds the cycles it spent waiting / working to prof[slot]; nullptr (the default) costs one load per CTA.
 __device__ unsigned long long* g_umma_prof = nullptr;
+// development knob (wrong results!): bit 0 = transform warps skip smem read / split / TMEM store, bit 1 = loaders skip
+// the cp.async gathers, bit 2 = MMA issuer skips the MMAs.  Used to measure the floor of each pipeline role.
+__device__ int g_umma_debug = 0;
 enum { PF_MMA_WAIT_A = 0, PF_MMA_WAIT_B, PF_MMA_TOTAL, PF_TR_WAIT_RAW, PF_TR_WAIT_A, PF_TR_TOTAL, PF_LD_WAIT_RAW,
        PF_LD_TOTAL, PF_PROLOGUE, PF_EPILOGUE, PF_CTA_TOTAL, PF_CTAS, PF_STAGES, PF_COUNT };
 #define PF_T() (prof ? clock64() : 0ll)
@@ -580,6 +583,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
 
     unsigned long long* const prof = g_umma_prof;
+    const int dbg = g_umma_debug;
     const long long t_cta0 = PF_T();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_b = smem_base + TS_RAW_STAGES * TS_RAW_BYTES;
@@ -644,7 +648,8 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             const unsigned char* rawp = smem_raw + (smem_base - smem_u32(smem_raw)) + rslot * TS_RAW_BYTES;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const uint4 x = *reinterpret_cast<const uint4*>(rawp + swz_off(r, c));
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (!(dbg & 1)) x = *reinterpret_cast<const uint4*>(rawp + swz_off(r, c));
                 v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
             }
             mbar_arrive(bar_raw_empty + 8 * rslot);     // values are in registers: the raw slot may be refilled
@@ -659,9 +664,11 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             w_a += PF_T() - tw;
             tc_fence_after();
             const uint32_t taddr = tmem_a + lane_addr + (uint32_t)(aslot * 64);
-            tmem_st32(taddr, v);
-            tmem_st32(taddr + 32, lo);
-            tmem_st_wait();
+            if (!(dbg & 1)) {
+                tmem_st32(taddr, v);
+                tmem_st32(taddr + 32, lo);
+                tmem_st_wait();
+            }
             tc_fence_before();
             mbar_arrive(bar_a_full + 8 * aslot);
         }
@@ -712,7 +719,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                 const int rr = rbase + RSTEP * j;
                 const bool ok = idx[j] >= 0;
                 const float* src = in + (ok ? ((size_t)idx[j] * CIN + c0) : 0);
-                cp_async_16(dst0 + swz_off(rr, chunk), src, ok ? 16u : 0u);
+                if (!(dbg & 2)) cp_async_16(dst0 + swz_off(rr, chunk), src, ok ? 16u : 0u);
             }
             cp_async_arrive_noinc(bar_raw_full + 8 * rslot);
         }
@@ -745,6 +752,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     const uint32_t first = (started >> tile) & 1u;
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
+                        if (dbg & 4) break;
                         const uint64_t adv = (uint64_t)(ks * 2);       // B: 8 fp32 = 32 B = 2 x 16 B
                         const uint32_t acol = (uint32_t)(ks * 8);      // A: 8 TMEM columns
                         umma_tf32_ts(d, a_lo + acol, db_hi + adv, IDESC, (first || ks > 0) ? 1u : 0u);
@@ -869,6 +877,11 @@ extern "C" {
 int ud_debug_umma_prof(void* buf) {
     unsigned long long* p = (unsigned long long*)buf;
     UD_CUDA_TRY(cudaMemcpyToSymbol(g_umma_prof, &p, sizeof(p)));
+    return UD_OK;
+}
+
+int ud_debug_umma_flags(int flags) {
+    UD_CUDA_TRY(cudaMemcpyToSymbol(g_umma_debug, &flags, sizeof(flags)));
     return UD_OK;
 }
 

@@ -103,6 +103,8 @@ int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
 int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
 /* development aid: device buffer of 16 uint64 receiving role-level cycle counts of the tensor-core kernel; NULL = off */
 int ud_debug_umma_prof(void* buf);
+/* development aid: disables pipeline roles of the tensor-core kernel (results become wrong); 0 = normal operation */
+int ud_debug_umma_flags(int flags);
 /* nbr (n,K) row-major gather table -> nbr_t (K,n) tap-major + tile_masks (ceil(n/128)) uint32 with bit k set when tap k
  * occurs in that 128-row tile: the two table forms the tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);

@@ -80,6 +80,8 @@ def main():
         x = torch.randn((rb.n_in, cin), device=dev)
         ks3 = rb.ksize
         w = torch.randn((cout, ks3[0], ks3[1], ks3[2], cin), device=dev) * 0.05
+        if os.environ.get("UD_MB_DEBUG_FLAGS"):
+            native.load().ud_debug_umma_flags(int(os.environ["UD_MB_DEBUG_FLAGS"]))
         if os.environ.get("UD_MB_PROF"):
             prof = torch.zeros(16, dtype=torch.int64, device=dev)
             native.load().ud_debug_umma_prof(native.ptr(prof))

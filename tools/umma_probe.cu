@@ -35,13 +35,15 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, u
 
 // mode: 0 = SS same accumulator, 1 = SS alternating 2 accumulators, 2 = TS same, 3 = TS alternating,
 //       4 = SS 4 accumulators round robin, 5 = bf16 SS same accumulator (K=16)
-__global__ void __launch_bounds__(128, 1) probe(int mode, int N, int M, int n_mma, long long* out) {
+__global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mma, long long* out, int st_iters) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 0.001f * (i & 63);
+    __shared__ volatile int stop_flag;
+    if (threadIdx.x == 0) stop_flag = 0;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 256) reinterpret_cast<float*>(smem_raw)[i] = 0.001f * (i & 63);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -83,6 +85,22 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int N, int M, int n_mm
             t1 = clock64();
         }
         if ((threadIdx.x & 31) == 0) out[blockIdx.x] = t1 - t0;
+        stop_flag = 1;
+    } else if (warp >= 4 && st_iters > 0) {
+        // concurrent TMEM writes: each warp stores 2 x 32 columns into its lane quadrant, columns [256, 480)
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t v = threadIdx.x;
+        int it = 0;
+        while (!stop_flag && it < st_iters) {
+            const uint32_t taddr = tmem + lane_addr + 256 + (uint32_t)((it % 3) * 64);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(v) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + 32), "r"(v) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            ++it;
+            // pace: roughly one 64-column store per `pace` cycles
+            long long t = clock64();
+            while (clock64() - t < 300) {}
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -95,22 +113,25 @@ int main() {
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc"};
     const int Ns[] = {16, 32, 64, 128, 256};
-    for (int grid : {1, 148})
+    for (int grid : {148})
         for (int mode = 0; mode < 6; ++mode)
             for (int N : Ns) {
                 if ((mode == 1 || mode == 3) && N > 256) continue;
                 if (mode == 4 && N > 128) continue;
                 if ((mode == 2 || mode == 3) && N > 224) continue;   // acc must not overlap the A columns at 480
                 for (int n_mma : {16, 256}) {
-                    probe<<<grid, 128, 64 * 1024>>>(mode, N, 128, n_mma, d_out);
+                  for (int st_iters : {0, 100000}) {
+                    if (st_iters && (mode != 2 || n_mma != 256)) continue;
+                    probe<<<grid, 256, 64 * 1024>>>(mode, N, 128, n_mma, d_out, st_iters);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     long long h[148];
                     cudaMemcpy(h, d_out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
                     long long mx = 0;
                     for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-                    printf("grid %3d  %-18s N=%3d  n_mma=%3d  cycles=%7lld  per_mma=%6.1f\n", grid, names[mode], N, n_mma, mx,
-                           (double)mx / n_mma);
+                    printf("grid %3d  %-18s N=%3d  n_mma=%3d  st=%d cycles=%7lld  per_mma=%6.1f\n", grid, names[mode], N, n_mma,
+                           st_iters > 0, mx, (double)mx / n_mma);
+                  }
                 }
             }
     return 0;
