@@ -176,8 +176,10 @@ k_pack_weights(const float* __restrict__ w, int K, int cin, int cout, float* __r
 
 // [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
 // tile_masks[row / 128] |= 1 << k for every tap k that occurs in the 128-row tile (zeroed by the launcher).
+// dst has leading dimension ld = n rounded up to 128; rows [n, ld) are written as -1.
 __global__ void __launch_bounds__(256)
-k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ dst, unsigned int* __restrict__ tile_masks) {
+k_transpose_table(const int* __restrict__ src, int n, int K, int ld, int* __restrict__ dst,
+                  unsigned int* __restrict__ tile_masks) {
     __shared__ int tile[32][33];
     const int r0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
@@ -190,7 +192,7 @@ k_transpose_table(const int* __restrict__ src, int n, int K, int* __restrict__ d
     for (int k = ty; k < K; k += 8) {
         const int r = r0 + tx;
         const int v = tile[tx][k];
-        if (r < n) dst[(size_t)k * n + r] = v;
+        if (r < ld) dst[(size_t)k * ld + r] = v;
         const unsigned any = __ballot_sync(0xffffffffu, r < n && v >= 0);
         if (any) m |= 1u << k;
     }
@@ -266,6 +268,7 @@ k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, c
     const int lane = tid & 31;
     const int row0 = blockIdx.x * tiles * TILE_M;
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
+    const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -316,7 +319,7 @@ k_spconv_umma(const float* __restrict__ in, const float* __restrict__ wpacked, c
         auto load_idx = [&](int(&idx)[8], int it) {
             const unsigned e = a_sched[it];
             const int tap = e & 31, tile = e >> 8;
-            const int* col = nbr_t + (size_t)tap * n_out + row0 + tile * TILE_M;
+            const int* col = nbr_t + (size_t)tap * ld_t + row0 + tile * TILE_M;
             const int lim = rows_cta - tile * TILE_M;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -490,26 +493,33 @@ int launch_umma(const float* in, const float* wpacked, const float* bias, const 
 
 
 // ================================================================================================
-// Variant "TS": the A operand goes through TMEM instead of shared memory.
+// Variant "TS" (default): the A operand goes through TMEM instead of shared memory.
 //
-// Shared-memory bandwidth bounds the SS kernel above (per 32-channel stage: 32 KB of hi/lo stores + 72 KB of
-// operand reads by the 12 MMAs).  Here a stage costs 16 KB (cp.async landing the raw fp32 rows) + 16 KB (one read
-// by the transform warps) + 24..48 KB (B reads):
-//   loader warps (4)     : prefetch the row indices, issue 16-byte cp.async (zero-fill for absent rows) into a
-//                          swizzled raw ring; completion is signalled by cp.async.mbarrier.arrive.noinc
-//   transform warps (2x4): thread == row.  Read the 128-byte row slice (conflict-free thanks to the swizzle),
-//                          split hi/lo in registers, tcgen05.st both halves into the stage's 64 TMEM columns
-//   MMA issuer (1 warp)  : tcgen05.mma kind::tf32 with A from TMEM, B (weights) from shared memory
-//   weight loader (1)    : as in the SS kernel
-// TMEM: columns [0, 256) accumulators (256/COUT tiles per CTA), [256, 512) four A stages of 32 hi + 32 lo columns.
-constexpr int TS_THREADS = 576;          // 8 transform + 8 loader + MMA + weight-loader warps
-constexpr int TS_LOADER_THREADS = 256;
-constexpr int TS_RAW_STAGES = 4;
-constexpr int TS_RAW_BYTES = TILE_M * 128;        // one [128 x 32] fp32 tile, raw
-constexpr int TS_A_STAGES = 4;
+// A pipeline stage = one kernel tap x KS input channels (KS = 64 for CIN >= 64, else 32) x one 128-row tile:
+//   weight/index warp (1) : cp.async.bulk of the pre-swizzled hi/lo weight slice (once per tap x channel block, shared by
+//                           the CTA's tiles) and of each stage's 512-byte row-index segment into a 16-deep smem ring
+//   loader warps (2 x 4)  : two groups on alternate stages; read the indices from smem, issue 16-byte cp.async
+//                           (zero-fill for absent rows) into a swizzled raw ring; completion = cp.async.mbarrier.arrive
+//   transform warps (2x4) : two sets on alternate stages; thread == row: read the row slice (conflict-free thanks to
+//                           the swizzle), split hi/lo in registers, tcgen05.st both halves into the stage's TMEM columns
+//   MMA issuer (1 warp)   : tcgen05.mma kind::tf32, A from TMEM, B from shared memory; 3 MMAs per 8 channels
+// TMEM: columns [0, 256) accumulators (256/COUT <= 8 tiles per CTA), [256, 512) A stages of KS hi + KS lo columns.
+// Every role's per-stage serial chain (mbarrier round trips, index fetch, descriptor set-up) was measured with the
+// debug knobs below; stages were sized so that none of them exceeds the tensor-pipe time of a stage.
+constexpr int TS_THREADS = 608;          // 8 transform + 8 loader + MMA + weight + index warps
+constexpr int TS_GROUP = 128;            // threads of one loader group / one transform set
 constexpr int TS_ACC_COLS = 256;
+constexpr int TS_IDX_STAGES = 16;
 
 __host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
+// channels per stage: 64 halves the per-stage handshake cost, but with COUT = 128 only two tiles share a weight slice
+// and the 64 KB slices would make the kernel L2-bound, so those shapes keep 32-channel stages
+__host__ __device__ constexpr int ts_ks(int cin, int cout) { return (cin >= 64 && cout <= 64) ? 64 : 32; }
+__host__ __device__ constexpr int ts_raw_stages(int cin, int cout) { return 4; }
+__host__ __device__ constexpr size_t ts_smem_bytes(int cin, int cout) {
+    return (size_t)ts_raw_stages(cin, cout) * TILE_M * ts_ks(cin, cout) * 4 +
+           (size_t)B_STAGES * 2 * cout * ts_ks(cin, cout) * 4 + (size_t)TS_IDX_STAGES * TILE_M * 4 + 1024;
+}
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -550,22 +560,31 @@ __device__ unsigned long long* g_umma_prof = nullptr;
 // the cp.async gathers, bit 2 = MMA issuer skips the MMAs.  Used to measure the floor of each pipeline role.
 __device__ int g_umma_debug = 0;
 enum { PF_MMA_WAIT_A = 0, PF_MMA_WAIT_B, PF_MMA_TOTAL, PF_TR_WAIT_RAW, PF_TR_WAIT_A, PF_TR_TOTAL, PF_LD_WAIT_RAW,
-       PF_LD_TOTAL, PF_PROLOGUE, PF_EPILOGUE, PF_CTA_TOTAL, PF_CTAS, PF_STAGES, PF_COUNT };
+       PF_LD_TOTAL, PF_PROLOGUE, PF_EPILOGUE, PF_CTA_TOTAL, PF_CTAS, PF_STAGES, PF_LD_WAIT_IDX, PF_COUNT };
 #define PF_T() (prof ? clock64() : 0ll)
 #define PF_ADD(slot, v) do { if (prof && lane == 0) atomicAdd(prof + (slot), (unsigned long long)(v)); } while (0)
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
-                 const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K, int tiles,
-              float* __restrict__ out) {
-    constexpr int NCHUNK = CIN / KC;
-    constexpr int B_BYTES = COUT * 128;
+                 const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
+                 int tiles, float* __restrict__ out) {
+    constexpr int KS = ts_ks(CIN, COUT);             // channels per stage
+    constexpr int NSUB = KS / KC;                    // 32-channel sub-tiles per stage
+    constexpr int NCHUNK = CIN / KS;                 // stages per tap
+    constexpr int A_COLS = 2 * KS;                   // TMEM columns of one A stage: KS hi | KS lo
+    constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
+    constexpr int RAW_STAGES = ts_raw_stages(CIN, COUT);
+    constexpr int RAW_BYTES = TILE_M * KS * 4;
+    constexpr int SUB_BYTES = TILE_M * 128;          // one [128 x 32] fp32 sub-tile
+    constexpr int BSUB_BYTES = COUT * 128;           // one [COUT x 32] fp32 weight sub-slice
+    constexpr int B_BYTES = 2 * NSUB * BSUB_BYTES;   // hi + lo, all sub-tiles of the stage
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(TILE_M >> 4) << 24);
-    static_assert(CIN % KC == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert(CIN % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
     static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
-    constexpr int NBAR = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * B_STAGES + 1;
+    static_assert(RAW_STAGES % 2 == 0 && A_STAGES % 2 == 0, "two groups alternate over the rings");
+    constexpr int NBAR = 2 * RAW_STAGES + 2 * A_STAGES + 2 * B_STAGES + 2 * TS_IDX_STAGES + 1;
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[NBAR];
@@ -581,35 +600,42 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     const int lane = tid & 31;
     const int row0 = blockIdx.x * tiles * TILE_M;
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
+    const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
 
     unsigned long long* const prof = g_umma_prof;
     const int dbg = g_umma_debug;
     const long long t_cta0 = PF_T();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t smem_b = smem_base + TS_RAW_STAGES * TS_RAW_BYTES;
+    unsigned char* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t smem_b = smem_base + RAW_STAGES * RAW_BYTES;
+    const uint32_t smem_idx = smem_b + B_STAGES * B_BYTES;
+    const int* const idx_ring = reinterpret_cast<const int*>(smem_al + RAW_STAGES * RAW_BYTES + B_STAGES * B_BYTES);
     const uint32_t bar_raw_full = smem_u32(&bars[0]);
-    const uint32_t bar_raw_empty = smem_u32(&bars[TS_RAW_STAGES]);
-    const uint32_t bar_a_full = smem_u32(&bars[2 * TS_RAW_STAGES]);
-    const uint32_t bar_a_empty = smem_u32(&bars[2 * TS_RAW_STAGES + TS_A_STAGES]);
-    const uint32_t bar_b_full = smem_u32(&bars[2 * TS_RAW_STAGES + 2 * TS_A_STAGES]);
-    const uint32_t bar_b_empty = smem_u32(&bars[2 * TS_RAW_STAGES + 2 * TS_A_STAGES + B_STAGES]);
-    const uint32_t bar_acc = smem_u32(&bars[NBAR - 1]);
+    const uint32_t bar_raw_empty = bar_raw_full + 8 * RAW_STAGES;
+    const uint32_t bar_a_full = bar_raw_empty + 8 * RAW_STAGES;
+    const uint32_t bar_a_empty = bar_a_full + 8 * A_STAGES;
+    const uint32_t bar_b_full = bar_a_empty + 8 * A_STAGES;
+    const uint32_t bar_b_empty = bar_b_full + 8 * B_STAGES;
+    const uint32_t bar_idx_full = bar_b_empty + 8 * B_STAGES;
+    const uint32_t bar_idx_empty = bar_idx_full + 8 * TS_IDX_STAGES;
+    const uint32_t bar_acc = bar_idx_empty + 8 * TS_IDX_STAGES;
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < TS_RAW_STAGES; ++s) {
-            mbar_init(bar_raw_full + 8 * s, TS_LOADER_THREADS);   // one cp.async-completion arrive per loader thread
-            mbar_init(bar_raw_empty + 8 * s, 128);      // one arrive per transform thread
+        for (int s = 0; s < RAW_STAGES; ++s) {
+            mbar_init(bar_raw_full + 8 * s, TS_GROUP);      // one cp.async-completion arrive per loader thread
+            mbar_init(bar_raw_empty + 8 * s, TS_GROUP);     // one arrive per transform thread
         }
-#pragma unroll
-        for (int s = 0; s < TS_A_STAGES; ++s) {
-            mbar_init(bar_a_full + 8 * s, 128);
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, TS_GROUP);
             mbar_init(bar_a_empty + 8 * s, 1);
         }
-#pragma unroll
         for (int s = 0; s < B_STAGES; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
             mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < TS_IDX_STAGES; ++s) {
+            mbar_init(bar_idx_full + 8 * s, 1);
+            mbar_init(bar_idx_empty + 8 * s, TS_GROUP / 32);   // lane 0 of each warp of the consuming loader group
         }
         mbar_init(bar_acc, 1);
         fence_barrier_init();
@@ -639,92 +665,84 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         long long w_raw = 0, w_a = 0;
         for (int it = g; it < n_a; it += 2) {
-            const int rslot = it % TS_RAW_STAGES;
-            const int aslot = it % TS_A_STAGES;
-            uint32_t v[32], lo[32];
+            const int rslot = it % RAW_STAGES;
+            const int aslot = it % A_STAGES;
             long long tw = PF_T();
-            mbar_wait(bar_raw_full + 8 * rslot, ((uint32_t)(it / TS_RAW_STAGES)) & 1u);
+            mbar_wait(bar_raw_full + 8 * rslot, ((uint32_t)(it / RAW_STAGES)) & 1u);
             w_raw += PF_T() - tw;
-            const unsigned char* rawp = smem_raw + (smem_base - smem_u32(smem_raw)) + rslot * TS_RAW_BYTES;
+            const unsigned char* rawp = smem_al + rslot * RAW_BYTES;
+            const uint32_t taddr = tmem_a + lane_addr + (uint32_t)(aslot * A_COLS);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                if (!(dbg & 1)) x = *reinterpret_cast<const uint4*>(rawp + swz_off(r, c));
-                v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-            }
-            mbar_arrive(bar_raw_empty + 8 * rslot);     // values are in registers: the raw slot may be refilled
+            for (int sub = 0; sub < NSUB; ++sub) {
+                uint32_t v[32], lo[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t h = v[i] & 0xffffe000u;
-                lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
-                v[i] = h;
+                for (int c = 0; c < 8; ++c) {
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (!(dbg & 1)) x = *reinterpret_cast<const uint4*>(rawp + sub * SUB_BYTES + swz_off(r, c));
+                    v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+                }
+                if (sub == NSUB - 1) mbar_arrive(bar_raw_empty + 8 * rslot);   // all of the slot is in registers
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t h = v[i] & 0xffffe000u;
+                    lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
+                    v[i] = h;
+                }
+                if (sub == 0) {
+                    tw = PF_T();
+                    mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+                    w_a += PF_T() - tw;
+                    tc_fence_after();
+                }
+                if (!(dbg & 1)) {
+                    tmem_st32(taddr + sub * 32, v);
+                    tmem_st32(taddr + KS + sub * 32, lo);
+                }
             }
-            tw = PF_T();
-            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / TS_A_STAGES)) & 1u) ^ 1u);
-            w_a += PF_T() - tw;
-            tc_fence_after();
-            const uint32_t taddr = tmem_a + lane_addr + (uint32_t)(aslot * 64);
-            if (!(dbg & 1)) {
-                tmem_st32(taddr, v);
-                tmem_st32(taddr + 32, lo);
-                tmem_st_wait();
-            }
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar_a_full + 8 * aslot);
         }
         if (q == 0) { PF_ADD(PF_TR_WAIT_RAW, w_raw); PF_ADD(PF_TR_WAIT_A, w_a); PF_ADD(PF_TR_TOTAL, PF_T() - t_main0); }
     } else if (warp < 16) {
-        // ============ loaders: indices (L2-prefetched 8 stages ahead, loaded one stage ahead) -> cp.async rows ============
-        constexpr int RPT = TILE_M * 8 / TS_LOADER_THREADS;       // rows per thread and stage
-        constexpr int RSTEP = TS_LOADER_THREADS / 8;
-        const int tg = tid - 256;
-        const int chunk = tg & 7;                    // 16-byte chunk of the 128-byte row slice
-        const int rbase = tg >> 3;                   // rows rbase + RSTEP*j
-        int idx[RPT], idx_next[RPT];
-        auto seg_ptr = [&](int it) {
-            const unsigned e = a_sched[it];
-            return nbr_t + (size_t)(e & 31) * n_out + row0 + (e >> 8) * TILE_M;
-        };
-        auto load_idx = [&](int(&dst)[RPT], int it) {
-            const int* col = seg_ptr(it);
-            const int lim = rows_cta - (a_sched[it] >> 8) * TILE_M;
+        // ============ loaders: group g handles stages it = g, g+2, ...: indices from the smem ring -> cp.async ============
+        const int g = (warp - 8) >> 2;
+        const int tg = (tid - 256) & (TS_GROUP - 1);
+        const int chunk = tg & 7;                    // 16-byte chunk of a 128-byte row slice
+        const int rbase = tg >> 3;                   // rows rbase + 16*j, j = 0..7
+        long long w_raw = 0, w_idx = 0;
+        for (int it = g; it < n_a; it += 2) {
+            const int islot = it % TS_IDX_STAGES;
+            const int rslot = it % RAW_STAGES;
+            long long tw = PF_T();
+            mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / TS_IDX_STAGES)) & 1u);
+            w_idx += PF_T() - tw;
+            int idx[8];
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const int rr = rbase + RSTEP * j;
-                dst[j] = rr < lim ? __ldg(col + rr) : -1;
-            }
-        };
-        auto prefetch_idx = [&](int it) {            // 512-byte index segment = 4 lines: lanes 0..3 of warp 8
-            if (tg < 4 && it < n_a) {
-                const int* p = seg_ptr(it) + tg * 32;
-                if (p < nbr_t + (size_t)K * n_out) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            }
-        };
-        for (int it = 0; it < 8; ++it) prefetch_idx(it);
-        long long w_raw = 0;
-        if (n_a > 0) load_idx(idx_next, 0);
-        for (int it = 0; it < n_a; ++it) {
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) idx[j] = idx_next[j];
-            if (it + 1 < n_a) load_idx(idx_next, it + 1);
-            prefetch_idx(it + 8);
-            const int rslot = it % TS_RAW_STAGES;
-            const int c0 = ((a_sched[it] >> 5) & 7) * KC + chunk * 4;
-            const long long tw = PF_T();
-            mbar_wait(bar_raw_empty + 8 * rslot, (((uint32_t)(it / TS_RAW_STAGES)) & 1u) ^ 1u);
+            for (int j = 0; j < 8; ++j) idx[j] = idx_ring[islot * TILE_M + rbase + 16 * j];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
+            const int c0 = ((a_sched[it] >> 5) & 7) * KS + chunk * 4;
+            tw = PF_T();
+            mbar_wait(bar_raw_empty + 8 * rslot, (((uint32_t)(it / RAW_STAGES)) & 1u) ^ 1u);
             w_raw += PF_T() - tw;
-            const uint32_t dst0 = smem_base + rslot * TS_RAW_BYTES;
+            const uint32_t dst0 = smem_base + rslot * RAW_BYTES;
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const int rr = rbase + RSTEP * j;
+            for (int j = 0; j < 8; ++j) {
+                const int rr = rbase + 16 * j;
                 const bool ok = idx[j] >= 0;
                 const float* src = in + (ok ? ((size_t)idx[j] * CIN + c0) : 0);
-                if (!(dbg & 2)) cp_async_16(dst0 + swz_off(rr, chunk), src, ok ? 16u : 0u);
+                const uint32_t dst = dst0 + swz_off(rr, chunk);
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub)
+                    if (!(dbg & 2)) cp_async_16(dst + sub * SUB_BYTES, src + sub * KC, ok ? 16u : 0u);
             }
             cp_async_arrive_noinc(bar_raw_full + 8 * rslot);
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-        if (warp == 8) { PF_ADD(PF_LD_WAIT_RAW, w_raw); PF_ADD(PF_LD_TOTAL, PF_T() - t_main0); }
+        if (((warp - 8) & 3) == 0) {
+            PF_ADD(PF_LD_WAIT_RAW, w_raw); PF_ADD(PF_LD_WAIT_IDX, w_idx); PF_ADD(PF_LD_TOTAL, PF_T() - t_main0);
+        }
     } else if (warp == 16) {
         // ============ MMA issuer ============
         unsigned int started = 0u;
@@ -735,29 +753,33 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             long long tw = PF_T();
             mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / B_STAGES)) & 1u);
             w_b += PF_T() - tw;
-            const uint32_t b_hi = smem_b + bslot * 2 * B_BYTES;
-            const uint64_t db_hi = umma_desc_sw128(b_hi), db_lo = umma_desc_sw128(b_hi + B_BYTES);
+            const uint32_t b_base = smem_b + bslot * B_BYTES;
             const int cnt = b_count[ib];
             for (int c = 0; c < cnt; ++c, ++it) {
-                const int aslot = it % TS_A_STAGES;
+                const int aslot = it % A_STAGES;
                 const int tile = a_sched[it] >> 8;
                 tw = PF_T();
-                mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / TS_A_STAGES)) & 1u);
+                mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
                 w_a += PF_T() - tw;
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t a_hi = tmem_a + (uint32_t)(aslot * 64);
-                    const uint32_t a_lo = a_hi + 32;
+                    const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
                     const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
                     const uint32_t first = (started >> tile) & 1u;
 #pragma unroll
-                    for (int ks = 0; ks < KC / 8; ++ks) {
-                        if (dbg & 4) break;
-                        const uint64_t adv = (uint64_t)(ks * 2);       // B: 8 fp32 = 32 B = 2 x 16 B
-                        const uint32_t acol = (uint32_t)(ks * 8);      // A: 8 TMEM columns
-                        umma_tf32_ts(d, a_lo + acol, db_hi + adv, IDESC, (first || ks > 0) ? 1u : 0u);
-                        umma_tf32_ts(d, a_hi + acol, db_lo + adv, IDESC, 1u);
-                        umma_tf32_ts(d, a_hi + acol, db_hi + adv, IDESC, 1u);
+                    for (int sub = 0; sub < NSUB; ++sub) {
+                        const uint64_t db_hi = umma_desc_sw128(b_base + (sub * 2) * BSUB_BYTES);
+                        const uint64_t db_lo = umma_desc_sw128(b_base + (sub * 2 + 1) * BSUB_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            if (dbg & 4) break;
+                            const uint64_t adv = (uint64_t)(ks * 2);                   // B: 8 fp32 = 32 B = 2 x 16 B
+                            const uint32_t a_hi = a_stage + (uint32_t)(sub * 32 + ks * 8);   // A: 8 TMEM columns
+                            const uint32_t a_lo = a_hi + KS;
+                            umma_tf32_ts(d, a_lo, db_hi + adv, IDESC, (first || sub > 0 || ks > 0) ? 1u : 0u);
+                            umma_tf32_ts(d, a_hi, db_lo + adv, IDESC, 1u);
+                            umma_tf32_ts(d, a_hi, db_hi + adv, IDESC, 1u);
+                        }
                     }
                     umma_commit(bar_a_empty + 8 * aslot);
                 }
@@ -771,23 +793,33 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         __syncwarp();
         PF_ADD(PF_MMA_WAIT_A, w_a); PF_ADD(PF_MMA_WAIT_B, w_b); PF_ADD(PF_MMA_TOTAL, PF_T() - t_main0);
     } else {
-        // ============ weight loader ============
-        if (lane == 0) {
+        // ============ warp 17: weight slices, warp 18: per-stage row-index segments (bulk async copies) ============
+        if (warp == 17 && lane == 0) {
             for (int ib = 0; ib < n_b; ++ib) {
                 const int bslot = ib % B_STAGES;
                 mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / B_STAGES)) & 1u) ^ 1u);
                 const unsigned e = b_sched[ib];
                 const int tap = e & 31, ch = e >> 5;
-                const float* src = wpacked + ((size_t)(tap * NCHUNK + ch) * 2) * COUT * KC;
-                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, 2 * B_BYTES);
-                bulk_g2s(smem_b + bslot * 2 * B_BYTES, src, 2 * B_BYTES, bar_b_full + 8 * bslot);
+                const float* src = wpacked + ((size_t)(tap * (CIN / KC) + ch * NSUB) * 2) * COUT * KC;
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
+                bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
+            }
+        } else if (warp == 18 && lane == 0) {
+            // runs up to TS_IDX_STAGES stages ahead of the loaders, gated only by the index ring itself
+            for (int it = 0; it < n_a; ++it) {
+                const int islot = it % TS_IDX_STAGES;
+                mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / TS_IDX_STAGES)) & 1u) ^ 1u);
+                const unsigned e = a_sched[it];
+                const int* seg = nbr_t + (size_t)(e & 31) * ld_t + row0 + (e >> 8) * TILE_M;
+                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, TILE_M * 4);
+                bulk_g2s(smem_idx + islot * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
             }
         }
         __syncwarp();
     }
 
-    const long long t_epi0 = PF_T();
     // ============ epilogue (warps 0-7: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+2, ...) ============
+    const long long t_epi0 = PF_T();
     if (warp < 8) {
         if (n_a > 0) {
             mbar_wait(bar_acc, 0u);
@@ -840,7 +872,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
 template <int CIN, int COUT>
 int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
                    const unsigned int* tile_masks, int n_out, int K, float* out, cudaStream_t stream) {
-    const size_t smem = (size_t)TS_RAW_STAGES * TS_RAW_BYTES + (size_t)B_STAGES * 2 * COUT * 128 + 1024;
+    const size_t smem = ts_smem_bytes(CIN, COUT);
     auto kern = k_spconv_umma_ts<CIN, COUT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
@@ -906,14 +938,16 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     return UD_OK;
 }
 
-// nbr (n, K) int32 row-major gather table -> nbr_t (K, n) tap-major + tile_masks (ceil(n/128)) uint32 (bit k set
+// nbr (n, K) int32 row-major gather table -> nbr_t (K, ld) tap-major, ld = n rounded up to 128 (padding = -1, base
+// 16-byte aligned so every (tile, tap) index segment can be bulk-copied) + tile_masks (ceil(n/128)) uint32 (bit k set
 // when tap k occurs in the 128-row tile): the two inputs ud_sparse_conv_tc_forward reads.
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || K < 1 || K > MAX_TAPS || (n > 0 && (!nbr || !nbr_t || !tile_masks))) return UD_ERR_INVALID_ARG;
     if (n == 0) return UD_OK;
     UD_CUDA_TRY(cudaMemsetAsync(tile_masks, 0, sizeof(unsigned int) * (size_t)((n + TILE_M - 1) / TILE_M), stream));
-    k_transpose_table<<<ud_blocks(n, 32), 256, 0, stream>>>(nbr, n, K, nbr_t, tile_masks);
+    const int ld = (n + TILE_M - 1) / TILE_M * TILE_M;
+    k_transpose_table<<<ud_blocks(ld, 32), 256, 0, stream>>>(nbr, n, K, ld, nbr_t, tile_masks);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }

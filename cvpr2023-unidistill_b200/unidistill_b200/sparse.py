@@ -37,14 +37,15 @@ class Rulebook:
         self.in_coords_for_inverse = None
 
     def tap_major(self, table):
-        """((K, n) transposed copy, (ceil(n/128),) per-tile tap masks) of one of this rulebook's (n, K) tables,
+        """((K, ld) transposed copy with ld = n rounded up to 128, (ceil(n/128),) per-tile tap masks) of one of this rulebook's (n, K) tables,
         built once and cached (the tensor-core kernel reads the 128 indices of a (tile, tap) as one contiguous
         segment and schedules only the taps that occur in a tile)."""
         key = table.data_ptr()
         t = self._tap_major.get(key)
         if t is None:
             n, K = int(table.shape[0]), int(table.shape[1])
-            tt = torch.empty((K, n), dtype=torch.int32, device=table.device)
+            ld = (n + 127) // 128 * 128            # padded with -1: whole 512-byte index segments per (tile, tap)
+            tt = torch.empty((K, ld), dtype=torch.int32, device=table.device)
             masks = torch.empty(((n + 127) // 128,), dtype=torch.int32, device=table.device)
             rc = native.load().ud_rulebook_transpose(native.ptr(table), n, K, native.ptr(tt), native.ptr(masks),
                                                      native.stream_ptr(table.device))

@@ -105,8 +105,9 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
 int ud_debug_umma_prof(void* buf);
 /* development aid: disables pipeline roles of the tensor-core kernel (results become wrong); 0 = normal operation */
 int ud_debug_umma_flags(int flags);
-/* nbr (n,K) row-major gather table -> nbr_t (K,n) tap-major + tile_masks (ceil(n/128)) uint32 with bit k set when tap k
- * occurs in that 128-row tile: the two table forms the tensor-core kernel reads */
+/* nbr (n,K) row-major gather table -> nbr_t (K,ld) tap-major with ld = n rounded up to 128 (padding -1; 16-byte aligned
+ * base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
+ * tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
 /* variant 0 = default kernel (A operand staged through TMEM), 1 = A operand staged through shared memory */
 int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,

@@ -90,12 +90,12 @@ def main():
             torch.cuda.synchronize()
             native.load().ud_debug_umma_prof(None)
             names = ["mma_wait_a", "mma_wait_b", "mma_total", "tr_wait_raw", "tr_wait_a", "tr_total", "ld_wait_raw",
-                     "ld_total", "prologue", "epilogue", "cta_total", "ctas", "stages"]
+                     "ld_total", "prologue", "epilogue", "cta_total", "ctas", "stages", "ld_wait_idx"]
             pv = prof.cpu().tolist()
             ctas, stages = max(1, pv[11]), max(1, pv[12])
             print("  role cycles for %d->%d: ctas=%d stages=%d (per CTA %.0f)" % (cin, cout, ctas, stages, stages / ctas))
-            for nm, v in zip(names[:11], pv[:11]):
-                div = 2 if nm.startswith("tr_") else 1      # two transform sets report
+            for nm, v in list(zip(names[:11], pv[:11])) + [(names[13], pv[13])]:
+                div = 2 if nm.startswith(("tr_", "ld_")) else 1      # two transform sets / loader groups report
                 print("    %-12s %10.0f cycles/CTA   %8.1f cycles/stage" % (nm, v / div / ctas, v / div / stages))
         with torch.no_grad():
             ms, out = timed(lambda: sparse.sparse_conv(x, w, None, rb))
