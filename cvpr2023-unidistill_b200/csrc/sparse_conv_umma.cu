@@ -24,6 +24,7 @@
 //                            warp 9           weight loader (cp.async.bulk + mbarrier expect_tx)
 //                            warps 0-3        epilogue afterwards: tcgen05.ld -> +bias -> global
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -172,6 +173,39 @@ k_pack_weights(const float* __restrict__ w, int K, int cin, int cout, float* __r
     const size_t base = ((size_t)(k * nchunk + chunk) * 2) * cout * KC;
     packed[base + (size_t)n * KC + pos] = hi;
     packed[base + (size_t)cout * KC + (size_t)n * KC + pos] = lo;
+}
+
+// Packed image for the bf16-correction kernel: per (tap, stage of KS channels) one block of
+//   [KS/32 sub-tiles: COUT x 32 tf32 hi, 128-byte swizzle] [COUT x KS bf16 W] [COUT x KS bf16 (W - hi)]
+// with the bf16 slices in the 128-byte (KS = 64) or 64-byte (KS = 32) swizzle.  Block size = 8 * COUT * KS bytes.
+__global__ void __launch_bounds__(256)
+k_pack_weights_bf(const float* __restrict__ w, int K, int cin, int cout, int ks, unsigned char* __restrict__ packed) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)K * cin * cout;
+    if (t >= total) return;
+    const int n = (int)(t % cout);
+    const int c = (int)((t / cout) % cin);
+    const int k = (int)(t / ((long long)cout * cin));
+    const float v = w[t];                                   // w[k][c][n]
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const float lo = v - hi;
+    const int nstage = cin / ks;
+    const int stage = c / ks, e = c % ks;                   // channel within the stage
+    const int nsub = ks / KC;
+    unsigned char* blk = packed + (size_t)(k * nstage + stage) * ((size_t)8 * cout * ks);
+    {   // tf32 hi: sub-tile e/32, row n, 32 floats, 16-byte chunks XOR (n & 7)
+        const int sub = e / KC, ee = e % KC;
+        const int pos = (((ee >> 2) ^ (n & 7)) << 2) | (ee & 3);
+        reinterpret_cast<float*>(blk + (size_t)sub * cout * 128)[(size_t)n * KC + pos] = hi;
+    }
+    {   // bf16 slices: row n of ks elements (2 B each); 16-byte chunk = 8 elements
+        const int chunk = e >> 3, within = e & 7;
+        const int sw = ks == 64 ? (chunk ^ (n & 7)) : (chunk ^ ((n >> 1) & 3));
+        const size_t off = (size_t)n * ks + sw * 8 + within;
+        __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(blk + (size_t)nsub * cout * 128);
+        wb[off] = __float2bfloat16_rn(v);
+        wb[(size_t)cout * ks + off] = __float2bfloat16_rn(lo);
+    }
 }
 
 // [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
@@ -553,6 +587,40 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// K-major operand tile with 64-byte rows (32 bf16), 64-byte swizzle: 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                              // SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {   // element 2j in the low half
+    const __nv_bfloat162 t = __floats2bfloat162_rn(even, odd);
+    return *reinterpret_cast<const uint32_t*>(&t);
+}
+
 // Optional role-level cycle accounting (development aid): when ud_debug_umma_prof() installed a buffer, every
 // role adds the cycles it spent waiting / working to prof[slot]; nullptr (the default) costs one load per CTA.
 __device__ unsigned long long* g_umma_prof = nullptr;
@@ -564,7 +632,9 @@ enum { PF_MMA_WAIT_A = 0, PF_MMA_WAIT_B, PF_MMA_TOTAL, PF_TR_WAIT_RAW, PF_TR_WAI
 #define PF_T() (prof ? clock64() : 0ll)
 #define PF_ADD(slot, v) do { if (prof && lane == 0) atomicAdd(prof + (slot), (unsigned long long)(v)); } while (0)
 
-template <int CIN, int COUT>
+// BF16C: the two correction products (lo x W, hi x W_lo) are issued as kind::f16 bf16 MMAs with K = 16 (their operands
+// only need ~8 significant bits since the terms are 2^-11 of the result): 8 instead of 12 tcgen05.mma per 32 channels.
+template <int CIN, int COUT, bool BF16C>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
@@ -578,7 +648,10 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     constexpr int RAW_BYTES = TILE_M * KS * 4;
     constexpr int SUB_BYTES = TILE_M * 128;          // one [128 x 32] fp32 sub-tile
     constexpr int BSUB_BYTES = COUT * 128;           // one [COUT x 32] fp32 weight sub-slice
-    constexpr int B_BYTES = 2 * NSUB * BSUB_BYTES;   // hi + lo, all sub-tiles of the stage
+    constexpr int B_BYTES = 2 * NSUB * BSUB_BYTES;   // hi + lo (or hi + bf16 W + bf16 W_lo), all sub-tiles of the stage
+    constexpr int BBF_BYTES = COUT * KS * 2;         // one bf16 [COUT x KS] weight slice
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                  ((uint32_t)(TILE_M >> 4) << 24);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(TILE_M >> 4) << 24);
     static_assert(CIN % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
@@ -695,8 +768,23 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     tc_fence_after();
                 }
                 if (!(dbg & 1)) {
-                    tmem_st32(taddr + sub * 32, v);
-                    tmem_st32(taddr + KS + sub * 32, lo);
+                    if constexpr (BF16C) {
+                        // stage columns: [0,KS) hi (tf32) | [KS, KS+KS/2) lo as bf16 pairs | [KS+KS/2, 2KS) value as bf16
+                        uint32_t lob[16], hib[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float h0 = __uint_as_float(v[2 * j]), h1 = __uint_as_float(v[2 * j + 1]);
+                            const float l0 = __uint_as_float(lo[2 * j]), l1 = __uint_as_float(lo[2 * j + 1]);
+                            lob[j] = pack_bf16x2(l0, l1);
+                            hib[j] = pack_bf16x2(h0 + l0, h1 + l1);
+                        }
+                        tmem_st32(taddr + sub * 32, v);
+                        tmem_st16(taddr + KS + sub * 16, lob);
+                        tmem_st16(taddr + KS + KS / 2 + sub * 16, hib);
+                    } else {
+                        tmem_st32(taddr + sub * 32, v);
+                        tmem_st32(taddr + KS + sub * 32, lo);
+                    }
                 }
             }
             tmem_st_wait();
@@ -766,19 +854,42 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
                     const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
                     const uint32_t first = (started >> tile) & 1u;
+                    if constexpr (BF16C) {
+                        // weights of the stage: [NSUB x (COUT x 128 B) tf32 hi] [COUT x KS bf16 W] [COUT x KS bf16 W_lo]
+                        const uint32_t wbf = b_base + NSUB * BSUB_BYTES;
+                        const uint64_t db_w = KS == 64 ? umma_desc_sw128(wbf) : umma_desc_sw64(wbf);
+                        const uint64_t db_wlo = KS == 64 ? umma_desc_sw128(wbf + BBF_BYTES) : umma_desc_sw64(wbf + BBF_BYTES);
 #pragma unroll
-                    for (int sub = 0; sub < NSUB; ++sub) {
-                        const uint64_t db_hi = umma_desc_sw128(b_base + (sub * 2) * BSUB_BYTES);
-                        const uint64_t db_lo = umma_desc_sw128(b_base + (sub * 2 + 1) * BSUB_BYTES);
+                        for (int sub = 0; sub < NSUB; ++sub) {
+                            const uint64_t db_hi = umma_desc_sw128(b_base + sub * BSUB_BYTES);
 #pragma unroll
-                        for (int ks = 0; ks < KC / 8; ++ks) {
-                            if (dbg & 4) break;
-                            const uint64_t adv = (uint64_t)(ks * 2);                   // B: 8 fp32 = 32 B = 2 x 16 B
-                            const uint32_t a_hi = a_stage + (uint32_t)(sub * 32 + ks * 8);   // A: 8 TMEM columns
-                            const uint32_t a_lo = a_hi + KS;
-                            umma_tf32_ts(d, a_lo, db_hi + adv, IDESC, (first || sub > 0 || ks > 0) ? 1u : 0u);
-                            umma_tf32_ts(d, a_hi, db_lo + adv, IDESC, 1u);
-                            umma_tf32_ts(d, a_hi, db_hi + adv, IDESC, 1u);
+                            for (int k16 = 0; k16 < 2; ++k16) {
+                                if (dbg & 4) break;
+                                const uint32_t a_hi = a_stage + (uint32_t)(sub * 32 + k16 * 16);
+                                const uint32_t a_lob = a_stage + (uint32_t)(KS + sub * 16 + k16 * 8);
+                                const uint32_t a_hib = a_lob + KS / 2;
+                                const uint64_t adv_bf = (uint64_t)((sub * 2 + k16) * 2);     // 16 bf16 = 32 B
+                                umma_bf16_ts(d, a_lob, db_w + adv_bf, IDESC_BF, (first || sub > 0 || k16 > 0) ? 1u : 0u);
+                                umma_bf16_ts(d, a_hib, db_wlo + adv_bf, IDESC_BF, 1u);
+                                umma_tf32_ts(d, a_hi, db_hi + (uint64_t)(k16 * 4), IDESC, 1u);
+                                umma_tf32_ts(d, a_hi + 8, db_hi + (uint64_t)(k16 * 4 + 2), IDESC, 1u);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int sub = 0; sub < NSUB; ++sub) {
+                            const uint64_t db_hi = umma_desc_sw128(b_base + (sub * 2) * BSUB_BYTES);
+                            const uint64_t db_lo = umma_desc_sw128(b_base + (sub * 2 + 1) * BSUB_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < KC / 8; ++ks) {
+                                if (dbg & 4) break;
+                                const uint64_t adv = (uint64_t)(ks * 2);                   // B: 8 fp32 = 32 B = 2 x 16 B
+                                const uint32_t a_hi = a_stage + (uint32_t)(sub * 32 + ks * 8);   // A: 8 TMEM columns
+                                const uint32_t a_lo = a_hi + KS;
+                                umma_tf32_ts(d, a_lo, db_hi + adv, IDESC, (first || sub > 0 || ks > 0) ? 1u : 0u);
+                                umma_tf32_ts(d, a_hi, db_lo + adv, IDESC, 1u);
+                                umma_tf32_ts(d, a_hi, db_hi + adv, IDESC, 1u);
+                            }
                         }
                     }
                     umma_commit(bar_a_empty + 8 * aslot);
@@ -800,7 +911,8 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                 mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / B_STAGES)) & 1u) ^ 1u);
                 const unsigned e = b_sched[ib];
                 const int tap = e & 31, ch = e >> 5;
-                const float* src = wpacked + ((size_t)(tap * (CIN / KC) + ch * NSUB) * 2) * COUT * KC;
+                // both packed formats keep one contiguous B_BYTES block per (tap, KS-channel stage)
+                const float* src = wpacked + (size_t)(tap * NCHUNK + ch) * (B_BYTES / 4);
                 mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
                 bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
             }
@@ -869,11 +981,11 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool BF16C>
 int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
                    const unsigned int* tile_masks, int n_out, int K, float* out, cudaStream_t stream) {
     const size_t smem = ts_smem_bytes(CIN, COUT);
-    auto kern = k_spconv_umma_ts<CIN, COUT>;
+    auto kern = k_spconv_umma_ts<CIN, COUT, BF16C>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
     const int tmax = ts_tiles_max(COUT);
@@ -900,8 +1012,9 @@ bool tc_shape_ok(int K, int cin, int cout) {
 
 #define UD_DISPATCH_UMMA(CI, CO)                                                                          \
     if (cin == CI && cout == CO)                                                                          \
-        return variant == 1 ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)    \
-                            : launch_umma_ts<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+        return variant == 1   ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)            \
+               : variant == 2 ? launch_umma_ts<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)  \
+                              : launch_umma_ts<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
 
 extern "C" {
 
@@ -927,12 +1040,20 @@ int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes) {
     return UD_OK;
 }
 
-// w: (K, cin, cout) f32 (the layout ud_sparse_conv_forward takes) -> packed hi/lo swizzled image (16-byte aligned).
-int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream_) {
+// w: (K, cin, cout) f32 (the layout ud_sparse_conv_forward takes) -> packed swizzled image (16-byte aligned) for
+// kernel `variant` (same meaning as in ud_sparse_conv_tc_forward; the image size does not depend on it).
+int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, int variant,
+                                   void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!w || !packed) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
     if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
+    if (variant == 0) {
+        k_pack_weights_bf<<<ud_blocks((long long)K * cin * cout, 256), 256, 0, stream>>>(
+            w, K, cin, cout, ts_ks(cin, cout), (unsigned char*)packed);
+        UD_LAUNCH_CHECK();
+        return UD_OK;
+    }
     k_pack_weights<<<ud_blocks((long long)K * cin * cout, 256), 256, 0, stream>>>(w, K, cin, cout, (float*)packed);
     UD_LAUNCH_CHECK();
     return UD_OK;
@@ -955,7 +1076,8 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
 // in (n_in, cin) f32, 16-byte aligned rows; wpacked from ud_sparse_conv_tc_pack_weights; bias (cout)|NULL;
 // nbr_t (K, n_out) int32 tap-major gather table and tile_masks (ceil(n_out/128)) from ud_rulebook_transpose;
 // out (n_out, cout) f32.
-// variant: 0 = default (A operand through TMEM, "TS"), 1 = A operand through shared memory ("SS").
+// variant: 0 = default (A through TMEM, bf16 correction MMAs), 1 = A through shared memory, 3xTF32 ("SS"),
+//          2 = A through TMEM, 3xTF32.  The weights must have been packed for the same variant.
 int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               int variant, void* stream_) {

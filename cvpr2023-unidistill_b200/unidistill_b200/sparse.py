@@ -148,7 +148,8 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 # tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
 # every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
-TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))   # 0: A through TMEM (default), 1: A through smem
+# 0: A through TMEM + bf16 correction MMAs (default), 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
+TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))
 
 
 def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
@@ -161,10 +162,10 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
     if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout):
         nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout)
         packed = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
+        rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_pack_weights")
         if meta is not None:
-            meta["kernel"] = "k_spconv_umma_ts" if TC_VARIANT == 0 else "k_spconv_umma"
+            meta["kernel"] = "k_spconv_umma" if TC_VARIANT == 1 else "k_spconv_umma_ts"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
         rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
                                native.ptr(packed), native.ptr(bias), native.ptr(table_t), native.ptr(masks), n_out, K,

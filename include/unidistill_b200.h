@@ -100,7 +100,7 @@ int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int
  * swizzled hi/lo image the kernel's bulk copies read (packed_bytes from ud_sparse_conv_tc_weight_bytes). */
 int ud_sparse_conv_tc_supported(int K, int cin, int cout);
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
-int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
+int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, int variant, void* stream);
 /* development aid: device buffer of 16 uint64 receiving role-level cycle counts of the tensor-core kernel; NULL = off */
 int ud_debug_umma_prof(void* buf);
 /* development aid: disables pipeline roles of the tensor-core kernel (results become wrong); 0 = normal operation */
@@ -109,7 +109,8 @@ int ud_debug_umma_flags(int flags);
  * base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
  * tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
-/* variant 0 = default kernel (A operand staged through TMEM), 1 = A operand staged through shared memory */
+/* variant 0 = default kernel (A operand staged through TMEM; hi*hi in TF32, the two correction products as bf16 MMAs),
+ * 1 = A through shared memory with 3xTF32, 2 = A through TMEM with 3xTF32; pack the weights for the same variant */
 int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               int variant, void* stream);

@@ -26,7 +26,7 @@ def _cloud(rng, B, shape, n, C):
     return coords, feat
 
 
-@pytest.fixture(params=[0, 1], ids=["A-via-TMEM", "A-via-smem"], autouse=True)
+@pytest.fixture(params=[0, 1, 2], ids=["TMEM-A+bf16-corrections", "smem-A-3xTF32", "TMEM-A-3xTF32"], autouse=True)
 def tc_variant(request):
     from unidistill_b200 import sparse
 
