@@ -151,12 +151,28 @@ class KernelTimer:
     def __init__(self):
         self.enabled = False
         self.records = []
+        self._pool = []
+
+    def prepare(self, n_pairs):
+        """Creates (and materialises, by recording once) n_pairs event pairs ahead of the timed region:
+        cudaEventCreate inside the region contends with NVML clock sampling for a driver lock."""
+        self._pool = []
+        for _ in range(int(n_pairs)):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            e1.record()
+            self._pool.append((e0, e1))
+        torch.cuda.synchronize()
 
     def call(self, key, meta, fn, *args):
         if not self.enabled:
             return fn(*args)
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        if self._pool:
+            e0, e1 = self._pool.pop()
+        else:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
