@@ -387,6 +387,7 @@ def run_ours(args):
     from unidistill_b200 import native
 
     native.load()
+    torch.backends.cudnn.benchmark = os.environ.get("UD_CUDNN_BENCHMARK", "1") != "0"   # dense BEV/head convs: autotune
     world, rank, local = _dist_setup(args.gpus)
     device = torch.device("cuda", local if world > 1 else 0)
     wl = WORKLOADS[args.workload](device, rank)
