@@ -110,6 +110,26 @@ def test_voxelize_random_ragged_batch(cuda, native_lib, seed):
     _check_voxelize(cuda, clouds, vs, rg, grid, 3, 100000)
 
 
+def test_mmdet3d_style_aliases(cuda, native_lib):
+    """hard_voxelize(points, voxels, coors, num, ...) / Voxelization(...) with the mmdet3d signatures."""
+    from unidistill_b200.mmdet3d_compat import Voxelization, hard_voxelize
+
+    rng = np.random.default_rng(2)
+    pts = (rng.standard_normal((3000, 4)) * np.array([4, 4, 1, 1])).astype(np.float32)
+    vs, pr = [0.5, 0.5, 0.5], [-8.0, -8.0, -2.0, 8.0, 8.0, 2.0]
+    rv, rc, rn, _ = O.voxelize_one(pts, vs, pr, [32, 32, 8], 5, 600)
+    p = torch.from_numpy(pts).to(cuda)
+    voxels = torch.zeros((600, 5, 4), device=cuda)
+    coors = torch.zeros((600, 3), dtype=torch.int32, device=cuda)
+    num = torch.zeros((600,), dtype=torch.int32, device=cuda)
+    m = hard_voxelize(p, voxels, coors, num, vs, pr, 5, 600)
+    assert m == rc.shape[0]
+    assert np.array_equal(coors[:m].cpu().numpy(), rc) and np.array_equal(num[:m].cpu().numpy(), rn)
+    assert np.array_equal(voxels[:m].cpu().numpy(), rv)
+    v2, c2, n2 = Voxelization(vs, pr, 5, max_voxels=(600, 700))(p)
+    assert np.array_equal(c2.cpu().numpy(), rc) and np.array_equal(v2.cpu().numpy(), rv)
+
+
 def test_voxelize_full_size_sample(cuda, native_lib):
     """BASELINE config sizes: 40k x 10 sweeps, 0.1 m grid, cap 120000 (binds)."""
     from unidistill_b200 import synthetic as S

@@ -38,6 +38,7 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, u
 __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mma, long long* out, int st_iters) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar2[4];
     __shared__ uint32_t tmem_base_s;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mm
     for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 256) reinterpret_cast<float*>(smem_raw)[i] = 0.001f * (i & 63);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -63,6 +65,32 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mm
         long long t0 = 0, t1 = 0;
         for (int rep = 0; rep < 3; ++rep) {
             t0 = clock64();
+            if (mode == 7 || mode == 8) {
+                // stage loop: wait on the barrier committed 2 (mode 7) / 4 (mode 8) groups ago, then 16 MMAs + commit
+                const int depth = mode == 7 ? 2 : 4;
+                const int groups = n_mma / 16;
+                for (int g = 0; g < groups; ++g) {
+                    if (g >= depth) {
+                        const int gg = g - depth;
+                        uint32_t done;
+                        do {
+                            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                         : "=r"(done) : "r"(smem_u32(&bar2[gg % 4])), "r"((uint32_t)(((gg / 4) + rep * ((groups + 3) / 4)) & 1)) : "memory");
+                        } while (!done);
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one_sync()) {
+                        const uint64_t db = desc_sw128(base + 16384);
+                        for (int i = 0; i < 16; ++i)
+                            mma_ts(tmem, tmem + 480 + (i & 3) * 8, db + (uint64_t)((i & 3) * 2), idesc, 1u);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[g % 4])) : "memory");
+                    }
+                    __syncwarp();
+                }
+                if (elect_one_sync())
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                __syncwarp();
+            } else
             if (elect_one_sync()) {
                 const uint64_t da = desc_sw128(base), db = desc_sw128(base + 16384);
                 for (int i = 0; i < n_mma; ++i) {
@@ -111,15 +139,15 @@ int main() {
     long long* d_out;
     cudaMalloc(&d_out, 148 * sizeof(long long));
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc"};
+    const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc", "?", "TS staged d2", "TS staged d4"};
     const int Ns[] = {16, 32, 64, 128, 256};
     for (int grid : {148})
-        for (int mode = 0; mode < 6; ++mode)
+        for (int mode : {2, 7, 8})
             for (int N : Ns) {
                 if ((mode == 1 || mode == 3) && N > 256) continue;
                 if (mode == 4 && N > 128) continue;
-                if ((mode == 2 || mode == 3) && N > 224) continue;   // acc must not overlap the A columns at 480
-                for (int n_mma : {16, 256}) {
+                if ((mode == 2 || mode == 3 || mode >= 7) && N > 224) continue;   // acc must not overlap the A columns at 480
+                for (int n_mma : {256}) {
                   for (int st_iters : {0, 100000}) {
                     if (st_iters && (mode != 2 || n_mma != 256)) continue;
                     probe<<<grid, 256, 64 * 1024>>>(mode, N, 128, n_mma, d_out, st_iters);
