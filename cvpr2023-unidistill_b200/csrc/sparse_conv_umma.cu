@@ -179,20 +179,25 @@ k_pack_weights(const float* __restrict__ w, int K, int cin, int cout, float* __r
 //   [KS/32 sub-tiles: COUT x 32 tf32 hi, 128-byte swizzle] [COUT x KS bf16 W] [COUT x KS bf16 (W - hi)]
 // with the bf16 slices in the 128-byte (KS = 64) or 64-byte (KS = 32) swizzle.  Block size = 8 * COUT * KS bytes.
 __global__ void __launch_bounds__(256)
-k_pack_weights_bf(const float* __restrict__ w, int K, int cin, int cout, int ks, unsigned char* __restrict__ packed) {
+k_pack_weights_bf(const float* __restrict__ w, int K, int cin, int cout, int ks, int tapg,
+                  unsigned char* __restrict__ packed) {
+    // virtual layer: K_eff = ceil(K / tapg) super-taps of cin * tapg channels (taps >= K contribute zeros)
+    const int cin_eff = cin * tapg;
+    const int k_eff = (K + tapg - 1) / tapg;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)K * cin * cout;
+    const long long total = (long long)k_eff * cin_eff * cout;
     if (t >= total) return;
     const int n = (int)(t % cout);
-    const int c = (int)((t / cout) % cin);
-    const int k = (int)(t / ((long long)cout * cin));
-    const float v = w[t];                                   // w[k][c][n]
+    const int cv = (int)((t / cout) % cin_eff);             // virtual channel = g * cin + c
+    const int kj = (int)(t / ((long long)cout * cin_eff));
+    const int tap = kj * tapg + cv / cin, c = cv % cin;
+    const float v = tap < K ? w[((size_t)tap * cin + c) * cout + n] : 0.f;      // w[k][c][n]
     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     const float lo = v - hi;
-    const int nstage = cin / ks;
-    const int stage = c / ks, e = c % ks;                   // channel within the stage
+    const int nstage = cin_eff / ks;
+    const int stage = cv / ks, e = cv % ks;                 // channel within the stage
     const int nsub = ks / KC;
-    unsigned char* blk = packed + (size_t)(k * nstage + stage) * ((size_t)8 * cout * ks);
+    unsigned char* blk = packed + (size_t)(kj * nstage + stage) * ((size_t)8 * cout * ks);
     {   // tf32 hi: sub-tile e/32, row n, 32 floats, 16-byte chunks XOR (n & 7)
         const int sub = e / KC, ee = e % KC;
         const int pos = (((ee >> 2) ^ (n & 7)) << 2) | (ee & 3);
@@ -223,9 +228,10 @@ k_transpose_table(const int* __restrict__ src, int n, int K, int ld, int* __rest
     }
     __syncthreads();
     unsigned int m = 0u;
-    for (int k = ty; k < K; k += 8) {
+    const int k_pad = (K + 3) / 4 * 4;                 // rows [K, k_pad) = -1: multi-tap stages read whole tap groups
+    for (int k = ty; k < k_pad; k += 8) {
         const int r = r0 + tx;
-        const int v = tile[tx][k];
+        const int v = k < K ? tile[tx][k] : -1;
         if (r < ld) dst[(size_t)k * ld + r] = v;
         const unsigned any = __ballot_sync(0xffffffffu, r < n && v >= 0);
         if (any) m |= 1u << k;
@@ -548,11 +554,14 @@ constexpr int TS_IDX_STAGES = 16;
 __host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
 // channels per stage: 64 halves the per-stage handshake cost, but with COUT = 128 only two tiles share a weight slice
 // and the 64 KB slices would make the kernel L2-bound, so those shapes keep 32-channel stages
-__host__ __device__ constexpr int ts_ks(int cin, int cout) { return (cin >= 64 && cout <= 64) ? 64 : 32; }
+// Narrow layers (CIN = 16 / 32) put 4 / 2 consecutive kernel taps into one 64-wide stage (a "super-tap": the gathered
+// rows of the taps side by side along K, their weights stacked), which halves / quarters the number of stages.
+__host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin : 1; }
+__host__ __device__ constexpr int ts_ks(int cin, int cout) { return (cin < 64 || cout <= 64) ? 64 : 32; }
 __host__ __device__ constexpr int ts_raw_stages(int cin, int cout) { return 4; }
 __host__ __device__ constexpr size_t ts_smem_bytes(int cin, int cout) {
     return (size_t)ts_raw_stages(cin, cout) * TILE_M * ts_ks(cin, cout) * 4 +
-           (size_t)B_STAGES * 2 * cout * ts_ks(cin, cout) * 4 + (size_t)TS_IDX_STAGES * TILE_M * 4 + 1024;
+           (size_t)B_STAGES * 2 * cout * ts_ks(cin, cout) * 4 + (size_t)TS_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 + 1024;
 }
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -639,9 +648,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
                  int tiles, float* __restrict__ out) {
-    constexpr int KS = ts_ks(CIN, COUT);             // channels per stage
+    constexpr int TAPG = BF16C ? ts_tapg(CIN) : 1;   // kernel taps per stage (narrow layers, see ts_tapg)
+    constexpr int KS = TAPG > 1 ? 64 : (BF16C ? ts_ks(CIN, COUT) : (CIN >= 64 && COUT <= 64 ? 64 : 32));
     constexpr int NSUB = KS / KC;                    // 32-channel sub-tiles per stage
-    constexpr int NCHUNK = CIN / KS;                 // stages per tap
+    constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
+    constexpr int IDX_INTS = TAPG * TILE_M;          // row indices of one stage
     constexpr int A_COLS = 2 * KS;                   // TMEM columns of one A stage: KS hi | KS lo
     constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
     constexpr int RAW_STAGES = ts_raw_stages(CIN, COUT);
@@ -654,9 +665,10 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                                   ((uint32_t)(TILE_M >> 4) << 24);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                ((uint32_t)(TILE_M >> 4) << 24);
-    static_assert(CIN % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert((CIN * TAPG) % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
     static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
     static_assert(RAW_STAGES % 2 == 0 && A_STAGES % 2 == 0, "two groups alternate over the rings");
+    static_assert(TAPG == 1 || (NCHUNK == 1 && (CIN == 16 || CIN == 32)), "multi-tap stages: CIN 16 or 32");
     constexpr int NBAR = 2 * RAW_STAGES + 2 * A_STAGES + 2 * B_STAGES + 2 * TS_IDX_STAGES + 1;
 
     extern __shared__ unsigned char smem_raw[];
@@ -713,13 +725,21 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
+    const int K_eff = (K + TAPG - 1) / TAPG;             // (super-)taps
     if (tid < MAX_TILES) {
         const int tile_g = blockIdx.x * tiles + tid;
-        tile_mask_s[tid] = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+        unsigned int m = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+        if (TAPG > 1) {                                  // bit j <- any tap of group j present in the tile
+            unsigned int me = 0u;
+            for (int j = 0; j < K_eff; ++j)
+                if ((m >> (j * TAPG)) & ((1u << TAPG) - 1u)) me |= 1u << j;
+            m = me;
+        }
+        tile_mask_s[tid] = m;
     }
     if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
     __syncthreads();
-    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
+    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K_eff, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -805,12 +825,21 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
             long long tw = PF_T();
             mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / TS_IDX_STAGES)) & 1u);
             w_idx += PF_T() - tw;
-            int idx[8];
+            // (tap slot, channel offset) of this thread's 16-byte chunk in sub-tile `sub`:
+            //   TAPG 1: one tap, channels c0 + sub*32 + chunk*4      TAPG 2 (CIN 32): tap = sub, channels chunk*4
+            //   TAPG 4 (CIN 16): tap = 2*sub + chunk/4, channels (chunk%4)*4
+            int idx[8][NSUB];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) idx[j] = idx_ring[islot * TILE_M + rbase + 16 * j];
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    const int gslot = TAPG == 1 ? 0 : (TAPG == 2 ? sub : 2 * sub + (chunk >> 2));
+                    idx[j][sub] = (TAPG == 1 && sub > 0) ? idx[j][0]
+                                                         : idx_ring[islot * IDX_INTS + gslot * TILE_M + rbase + 16 * j];
+                }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
-            const int c0 = ((a_sched[it] >> 5) & 7) * KS + chunk * 4;
+            const int c0 = TAPG == 1 ? ((a_sched[it] >> 5) & 7) * KS + chunk * 4 : (TAPG == 2 ? chunk * 4 : (chunk & 3) * 4);
             tw = PF_T();
             mbar_wait(bar_raw_empty + 8 * rslot, (((uint32_t)(it / RAW_STAGES)) & 1u) ^ 1u);
             w_raw += PF_T() - tw;
@@ -818,12 +847,13 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int rr = rbase + 16 * j;
-                const bool ok = idx[j] >= 0;
-                const float* src = in + (ok ? ((size_t)idx[j] * CIN + c0) : 0);
                 const uint32_t dst = dst0 + swz_off(rr, chunk);
 #pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub)
-                    if (!(dbg & 2)) cp_async_16(dst + sub * SUB_BYTES, src + sub * KC, ok ? 16u : 0u);
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    const bool ok = idx[j][sub] >= 0;
+                    const float* src = in + (ok ? ((size_t)idx[j][sub] * CIN + c0 + (TAPG == 1 ? sub * KC : 0)) : 0);
+                    if (!(dbg & 2)) cp_async_16(dst + sub * SUB_BYTES, src, ok ? 16u : 0u);
+                }
             }
             cp_async_arrive_noinc(bar_raw_full + 8 * rslot);
         }
@@ -922,9 +952,12 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                 const int islot = it % TS_IDX_STAGES;
                 mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / TS_IDX_STAGES)) & 1u) ^ 1u);
                 const unsigned e = a_sched[it];
-                const int* seg = nbr_t + (size_t)(e & 31) * ld_t + row0 + (e >> 8) * TILE_M;
-                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, TILE_M * 4);
-                bulk_g2s(smem_idx + islot * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
+                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, IDX_INTS * 4);
+#pragma unroll
+                for (int g = 0; g < TAPG; ++g) {       // taps of the group; rows [K, K4) of the table are -1
+                    const int* seg = nbr_t + (size_t)((e & 31) * TAPG + g) * ld_t + row0 + (e >> 8) * TILE_M;
+                    bulk_g2s(smem_idx + (islot * TAPG + g) * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
+                }
             }
         }
         __syncwarp();
@@ -999,12 +1032,17 @@ int launch_umma_ts(const float* in, const float* wpacked, const float* bias, con
     return UD_OK;
 }
 
-// forward shapes of VoxelResBackBone8x with C >= 32 and the dgrad (cin/cout swapped) of every layer but the first
-bool tc_shape_ok(int K, int cin, int cout) {
+// forward shapes of VoxelResBackBone8x and the dgrad (cin/cout swapped) of every layer but the first; the CIN = 16
+// shapes exist only in the default variant (multi-tap stages)
+bool tc_shape_ok(int K, int cin, int cout, int variant) {
     static const int shapes[][2] = {{32, 16}, {32, 32}, {32, 64}, {64, 32}, {64, 64}, {64, 128}, {128, 64}, {128, 128}};
-    if (K < 1 || K > MAX_TAPS) return false;
+    static const int narrow[][2] = {{16, 16}, {16, 32}};
+    if (K < 1 || K > MAX_TAPS || variant < 0 || variant > 2) return false;
     for (const auto& s : shapes)
         if (s[0] == cin && s[1] == cout) return true;
+    if (variant == 0)
+        for (const auto& s : narrow)
+            if (s[0] == cin && s[1] == cout) return true;
     return false;
 }
 
@@ -1030,13 +1068,16 @@ int ud_debug_umma_flags(int flags) {
     return UD_OK;
 }
 
-// 1 when (K, cin, cout) has a tensor-core instantiation, else 0.
-int ud_sparse_conv_tc_supported(int K, int cin, int cout) { return tc_shape_ok(K, cin, cout) ? 1 : 0; }
+// 1 when (K, cin, cout) has a tensor-core instantiation in kernel `variant`, else 0.
+int ud_sparse_conv_tc_supported(int K, int cin, int cout, int variant) {
+    return tc_shape_ok(K, cin, cout, variant) ? 1 : 0;
+}
 
-int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes) {
+int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, int variant, size_t* bytes) {
     if (!bytes) return UD_ERR_INVALID_ARG;
-    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
-    *bytes = (size_t)K * cin * cout * 2 * sizeof(float);
+    if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
+    const int tapg = variant == 0 ? ts_tapg(cin) : 1;
+    *bytes = (size_t)((K + tapg - 1) / tapg) * (cin * tapg) * cout * 2 * sizeof(float);
     return UD_OK;
 }
 
@@ -1046,11 +1087,13 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
                                    void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!w || !packed) return UD_ERR_INVALID_ARG;
-    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
     if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
     if (variant == 0) {
-        k_pack_weights_bf<<<ud_blocks((long long)K * cin * cout, 256), 256, 0, stream>>>(
-            w, K, cin, cout, ts_ks(cin, cout), (unsigned char*)packed);
+        const int tapg = ts_tapg(cin);
+        const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
+        k_pack_weights_bf<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, ts_ks(cin, cout), tapg,
+                                                                      (unsigned char*)packed);
         UD_LAUNCH_CHECK();
         return UD_OK;
     }
@@ -1059,7 +1102,8 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     return UD_OK;
 }
 
-// nbr (n, K) int32 row-major gather table -> nbr_t (K, ld) tap-major, ld = n rounded up to 128 (padding = -1, base
+// nbr (n, K) int32 row-major gather table -> nbr_t (K4, ld) tap-major, K4 = K rounded up to 4 and ld = n rounded up to 128
+// (all padding = -1, base
 // 16-byte aligned so every (tile, tap) index segment can be bulk-copied) + tile_masks (ceil(n/128)) uint32 (bit k set
 // when tap k occurs in the 128-row tile): the two inputs ud_sparse_conv_tc_forward reads.
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream_) {
@@ -1084,9 +1128,15 @@ int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* wpacked = (const float*)wpacked_;
     if (!in || !wpacked || !nbr_t || !tile_masks || !out || n_out < 0) return UD_ERR_INVALID_ARG;
-    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
     if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out) & 15u) != 0) return UD_ERR_INVALID_ARG;
     if (n_out == 0) return UD_OK;
+    if (variant == 0) {
+        if (cin == 16 && cout == 16)
+            return launch_umma_ts<16, 16, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+        if (cin == 16 && cout == 32)
+            return launch_umma_ts<16, 32, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+    }
     UD_DISPATCH_UMMA(32, 16)
     UD_DISPATCH_UMMA(32, 32)
     UD_DISPATCH_UMMA(32, 64)

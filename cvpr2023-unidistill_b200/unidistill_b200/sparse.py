@@ -45,7 +45,7 @@ class Rulebook:
         if t is None:
             n, K = int(table.shape[0]), int(table.shape[1])
             ld = (n + 127) // 128 * 128            # padded with -1: whole 512-byte index segments per (tile, tap)
-            tt = torch.empty((K, ld), dtype=torch.int32, device=table.device)
+            tt = torch.empty(((K + 3) // 4 * 4, ld), dtype=torch.int32, device=table.device)
             masks = torch.empty(((n + 127) // 128,), dtype=torch.int32, device=table.device)
             rc = native.load().ud_rulebook_transpose(native.ptr(table), n, K, native.ptr(tt), native.ptr(masks),
                                                      native.stream_ptr(table.device))
@@ -159,8 +159,8 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
     sp = native.stream_ptr(dev)
     meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
             "table": table} if native.TIMER.enabled else None
-    if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout):
-        nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout)
+    if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout, TC_VARIANT):
+        nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout, TC_VARIANT)
         packed = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_pack_weights")

@@ -98,15 +98,15 @@ int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int
  * accumulators in TMEM; csrc/sparse_conv_umma.cu).  Same arithmetic contract as ud_sparse_conv_forward for
  * the (cin, cout) pairs ud_sparse_conv_tc_supported() accepts; the weights are first packed into the
  * swizzled hi/lo image the kernel's bulk copies read (packed_bytes from ud_sparse_conv_tc_weight_bytes). */
-int ud_sparse_conv_tc_supported(int K, int cin, int cout);
-int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
+int ud_sparse_conv_tc_supported(int K, int cin, int cout, int variant);
+int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, int variant, size_t* bytes);
 int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, int variant, void* stream);
 /* development aid: device buffer of 16 uint64 receiving role-level cycle counts of the tensor-core kernel; NULL = off */
 int ud_debug_umma_prof(void* buf);
 /* development aid: disables pipeline roles of the tensor-core kernel (results become wrong); 0 = normal operation */
 int ud_debug_umma_flags(int flags);
-/* nbr (n,K) row-major gather table -> nbr_t (K,ld) tap-major with ld = n rounded up to 128 (padding -1; 16-byte aligned
- * base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
+/* nbr (n,K) row-major gather table -> nbr_t (K4,ld) tap-major with K4 = K rounded up to 4, ld = n rounded up to 128
+ * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
  * tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
 /* variant 0 = default kernel (A operand staged through TMEM; hi*hi in TF32, the two correction products as bf16 MMAs),

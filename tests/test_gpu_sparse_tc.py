@@ -40,12 +40,12 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
 
 
-@pytest.mark.parametrize("cin,cout", [(32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64),
-                                      (128, 128)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (64, 128),
+                                      (128, 64), (128, 128)])
 def test_tc_subm_matches_oracle(cuda, native_lib, cin, cout):
     from unidistill_b200 import sparse
 
-    assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout) == 1
+    assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 0) == 1
     rng = np.random.default_rng(cin * 7 + cout)
     B, shape, n = 2, [7, 20, 20], 1931                     # 1931 rows: 15 full tiles + a ragged tail
     coords, feat = _cloud(rng, B, shape, n, cin)
@@ -70,7 +70,7 @@ def test_tc_subm_matches_oracle(cuda, native_lib, cin, cout):
     assert float((np.abs(out_tc - ref).max(axis=1) / row_scale).max()) < 1e-3
 
 
-@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
+@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(16, 32, 3, 2, 1), (32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
                                                        (128, 128, (3, 1, 1), (2, 1, 1), 0)])
 def test_tc_strided_matches_oracle(cuda, native_lib, cin, cout, ksize, stride, pad):
     from unidistill_b200 import sparse

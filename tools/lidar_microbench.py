@@ -101,7 +101,7 @@ def main():
             ms, out = timed(lambda: sparse.sparse_conv(x, w, None, rb))
         byt = rb.n_in * cin * 4 + rb.n_out * cout * 4 + rb.n_out * rb.K * 4 + rb.K * cin * cout * 4
         rows.append(("conv %s %d->%d N=%d P=%d" % (kind, cin, cout, rb.n_out, P), ms, byt, 2.0 * P * cin * cout))
-        if sparse.USE_TENSOR_CORES and native.load().ud_sparse_conv_tc_supported(rb.K, cin, cout):
+        if sparse.USE_TENSOR_CORES and native.load().ud_sparse_conv_tc_supported(rb.K, cin, cout, sparse.TC_VARIANT):
             sparse.USE_TENSOR_CORES = False
             with torch.no_grad():
                 ms2, out2 = timed(lambda: sparse.sparse_conv(x, w, None, rb))
