@@ -193,6 +193,7 @@ class LidarForward:
         cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
         self.model = models.BEVFusionCenterHead(cfg).to(device).train()   # BN on batch statistics (student and
         self.model.use_channels_last(os.environ.get("UD_CHANNELS_LAST", "1") != "0")  # teacher both run so, quirk 9)
+        self.model.use_cuda_graph(os.environ.get("UD_DENSE_GRAPH", "1") != "0")
         batch = S.lidar_batch(BS_PER_GPU, seed=seed + rank)
         self.points_host = batch["points"].pin_memory()                   # (B, Nmax, 5) zero padded (collate_fn)
         self.gt_host = _gt_with_labels(batch).pin_memory()

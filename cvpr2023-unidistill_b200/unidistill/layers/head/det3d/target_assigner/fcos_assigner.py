@@ -117,7 +117,7 @@ class FCOSAssigner(BaseAssigner):
         near = torch.topk(d2, topk, dim=2, largest=False).indices              # (B, M, topk)
 
         heatmaps, inds, masks, cats, encs = {}, {}, {}, {}, {}
-        inf = torch.tensor(float("inf"), device=device)
+        inf = torch.full((), float("inf"), device=device)      # device-side fill: CUDA-graph capturable
         rank = torch.arange(max_objs, device=device).unsqueeze(0)
         for t, task in enumerate(self.tasks):
             n_cls = len(task["class_names"])

@@ -220,8 +220,69 @@ class DetHead(nn.Module):
         ret = self.dense_head(x, gt_boxes)
         if self.training:
             for _, enc in ret["box_encoding"].items():
-                enc[torch.isinf(enc)] = 0       # log(0) of padded boxes (quirk 10)
+                enc.masked_fill_(torch.isinf(enc), 0)       # log(0) of padded boxes (quirk 10); no host sync
         return ret
+
+
+class GraphedDenseTrunk:
+    """CUDA-graph replay of the dense 2-D part (BaseBEVBackbone + CenterHead towers) for gradient-free forwards.
+
+    That part is ~500 small cuDNN / elementwise launches with static shapes; issued eagerly from Python it costs more
+    host time than the GPU needs to execute it.  The graph is captured on first use per input signature (after a
+    warm-up on a side stream; BatchNorm running statistics are restored afterwards so the extra runs leave no
+    trace) and replayed on a static input buffer.  Outputs are static buffers, valid until the next call."""
+
+    def __init__(self, model):
+        self.model = model
+        self.key = None
+        self.graph = None
+        self.static_in = None
+        self.static_out = None
+
+    def _run(self, x, gt):
+        feats, pyramid = self.model.bev_encoder(x)
+        head = self.model.det_head.dense_head
+        h = head.shared_conv(feats)
+        if head.upsample_for_pedestrian:
+            h = head.upsample_conv(h)
+        ret = {"multi_head_features": [task(h) for task in head.tasks]}
+        if gt is not None and (head.training or head.distill):
+            # FCOSAssigner.assign_targets is a static-shape, sync-free tensor program: it rides in the same graph
+            ret.update(head.assign_targets(gt))
+            if head.training:
+                for _, enc in ret["box_encoding"].items():
+                    enc.masked_fill_(torch.isinf(enc), 0)     # log(0) of padded boxes (quirk 10)
+        return feats, pyramid, ret
+
+    def _bn_buffers(self):
+        mods = [self.model.bev_encoder, self.model.det_head.dense_head]
+        return [b for m in mods for b in m.buffers()]
+
+    def __call__(self, bev, gt=None):
+        head = self.model.det_head.dense_head
+        key = (tuple(bev.shape), tuple(bev.stride()), bev.dtype, bev.device, self.model.training, head.distill,
+               None if gt is None else (tuple(gt.shape), gt.dtype))
+        if self.graph is None or key != self.key:
+            snap = [b.detach().clone() for b in self._bn_buffers()]
+            self.static_in = bev.detach().clone(memory_format=torch.preserve_format)
+            self.static_gt = None if gt is None else gt.detach().clone()
+            side = torch.cuda.Stream(device=bev.device)
+            side.wait_stream(torch.cuda.current_stream(bev.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._run(self.static_in, self.static_gt)
+            torch.cuda.current_stream(bev.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_out = self._run(self.static_in, self.static_gt)
+            for b, v in zip(self._bn_buffers(), snap):
+                b.copy_(v)
+            self.key = key
+        self.static_in.copy_(bev)
+        if gt is not None:
+            self.static_gt.copy_(gt)
+        self.graph.replay()
+        return self.static_out
 
 
 class BEVFusionCenterHead(BaseMultiSensorFusion):
@@ -240,6 +301,12 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self.bev_encoder = BevEncoder(model_cfg.bev_encoder)
         self.det_head = DetHead(model_cfg.det_head)
         self._channels_last = False
+        self._dense_graph = None
+
+    def use_cuda_graph(self, enable=True):
+        """Gradient-free forwards replay the dense 2-D part from a CUDA graph (see GraphedDenseTrunk)."""
+        self._dense_graph = GraphedDenseTrunk(self) if enable else None
+        return self
 
     def use_channels_last(self, enable=True):
         """Keeps the dense 2-D part (BEV backbone, fusion conv, detection head, image nets) in NHWC memory so cuDNN's
@@ -272,13 +339,20 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         model_output = self.extract_bev(lidar_points, cameras_imgs, metas)
         if self._channels_last:
             model_output = model_output.contiguous(memory_format=torch.channels_last)
-        x = self.bev_encoder(model_output)
-        ret = self.det_head(x[0], gt_boxes)
+        if self._dense_graph is not None and not torch.is_grad_enabled() and model_output.is_cuda:
+            feats, pyramid, ret = self._dense_graph(model_output, gt_boxes)
+            x = (feats, pyramid)
+            head = self.det_head.dense_head
+            if not (head.training or head.distill):
+                ret = head.proposal_layer.generate_predicted_boxes(ret, {})
+        else:
+            x = self.bev_encoder(model_output)
+            ret = self.det_head(x[0], gt_boxes)
         if return_feature:
             return model_output, x[0], ret["multi_head_features"]
         if self.training:
             for _, enc in ret["box_encoding"].items():
-                enc[torch.isinf(enc)] = 0
+                enc.masked_fill_(torch.isinf(enc), 0)
             if normalisers is not None:
                 normalisers(ret)
             loss_rpn, tb_dict = self.det_head.dense_head.get_loss(ret)

@@ -3,6 +3,7 @@ dense()/scatter-to-BEV.  These are the primitives the `spconv` shim and the mirr
 `unidistill.layers` modules are made of (reference: layers/blocks_3d/det3d/spconv_backbone.py).
 """
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -152,7 +153,32 @@ USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
 TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))
 
 
-def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
+# id(weight) -> (weakref to the weight, its _version, kernel variant, packed image): re-pack only when the parameter
+# object is new or was modified in place (optimizer steps and load_state_dict bump _version)
+_PACK_CACHE = {}
+
+
+def _packed_weights(w_k, K, cin, cout, sp, weight=None):
+    lib = native.load()
+    if weight is not None:
+        hit = _PACK_CACHE.get(id(weight))
+        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == TC_VARIANT \
+                and hit[3].device == weight.device:
+            return hit[3]
+    w_k = w_k() if callable(w_k) else w_k
+    nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout, TC_VARIANT)
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=w_k.device)
+    rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), TC_VARIANT, sp)
+    native.check(rc, "ud_sparse_conv_tc_pack_weights")
+    if weight is not None:
+        if len(_PACK_CACHE) > 256:
+            for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
+                del _PACK_CACHE[k]
+        _PACK_CACHE[id(weight)] = (weakref.ref(weight), weight._version, TC_VARIANT, packed)
+    return packed
+
+
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None):
     lib = native.load()
     dev = feats.device
     out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
@@ -160,10 +186,7 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
     meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
             "table": table} if native.TIMER.enabled else None
     if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout, TC_VARIANT):
-        nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout, TC_VARIANT)
-        packed = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), TC_VARIANT, sp)
-        native.check(rc, "ud_sparse_conv_tc_pack_weights")
+        packed = _packed_weights(w_k, K, cin, cout, sp, weight)
         if meta is not None:
             meta["kernel"] = "k_spconv_umma" if TC_VARIANT == 1 else "k_spconv_umma_ts"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
@@ -174,6 +197,8 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None):
         return out
     if meta is not None:
         meta["kernel"] = "k_spconv_gather_gemm"
+    if callable(w_k):
+        w_k = w_k()
     rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_forward, native.ptr(feats),
                            native.ptr(w_k), native.ptr(bias), native.ptr(table),
                            n_out, K, cin, cout, native.ptr(out), sp)
@@ -196,18 +221,25 @@ class SparseConvFunction(Function):
         features = features.contiguous().float()
         rb = rulebook
         cout, cin = int(weight.shape[0]), int(weight.shape[-1])
-        w_k = weight_to_taps(weight.detach().float())
+        w_cell = []
+
+        def w_k_fn():                       # (K, Cin, Cout) copy, only materialised when something needs it
+            if not w_cell:
+                w_cell.append(weight_to_taps(weight.detach().float()))
+            return w_cell[0]
+
         if not inverse:
             table, n_out = rb.nbr_out, rb.n_out
         else:  # SparseInverseConv3d: roles of the paired strided conv swapped
             table, n_out = rb.nbr_in, rb.n_in
         assert features.shape[1] == cin, "feature width %d != conv in_channels %d" % (features.shape[1], cin)
         b = bias.detach().float().contiguous() if bias is not None else None
-        out = _conv_forward_raw(features, w_k, b, table, n_out, rb.K, cin, cout, rb)
+        out = _conv_forward_raw(features, w_k_fn, b, table, n_out, rb.K, cin, cout, rb, weight)
         ctx.rb, ctx.inverse = rb, inverse
         ctx.has_bias = bias is not None
         ctx.wshape = tuple(weight.shape)
-        ctx.save_for_backward(features, w_k)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(features, w_k_fn())
         return out
 
     @staticmethod
