@@ -647,7 +647,7 @@ template <int CIN, int COUT, bool BF16C>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
-                 int tiles, float* __restrict__ out) {
+                 int tiles, float* __restrict__ out, double* __restrict__ stats) {
     constexpr int TAPG = BF16C ? ts_tapg(CIN) : 1;   // kernel taps per stage (narrow layers, see ts_tapg)
     constexpr int KS = TAPG > 1 ? 64 : (BF16C ? ts_ks(CIN, COUT) : (CIN >= 64 && COUT <= 64 ? 64 : 32));
     constexpr int NSUB = KS / KC;                    // 32-channel sub-tiles per stage
@@ -679,6 +679,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     __shared__ unsigned short b_sched[MAX_TAPS * 4];       // tap | chunk << 5
     __shared__ unsigned short b_count[MAX_TAPS * 4];       // A stages that use this weight slice
     __shared__ int n_a_s, n_b_s;
+    __shared__ float col_sum_s[2 * 256];                   // fused BatchNorm statistics: per-column sum | sum of squares
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -686,6 +687,7 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     const int row0 = blockIdx.x * tiles * TILE_M;
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
     const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
+    if (stats != nullptr && tid < 2 * COUT) col_sum_s[(tid / COUT) * 256 + tid % COUT] = 0.f;
 
     unsigned long long* const prof = g_umma_prof;
     const int dbg = g_umma_debug;
@@ -989,20 +991,61 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
 #pragma unroll
                     for (int i = 0; i < CW; ++i) v[i] = 0u;
                 }
-                if (r_local < rows_cta) {
-                    float* dst = out + (size_t)row * COUT + c0;
+                const bool row_ok = r_local < rows_cta;
+                float* dst = out + (size_t)row * COUT + c0;
 #pragma unroll
-                    for (int i = 0; i < CW; i += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(v[i + 0]);
-                        o.y = __uint_as_float(v[i + 1]);
-                        o.z = __uint_as_float(v[i + 2]);
-                        o.w = __uint_as_float(v[i + 3]);
-                        if (bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int i = 0; i < CW; i += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[i + 0]);
+                    o.y = __uint_as_float(v[i + 1]);
+                    o.z = __uint_as_float(v[i + 2]);
+                    o.w = __uint_as_float(v[i + 3]);
+                    if (bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
+                    if (stats != nullptr) {           // keep the final values for the column statistics (0 for rows past n_out)
+                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
+                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
+                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
+                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
+                    }
+                }
+                if (stats != nullptr) {
+                    // column sums over the warp's 32 rows by a butterfly: after log2(32) exchange rounds lane j holds
+                    // the sum of column perm(j); 31 shuffles per quantity instead of 32 x 5
+                    float a[32], q[32];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        a[i] = __uint_as_float(v[i]);
+                        q[i] = a[i] * a[i];
+                    }
+                    int col = 0;
+#pragma unroll
+                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float sa = up ? a[i] : a[i + sft];
+                            const float sq = up ? q[i] : q[i + sft];
+                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
+                            const float rq = __shfl_xor_sync(0xffffffffu, sq, sft);
+                            a[i] = (up ? a[i + sft] : a[i]) + ra;
+                            q[i] = (up ? q[i + sft] : q[i]) + rq;
                         }
-                        *reinterpret_cast<float4*>(dst + i) = o;
+                        if (up) col += sft;
+                    }
+                    if (CW == 32 || lane < 16 || true) {
+                        // lane L holds column `col` (CW == 16: lanes L and L^16 hold halves of the same column)
+                        if (CW == 16) {
+                            a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+                            q[0] += __shfl_xor_sync(0xffffffffu, q[0], 16);
+                        }
+                        if (CW == 32 || lane < 16) {
+                            atomicAdd(&col_sum_s[c0 + col], a[0]);
+                            atomicAdd(&col_sum_s[256 + c0 + col], q[0]);
+                        }
                     }
                 }
             }
@@ -1010,13 +1053,17 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     }
     tc_fence_before();
     __syncthreads();
+    if (stats != nullptr && tid < 2 * COUT) {
+        const float vsum = col_sum_s[(tid / COUT) * 256 + tid % COUT];
+        if (vsum != 0.f) atomicAdd(stats + tid, (double)vsum);
+    }
     if (warp == 0) { const long long t_end = PF_T(); PF_ADD(PF_EPILOGUE, t_end - t_epi0); PF_ADD(PF_CTA_TOTAL, t_end - t_cta0); }
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
 template <int CIN, int COUT, bool BF16C>
 int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
-                   const unsigned int* tile_masks, int n_out, int K, float* out, cudaStream_t stream) {
+                   const unsigned int* tile_masks, int n_out, int K, float* out, double* stats, cudaStream_t stream) {
     const size_t smem = ts_smem_bytes(CIN, COUT);
     auto kern = k_spconv_umma_ts<CIN, COUT, BF16C>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1027,7 +1074,7 @@ int launch_umma_ts(const float* in, const float* wpacked, const float* bias, con
     if (tiles < 1) tiles = 1;
     if (tiles > tmax) tiles = tmax;
     const int ctas = (n_tiles + tiles - 1) / tiles;
-    kern<<<ctas, TS_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out);
+    kern<<<ctas, TS_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -1051,8 +1098,8 @@ bool tc_shape_ok(int K, int cin, int cout, int variant) {
 #define UD_DISPATCH_UMMA(CI, CO)                                                                          \
     if (cin == CI && cout == CO)                                                                          \
         return variant == 1   ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)            \
-               : variant == 2 ? launch_umma_ts<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)  \
-                              : launch_umma_ts<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+               : variant == 2 ? launch_umma_ts<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
+                              : launch_umma_ts<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
 
 extern "C" {
 
@@ -1122,20 +1169,24 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
 // out (n_out, cout) f32.
 // variant: 0 = default (A through TMEM, bf16 correction MMAs), 1 = A through shared memory, 3xTF32 ("SS"),
 //          2 = A through TMEM, 3xTF32.  The weights must have been packed for the same variant.
+// bn_sums (nullable, variants 0 and 2): double[2 * cout] that the kernel ADDS the per-channel sum and sum of squares of
+// `out` to (the statistics pass of the BatchNorm that follows, fused into the epilogue); the caller zeroes it.
 int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
-                              int variant, void* stream_) {
+                              double* bn_sums, int variant, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const float* wpacked = (const float*)wpacked_;
     if (!in || !wpacked || !nbr_t || !tile_masks || !out || n_out < 0) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
     if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out) & 15u) != 0) return UD_ERR_INVALID_ARG;
     if (n_out == 0) return UD_OK;
+    double* stats = variant == 1 ? nullptr : bn_sums;
+    if (variant == 1 && bn_sums != nullptr) return UD_ERR_UNSUPPORTED;
     if (variant == 0) {
         if (cin == 16 && cout == 16)
-            return launch_umma_ts<16, 16, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+            return launch_umma_ts<16, 16, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
         if (cin == 16 && cout == 32)
-            return launch_umma_ts<16, 32, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream);
+            return launch_umma_ts<16, 32, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
     }
     UD_DISPATCH_UMMA(32, 16)
     UD_DISPATCH_UMMA(32, 32)

@@ -151,6 +151,9 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
 # 0: A through TMEM + bf16 correction MMAs (default), 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
 TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))
+# the tensor-core kernel's epilogue also accumulates the per-channel sum / sum of squares of its output, so the
+# BatchNorm1d that follows skips its statistics pass (attribute `_ud_bn_sums` on the conv output, see batch_norm_act)
+FUSE_BN_STATS = os.environ.get("UD_FUSE_BN_STATS", "1") != "0"
 
 
 # id(weight) -> (weakref to the weight, its _version, kernel variant, packed image): re-pack only when the parameter
@@ -178,7 +181,7 @@ def _packed_weights(w_k, K, cin, cout, sp, weight=None):
     return packed
 
 
-def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None):
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None, want_stats=False):
     lib = native.load()
     dev = feats.device
     out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
@@ -190,10 +193,15 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
         if meta is not None:
             meta["kernel"] = "k_spconv_umma" if TC_VARIANT == 1 else "k_spconv_umma_ts"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
+        sums = None
+        if want_stats and FUSE_BN_STATS and TC_VARIANT != 1:
+            sums = torch.zeros((2, cout), dtype=torch.float64, device=dev)
         rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
                                native.ptr(packed), native.ptr(bias), native.ptr(table_t), native.ptr(masks), n_out, K,
-                               cin, cout, native.ptr(out), TC_VARIANT, sp)
+                               cin, cout, native.ptr(out), native.ptr(sums), TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_forward")
+        if sums is not None:
+            out._ud_bn_sums = sums
         return out
     if meta is not None:
         meta["kernel"] = "k_spconv_gather_gemm"
@@ -234,7 +242,7 @@ class SparseConvFunction(Function):
             table, n_out = rb.nbr_in, rb.n_in
         assert features.shape[1] == cin, "feature width %d != conv in_channels %d" % (features.shape[1], cin)
         b = bias.detach().float().contiguous() if bias is not None else None
-        out = _conv_forward_raw(features, w_k_fn, b, table, n_out, rb.K, cin, cout, rb, weight)
+        out = _conv_forward_raw(features, w_k_fn, b, table, n_out, rb.K, cin, cout, rb, weight, want_stats=True)
         ctx.rb, ctx.inverse = rb, inverse
         ctx.has_bias = bias is not None
         ctx.wshape = tuple(weight.shape)
@@ -286,7 +294,8 @@ class BatchNormActFunction(Function):
     """y = relu?(batch_norm(x) (+ residual)) over the rows of an (N, C) matrix; two kernels forward."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, training, momentum, eps, relu):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, training, momentum, eps, relu,
+                fused_sums=None):
         native.require_cuda(x)
         lib = native.load()
         x = x.contiguous()
@@ -297,11 +306,13 @@ class BatchNormActFunction(Function):
         shift = torch.empty((C,), dtype=torch.float32, device=dev)
         res = residual.contiguous() if residual is not None else None
         if training:
-            sums = torch.empty((2, C), dtype=torch.float64, device=dev)
             save_mean = torch.empty((C,), dtype=torch.float32, device=dev)
             save_invstd = torch.empty((C,), dtype=torch.float32, device=dev)
-            rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums[0]), native.ptr(sums[1]), sp)
-            native.check(rc, "ud_bn_stats")
+            sums = fused_sums
+            if sums is None or tuple(sums.shape) != (2, C) or sums.device != dev:
+                sums = torch.empty((2, C), dtype=torch.float64, device=dev)
+                rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums[0]), native.ptr(sums[1]), sp)
+                native.check(rc, "ud_bn_stats")
             rc = lib.ud_bn_finalize(native.ptr(sums[0]), native.ptr(sums[1]), n, C, native.ptr(gamma),
                                     native.ptr(beta), float(eps), float(momentum), native.ptr(running_mean),
                                     native.ptr(running_var), native.ptr(scale), native.ptr(shift),
@@ -342,13 +353,13 @@ class BatchNormActFunction(Function):
             native.check(rc, "ud_bn_backward")
             dgamma = sums[1].float() if ctx.has_affine else None
             dbeta = sums[0].float() if ctx.has_affine else None
-            return dx, dgamma, dbeta, dres, None, None, None, None, None, None
+            return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None
         y, scale = ctx.saved_tensors
         g = dy * (y > 0).to(dy.dtype) if ctx.relu else dy
         dx = g * scale
         dres = g if ctx.has_res else None
         # eval-mode BN: parameters are treated as constants (frozen-teacher use)
-        return dx, None, None, dres, None, None, None, None, None, None
+        return dx, None, None, dres, None, None, None, None, None, None, None
 
 
 def batch_norm_act(x, bn, relu=True, residual=None):
@@ -365,7 +376,8 @@ def batch_norm_act(x, bn, relu=True, residual=None):
         if residual is not None:
             y = y + residual
         return torch.relu(y) if relu else y
-    return BatchNormActFunction.apply(x, bn.weight, bn.bias, residual, rm, rv, training, momentum, bn.eps, relu)
+    fused = getattr(x, "_ud_bn_sums", None) if (training and x.is_contiguous()) else None
+    return BatchNormActFunction.apply(x, bn.weight, bn.bias, residual, rm, rv, training, momentum, bn.eps, relu, fused)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -111,9 +111,11 @@ int ud_debug_umma_flags(int flags);
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
 /* variant 0 = default kernel (A operand staged through TMEM; hi*hi in TF32, the two correction products as bf16 MMAs),
  * 1 = A through shared memory with 3xTF32, 2 = A through TMEM with 3xTF32; pack the weights for the same variant */
+/* bn_sums (nullable; not with variant 1): double[2*cout]; the kernel adds the per-channel sum and sum of squares of `out`
+ * to it, i.e. the statistics pass of the BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113) */
 int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
-                              int variant, void* stream);
+                              double* bn_sums, int variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /

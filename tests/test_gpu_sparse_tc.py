@@ -87,6 +87,34 @@ def test_tc_strided_matches_oracle(cuda, native_lib, cin, cout, ksize, stride, p
     assert _rel(out.cpu().numpy(), ref) < TC_TOL
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 64), (64, 64), (128, 128)])
+def test_tc_fused_batchnorm_statistics(cuda, native_lib, cin, cout, tc_variant):
+    """The epilogue's per-channel sum / sum of squares == a separate pass over the conv output (ragged tail rows
+    and the bias included), and BatchNorm driven by them == nn.BatchNorm1d."""
+    from unidistill_b200 import sparse
+
+    if tc_variant == 1 or (cin == 16 and tc_variant != 0):
+        pytest.skip("statistics are fused into the TMEM-operand kernels only")
+    rng = np.random.default_rng(cin + cout)
+    B, shape, n = 2, [7, 24, 24], 2777
+    coords, feat = _cloud(rng, B, shape, n, cin)
+    w = torch.from_numpy((rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)).to(cuda)
+    bias = torch.from_numpy(rng.standard_normal((cout,)).astype(np.float32)).to(cuda)
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    out = sparse.sparse_conv(torch.from_numpy(feat).to(cuda), w, bias, rb)
+    sums = getattr(out, "_ud_bn_sums", None)
+    assert sums is not None and tuple(sums.shape) == (2, cout)
+    ref0, ref1 = out.double().sum(0), (out.double() ** 2).sum(0)
+    assert torch.allclose(sums[0], ref0, rtol=1e-5, atol=1e-4 * float(ref1.max().sqrt()))
+    assert torch.allclose(sums[1], ref1, rtol=1e-5)
+    bn = torch.nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01).to(cuda).train()
+    bn_ref = torch.nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01).to(cuda).train()
+    y = sparse.batch_norm_act(out, bn, relu=True)
+    y_ref = torch.relu(bn_ref(out.clone()))
+    assert float((y - y_ref).abs().max()) < 1e-4
+    assert torch.allclose(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-7)
+
+
 def test_tc_single_row_and_isolated_voxels(cuda, native_lib):
     """One active voxel (only the centre tap exists) and voxels with no neighbours: out = in @ W[centre]."""
     from unidistill_b200 import sparse
