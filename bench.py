@@ -8,7 +8,7 @@ Workload at N=1 (BASELINE.json configs[1]): BEVFusion-LiDAR forward = hard voxel
 VoxelResBackBone8x sparse encoder -> scatter to a 128x128 BEV -> BaseBEVBackbone -> CenterHead towers
 (+ the target assignment CenterHead.forward performs in training mode), bs=4 per GPU, every sample =
 10 sweeps x 40k synthetic ring-LiDAR points.  N>1: every rank runs its own batch (samples are independent;
-a forward has no exchange step) -> weak scaling.  `--workload camera|distill` select configs[2] / [3].
+a forward has no exchange step) -> weak scaling.  `--workload camera|distill|distill_lidar` select configs[2] / [3] / [4].
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
@@ -281,6 +281,8 @@ class DistillTrainStep:
 
     name = ("camera-student <- LiDAR-teacher distill step (fwd teacher+student, 3 distill losses, bwd, grad "
             "all-reduce, AdamW), bs=4/GPU, 128x128 BEV")
+    teacher_modalities = dict(lidar=True, camera=False)
+    student_modalities = dict(lidar=False, camera=True)
 
     def __init__(self, device, rank, seed=0):
         import torch
@@ -291,8 +293,8 @@ class DistillTrainStep:
         torch.manual_seed(0)
         self.device = device
         cl = os.environ.get("UD_CHANNELS_LAST", "1") != "0"
-        t_cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
-        s_cfg = models.make_model_cfg(bev=128, lidar=False, camera=True)
+        t_cfg = models.make_model_cfg(bev=128, **self.teacher_modalities)
+        s_cfg = models.make_model_cfg(bev=128, **self.student_modalities)
         teacher = models.BEVFusionCenterHead(t_cfg).to(device).use_channels_last(cl)
         student = models.BEVFusionCenterHead(s_cfg).to(device).use_channels_last(cl)
         self.step_fn = DistillStep(student, teacher, t_cfg["geometry"])
@@ -323,7 +325,18 @@ class DistillTrainStep:
         return out
 
 
-WORKLOADS = {"lidar": LidarForward, "camera": CameraForward, "distill": DistillTrainStep}
+class DistillLidarTrainStep(DistillTrainStep):
+    """configs[4]: LiDAR-student <- fusion-teacher distillation step (teacher = LiDAR + camera branches +
+    FusionEncoder, frozen; student = LiDAR branch trained through the sparse-conv dgrad/wgrad kernels)."""
+
+    name = ("LiDAR-student <- fusion-teacher distill step (fwd teacher+student, 3 distill losses, bwd, grad "
+            "all-reduce, AdamW), 40k pts x10 sweeps, bs=4/GPU, 128x128 BEV")
+    teacher_modalities = dict(lidar=True, camera=True)
+    student_modalities = dict(lidar=True, camera=False)
+
+
+WORKLOADS = {"lidar": LidarForward, "camera": CameraForward, "distill": DistillTrainStep,
+             "distill_lidar": DistillLidarTrainStep}
 
 
 # ---------------------------------------------------------------------------------------------------

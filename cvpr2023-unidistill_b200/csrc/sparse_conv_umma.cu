@@ -24,127 +24,18 @@
 //                            warp 9           weight loader (cp.async.bulk + mbarrier expect_tx)
 //                            warps 0-3        epilogue afterwards: tcgen05.ld -> +bias -> global
 #include "common.cuh"
+#include "umma_common.cuh"
 #include <cuda_bf16.h>
 
 namespace {
+
+using namespace ud_umma;
 
 constexpr int TILE_M = 128;
 constexpr int KC = 32;                 // channels per pipeline stage (= one 128-byte swizzle row of fp32)
 constexpr int NTHREADS = 320;
 constexpr int GATHER_THREADS = 128;    // per gather group
 constexpr int MAX_TAPS = 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// One lane of the (converged) warp; nvcc recognises elect.sync and issues the tcgen05 instructions of the guarded
-// region directly instead of wrapping each one in its own election loop.
-__device__ __forceinline__ bool elect_one_sync() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate, M=128, N from idesc, K=8
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address      bits [0,14)
-    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset  bits [32,46)
-    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ uint32_t swz_off(int row, int chunk16) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 constexpr int A_STAGES = 4;            // ring of gathered A tiles (hi + lo, 32 KB each)
 constexpr int B_STAGES = 2;            // ring of weight slices (hi + lo)
@@ -211,6 +102,33 @@ k_pack_weights_bf(const float* __restrict__ w, int K, int cin, int cout, int ks,
         wb[off] = __float2bfloat16_rn(v);
         wb[(size_t)cout * ks + off] = __float2bfloat16_rn(lo);
     }
+}
+
+// Packed image for the bf16x3 kernel (MODE_BF3): per (super-tap, stage of 64 channels) one block of
+//   [COUT x 64 bf16 W_hi] [COUT x 64 bf16 W_lo],  W_hi = bf16(W), W_lo = bf16(W - W_hi), 128-byte swizzle.
+// Block size = 4 * COUT * 64 bytes.
+__global__ void __launch_bounds__(256)
+k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int tapg, unsigned char* __restrict__ packed) {
+    constexpr int ks = 64;
+    const int cin_eff = cin * tapg;
+    const int k_eff = (K + tapg - 1) / tapg;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)k_eff * cin_eff * cout;
+    if (t >= total) return;
+    const int n = (int)(t % cout);
+    const int cv = (int)((t / cout) % cin_eff);             // virtual channel = g * cin + c
+    const int kj = (int)(t / ((long long)cout * cin_eff));
+    const int tap = kj * tapg + cv / cin, c = cv % cin;
+    const float v = tap < K ? w[((size_t)tap * cin + c) * cout + n] : 0.f;      // w[k][c][n]
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int nstage = cin_eff / ks;
+    const int stage = cv / ks, e = cv % ks;
+    __nv_bfloat16* blk = reinterpret_cast<__nv_bfloat16*>(packed + (size_t)(kj * nstage + stage) * ((size_t)4 * cout * ks));
+    const int chunk = e >> 3, within = e & 7;               // 16-byte chunk = 8 bf16
+    const size_t off = (size_t)n * ks + (size_t)((chunk ^ (n & 7)) * 8 + within);
+    blk[off] = hi;
+    blk[(size_t)cout * ks + off] = lo;
 }
 
 // [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
@@ -559,9 +477,28 @@ __host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / 
 __host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin : 1; }
 __host__ __device__ constexpr int ts_ks(int cin, int cout) { return (cin < 64 || cout <= 64) ? 64 : 32; }
 __host__ __device__ constexpr int ts_raw_stages(int cin, int cout) { return 4; }
-__host__ __device__ constexpr size_t ts_smem_bytes(int cin, int cout) {
-    return (size_t)ts_raw_stages(cin, cout) * TILE_M * ts_ks(cin, cout) * 4 +
-           (size_t)B_STAGES * 2 * cout * ts_ks(cin, cout) * 4 + (size_t)TS_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 + 1024;
+// kernel modes of k_spconv_umma_ts
+constexpr int MODE_3XTF32 = 0;   // hi/lo TF32 split, 3 tf32 MMAs per 8 channels                      (variant 2)
+constexpr int MODE_BF16C = 1;    // tf32 hi*hi + two bf16 correction MMAs: 4 MMAs per 16 channels      (variant 0)
+constexpr int MODE_BF3 = 2;      // bf16 hi/lo split of both operands, 3 bf16 MMAs per 16 channels     (variant 3)
+__host__ __device__ constexpr int ts_mode_tapg(int cin, int mode) { return mode == MODE_3XTF32 ? 1 : ts_tapg(cin); }
+__host__ __device__ constexpr int ts_mode_ks(int cin, int cout, int mode) {
+    return mode == MODE_BF3 ? 64
+                            : (ts_mode_tapg(cin, mode) > 1 ? 64
+                               : (mode == MODE_BF16C ? ts_ks(cin, cout) : (cin >= 64 && cout <= 64 ? 64 : 32)));
+}
+// bytes of one weight slice (one (super-)tap x KS channels): fp32 hi + lo (or hi + 2 bf16 slices) = 8 B per element,
+// two bf16 slices = 4 B per element in MODE_BF3
+__host__ __device__ constexpr int ts_b_bytes(int cin, int cout, int mode) {
+    return (mode == MODE_BF3 ? 4 : 8) * cout * ts_mode_ks(cin, cout, mode);
+}
+__host__ __device__ constexpr int ts_b_stages(int cin, int cout, int mode) {
+    return (mode == MODE_BF3 && cout <= 64) ? 4 : B_STAGES;
+}
+__host__ __device__ constexpr size_t ts_smem_bytes(int cin, int cout, int mode) {
+    return (size_t)ts_raw_stages(cin, cout) * TILE_M * ts_mode_ks(cin, cout, mode) * 4 +
+           (size_t)ts_b_stages(cin, cout, mode) * ts_b_bytes(cin, cout, mode) +
+           (size_t)TS_IDX_STAGES * ts_mode_tapg(cin, mode) * TILE_M * 4 + 1024;
 }
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -643,23 +580,30 @@ enum { PF_MMA_WAIT_A = 0, PF_MMA_WAIT_B, PF_MMA_TOTAL, PF_TR_WAIT_RAW, PF_TR_WAI
 
 // BF16C: the two correction products (lo x W, hi x W_lo) are issued as kind::f16 bf16 MMAs with K = 16 (their operands
 // only need ~8 significant bits since the terms are 2^-11 of the result): 8 instead of 12 tcgen05.mma per 32 channels.
-template <int CIN, int COUT, bool BF16C>
+// BF3 (default): both operands split into bf16 hi + bf16 lo (x = hi + lo to ~2^-17) and the product accumulated as
+// lo*W_hi + hi*W_lo + hi*W_hi with three kind::f16 bf16 MMAs (K = 16): 12 tcgen05.mma per 64 channels, half the TMEM
+// and shared-memory operand bytes of BF16C, ~2^-16 relative error per product.
+template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
                  int tiles, float* __restrict__ out, double* __restrict__ stats) {
-    constexpr int TAPG = BF16C ? ts_tapg(CIN) : 1;   // kernel taps per stage (narrow layers, see ts_tapg)
-    constexpr int KS = TAPG > 1 ? 64 : (BF16C ? ts_ks(CIN, COUT) : (CIN >= 64 && COUT <= 64 ? 64 : 32));
+    constexpr bool BF16C = MODE == MODE_BF16C;
+    constexpr bool BF3 = MODE == MODE_BF3;
+    constexpr int TAPG = ts_mode_tapg(CIN, MODE);    // kernel taps per stage (narrow layers, see ts_tapg)
+    constexpr int KS = ts_mode_ks(CIN, COUT, MODE);
+    constexpr int B_STAGES = ts_b_stages(CIN, COUT, MODE);   // shadows the file-level constant
     constexpr int NSUB = KS / KC;                    // 32-channel sub-tiles per stage
     constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
     constexpr int IDX_INTS = TAPG * TILE_M;          // row indices of one stage
-    constexpr int A_COLS = 2 * KS;                   // TMEM columns of one A stage: KS hi | KS lo
+    constexpr int A_COLS = BF3 ? KS : 2 * KS;        // TMEM columns of one A stage: KS hi | KS lo (BF3: bf16 pairs)
     constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
     constexpr int RAW_STAGES = ts_raw_stages(CIN, COUT);
     constexpr int RAW_BYTES = TILE_M * KS * 4;
     constexpr int SUB_BYTES = TILE_M * 128;          // one [128 x 32] fp32 sub-tile
     constexpr int BSUB_BYTES = COUT * 128;           // one [COUT x 32] fp32 weight sub-slice
-    constexpr int B_BYTES = 2 * NSUB * BSUB_BYTES;   // hi + lo (or hi + bf16 W + bf16 W_lo), all sub-tiles of the stage
+    constexpr int B_BYTES = ts_b_bytes(CIN, COUT, MODE);   // hi + lo (or hi + bf16 W + bf16 W_lo; BF3: bf16 hi + bf16 lo)
+    static_assert(BF3 || B_BYTES == 2 * NSUB * BSUB_BYTES, "weight slice size");
     constexpr int BBF_BYTES = COUT * KS * 2;         // one bf16 [COUT x KS] weight slice
     constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                   ((uint32_t)(TILE_M >> 4) << 24);
@@ -777,11 +721,13 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     v[4 * c + 0] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
                 }
                 if (sub == NSUB - 1) mbar_arrive(bar_raw_empty + 8 * rslot);   // all of the slot is in registers
+                if constexpr (!BF3) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t h = v[i] & 0xffffe000u;
-                    lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
-                    v[i] = h;
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t h = v[i] & 0xffffe000u;
+                        lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h));
+                        v[i] = h;
+                    }
                 }
                 if (sub == 0) {
                     tw = PF_T();
@@ -790,7 +736,19 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     tc_fence_after();
                 }
                 if (!(dbg & 1)) {
-                    if constexpr (BF16C) {
+                    if constexpr (BF3) {
+                        // stage columns: [0, KS/2) hi as bf16 pairs | [KS/2, KS) lo as bf16 pairs (v holds x unsplit)
+                        uint32_t lob[16], hib[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+                            const __nv_bfloat162 hb = __floats2bfloat162_rn(x0, x1);
+                            hib[j] = *reinterpret_cast<const uint32_t*>(&hb);
+                            lob[j] = pack_bf16x2(x0 - __low2float(hb), x1 - __high2float(hb));
+                        }
+                        tmem_st16(taddr + sub * 16, hib);
+                        tmem_st16(taddr + KS / 2 + sub * 16, lob);
+                    } else if constexpr (BF16C) {
                         // stage columns: [0,KS) hi (tf32) | [KS, KS+KS/2) lo as bf16 pairs | [KS+KS/2, 2KS) value as bf16
                         uint32_t lob[16], hib[16];
 #pragma unroll
@@ -886,7 +844,21 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
                     const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
                     const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
                     const uint32_t first = (started >> tile) & 1u;
-                    if constexpr (BF16C) {
+                    if constexpr (BF3) {
+                        // weights of the stage: [COUT x 64 bf16 W_hi] [COUT x 64 bf16 W_lo], 128-byte swizzle
+                        const uint64_t db_hi = umma_desc_sw128(b_base);
+                        const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
+#pragma unroll
+                        for (int k16 = 0; k16 < KS / 16; ++k16) {
+                            if (dbg & 4) break;
+                            const uint32_t a_hi = a_stage + (uint32_t)(k16 * 8);          // 16 bf16 = 8 TMEM columns
+                            const uint32_t a_lo = a_hi + KS / 2;
+                            const uint64_t adv = (uint64_t)(k16 * 2);                     // 16 bf16 = 32 B
+                            umma_bf16_ts(d, a_lo, db_hi + adv, IDESC_BF, (first || k16 > 0) ? 1u : 0u);
+                            umma_bf16_ts(d, a_hi, db_lo + adv, IDESC_BF, 1u);
+                            umma_bf16_ts(d, a_hi, db_hi + adv, IDESC_BF, 1u);
+                        }
+                    } else if constexpr (BF16C) {
                         // weights of the stage: [NSUB x (COUT x 128 B) tf32 hi] [COUT x KS bf16 W] [COUT x KS bf16 W_lo]
                         const uint32_t wbf = b_base + NSUB * BSUB_BYTES;
                         const uint64_t db_w = KS == 64 ? umma_desc_sw128(wbf) : umma_desc_sw64(wbf);
@@ -1061,11 +1033,11 @@ k_spconv_umma_ts(const float* __restrict__ in, const float* __restrict__ wpacked
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
-template <int CIN, int COUT, bool BF16C>
+template <int CIN, int COUT, int MODE>
 int launch_umma_ts(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
                    const unsigned int* tile_masks, int n_out, int K, float* out, double* stats, cudaStream_t stream) {
-    const size_t smem = ts_smem_bytes(CIN, COUT);
-    auto kern = k_spconv_umma_ts<CIN, COUT, BF16C>;
+    const size_t smem = ts_smem_bytes(CIN, COUT, MODE);
+    auto kern = k_spconv_umma_ts<CIN, COUT, MODE>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
     const int tmax = ts_tiles_max(COUT);
@@ -1084,10 +1056,10 @@ int launch_umma_ts(const float* in, const float* wpacked, const float* bias, con
 bool tc_shape_ok(int K, int cin, int cout, int variant) {
     static const int shapes[][2] = {{32, 16}, {32, 32}, {32, 64}, {64, 32}, {64, 64}, {64, 128}, {128, 64}, {128, 128}};
     static const int narrow[][2] = {{16, 16}, {16, 32}};
-    if (K < 1 || K > MAX_TAPS || variant < 0 || variant > 2) return false;
+    if (K < 1 || K > MAX_TAPS || variant < 0 || variant > 3) return false;
     for (const auto& s : shapes)
         if (s[0] == cin && s[1] == cout) return true;
-    if (variant == 0)
+    if (variant == 0 || variant == 3)
         for (const auto& s : narrow)
             if (s[0] == cin && s[1] == cout) return true;
     return false;
@@ -1098,8 +1070,9 @@ bool tc_shape_ok(int K, int cin, int cout, int variant) {
 #define UD_DISPATCH_UMMA(CI, CO)                                                                          \
     if (cin == CI && cout == CO)                                                                          \
         return variant == 1   ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)            \
-               : variant == 2 ? launch_umma_ts<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
-                              : launch_umma_ts<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+               : variant == 2 ? launch_umma_ts<CI, CO, MODE_3XTF32>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
+               : variant == 3 ? launch_umma_ts<CI, CO, MODE_BF3>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
+                              : launch_umma_ts<CI, CO, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
 
 extern "C" {
 
@@ -1123,7 +1096,7 @@ int ud_sparse_conv_tc_supported(int K, int cin, int cout, int variant) {
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, int variant, size_t* bytes) {
     if (!bytes) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
-    const int tapg = variant == 0 ? ts_tapg(cin) : 1;
+    const int tapg = (variant == 0 || variant == 3) ? ts_tapg(cin) : 1;     // variant 3 needs half of this
     *bytes = (size_t)((K + tapg - 1) / tapg) * (cin * tapg) * cout * 2 * sizeof(float);
     return UD_OK;
 }
@@ -1136,6 +1109,13 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     if (!w || !packed) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
     if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
+    if (variant == 3) {
+        const int tapg = ts_tapg(cin);
+        const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
+        k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, tapg, (unsigned char*)packed);
+        UD_LAUNCH_CHECK();
+        return UD_OK;
+    }
     if (variant == 0) {
         const int tapg = ts_tapg(cin);
         const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
@@ -1167,9 +1147,10 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
 // in (n_in, cin) f32, 16-byte aligned rows; wpacked from ud_sparse_conv_tc_pack_weights; bias (cout)|NULL;
 // nbr_t (K, n_out) int32 tap-major gather table and tile_masks (ceil(n_out/128)) from ud_rulebook_transpose;
 // out (n_out, cout) f32.
-// variant: 0 = default (A through TMEM, bf16 correction MMAs), 1 = A through shared memory, 3xTF32 ("SS"),
-//          2 = A through TMEM, 3xTF32.  The weights must have been packed for the same variant.
-// bn_sums (nullable, variants 0 and 2): double[2 * cout] that the kernel ADDS the per-channel sum and sum of squares of
+// variant: 0 = A through TMEM, tf32 hi*hi + bf16 correction MMAs, 1 = A through shared memory, 3xTF32 ("SS"),
+//          2 = A through TMEM, 3xTF32, 3 = A through TMEM, bf16x3 (bf16 hi/lo split of both operands).
+//          The weights must have been packed for the same variant.
+// bn_sums (nullable, variants 0, 2 and 3): double[2 * cout] that the kernel ADDS the per-channel sum and sum of squares of
 // `out` to (the statistics pass of the BatchNorm that follows, fused into the epilogue); the caller zeroes it.
 int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
@@ -1184,9 +1165,15 @@ int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float
     if (variant == 1 && bn_sums != nullptr) return UD_ERR_UNSUPPORTED;
     if (variant == 0) {
         if (cin == 16 && cout == 16)
-            return launch_umma_ts<16, 16, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+            return launch_umma_ts<16, 16, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
         if (cin == 16 && cout == 32)
-            return launch_umma_ts<16, 32, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+            return launch_umma_ts<16, 32, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+    }
+    if (variant == 3) {
+        if (cin == 16 && cout == 16)
+            return launch_umma_ts<16, 16, MODE_BF3>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+        if (cin == 16 && cout == 32)
+            return launch_umma_ts<16, 32, MODE_BF3>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
     }
     UD_DISPATCH_UMMA(32, 16)
     UD_DISPATCH_UMMA(32, 32)

@@ -149,11 +149,15 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 # tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
 # every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
-# 0: A through TMEM + bf16 correction MMAs (default), 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
-TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "0"))
+# 3: A through TMEM, bf16x3 operand split (default), 0: A through TMEM, tf32 + bf16 correction MMAs,
+# 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
+TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "3"))
 # the tensor-core kernel's epilogue also accumulates the per-channel sum / sum of squares of its output, so the
 # BatchNorm1d that follows skips its statistics pass (attribute `_ud_bn_sums` on the conv output, see batch_norm_act)
 FUSE_BN_STATS = os.environ.get("UD_FUSE_BN_STATS", "1") != "0"
+# weight gradients of the C >= 32 layers on the tensor cores (TF32 operands rounded to nearest, fp32 accumulation);
+# UD_SPCONV_TC_WGRAD=0 keeps them on the fp32 SIMT kernel
+USE_TC_WGRAD = os.environ.get("UD_SPCONV_TC_WGRAD", "1") != "0"
 
 
 # id(weight) -> (weakref to the weight, its _version, kernel variant, packed image): re-pack only when the parameter
@@ -275,10 +279,16 @@ class SparseConvFunction(Function):
                 table, n_rows = rb.nbr_out, rb.n_out
             else:
                 table, n_rows = rb.nbr_in, rb.n_in
-            rc = lib.ud_sparse_conv_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table),
-                                          n_rows, K, cin, cout, native.ptr(dw),
-                                          native.stream_ptr(grad_out.device))
-            native.check(rc, "ud_sparse_conv_wgrad")
+            sp = native.stream_ptr(grad_out.device)
+            if USE_TENSOR_CORES and USE_TC_WGRAD and n_rows > 0 and lib.ud_sparse_conv_tc_wgrad_supported(K, cin, cout):
+                table_t, masks = rb.tap_major(table)           # cached by the forward pass (same table)
+                rc = lib.ud_sparse_conv_tc_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table_t),
+                                                 native.ptr(masks), n_rows, K, cin, cout, native.ptr(dw), sp)
+                native.check(rc, "ud_sparse_conv_tc_wgrad")
+            else:
+                rc = lib.ud_sparse_conv_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table),
+                                              n_rows, K, cin, cout, native.ptr(dw), sp)
+                native.check(rc, "ud_sparse_conv_wgrad")
             dweight = dw.permute(2, 0, 1).reshape(ctx.wshape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             dbias = grad_out.sum(0)

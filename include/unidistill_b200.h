@@ -109,13 +109,23 @@ int ud_debug_umma_flags(int flags);
  * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
  * tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
-/* variant 0 = default kernel (A operand staged through TMEM; hi*hi in TF32, the two correction products as bf16 MMAs),
+/* variant 3 = default kernel (A operand staged through TMEM; both operands split into bf16 hi + bf16 lo, three bf16 MMAs
+ * per 16 channels), 0 = A through TMEM, hi*hi in TF32 + the two correction products as bf16 MMAs,
  * 1 = A through shared memory with 3xTF32, 2 = A through TMEM with 3xTF32; pack the weights for the same variant */
 /* bn_sums (nullable; not with variant 1): double[2*cout]; the kernel adds the per-channel sum and sum of squares of `out`
  * to it, i.e. the statistics pass of the BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113) */
 int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               double* bn_sums, int variant, void* stream);
+
+/* Tensor-core weight gradient (csrc/sparse_conv_wgrad_umma.cu): dw[k] += in[nbr[o][k],:]^T dout[o,:] as tcgen05 MMAs
+ * over the row dimension (both operands MN-major in shared memory, rounded to TF32 to-nearest on the way in, fp32
+ * accumulators for up to 512/cout kernel taps in TMEM).  nbr_t / tile_masks: ud_rulebook_transpose of the same (n_rows,K)
+ * table ud_sparse_conv_wgrad takes; dw (K,cin,cout) is accumulated into (caller zeroes it).  Replaces the wgrad half of
+ * spconv's indice_conv backward (spconv_backbone.py:21-48,70-92 under autograd). */
+int ud_sparse_conv_tc_wgrad_supported(int K, int cin, int cout);
+int ud_sparse_conv_tc_wgrad(const float* in, const float* dout, const int* nbr_t, const unsigned int* tile_masks,
+                            int n_rows, int K, int cin, int cout, float* dw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /

@@ -285,7 +285,9 @@ def test_conv_backward_parity(cuda, native_lib, cin, cout, strided):
 
     assert _rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 5e-5
     assert _rel_err(f_g.grad.cpu().numpy(), f_c.grad.numpy()) < 1e-4, "dgrad"
-    assert _rel_err(w_g.grad.cpu().numpy(), w_c.grad.numpy()) < 1e-4, "wgrad"
+    # C >= 32 layers: tensor-core wgrad with TF32 (round-to-nearest) operands, see tests/test_gpu_sparse_tc.py
+    tc_wgrad = sparse.USE_TENSOR_CORES and sparse.USE_TC_WGRAD and native_lib.ud_sparse_conv_tc_wgrad_supported(27, cin, cout)
+    assert _rel_err(w_g.grad.cpu().numpy(), w_c.grad.numpy()) < (1e-3 if tc_wgrad else 1e-4), "wgrad"
     if bias is not None:
         assert _rel_err(b_g.grad.cpu().numpy(), b_c.grad.numpy()) < 1e-4, "bias grad"
 

@@ -26,7 +26,8 @@ def _cloud(rng, B, shape, n, C):
     return coords, feat
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["TMEM-A+bf16-corrections", "smem-A-3xTF32", "TMEM-A-3xTF32"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3], ids=["TMEM-A+bf16-corrections", "smem-A-3xTF32", "TMEM-A-3xTF32", "TMEM-A-bf16x3"],
+                autouse=True)
 def tc_variant(request):
     from unidistill_b200 import sparse
 
@@ -46,6 +47,7 @@ def test_tc_subm_matches_oracle(cuda, native_lib, cin, cout):
     from unidistill_b200 import sparse
 
     assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 0) == 1
+    assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 3) == 1
     rng = np.random.default_rng(cin * 7 + cout)
     B, shape, n = 2, [7, 20, 20], 1931                     # 1931 rows: 15 full tiles + a ragged tail
     coords, feat = _cloud(rng, B, shape, n, cin)
@@ -93,7 +95,7 @@ def test_tc_fused_batchnorm_statistics(cuda, native_lib, cin, cout, tc_variant):
     and the bias included), and BatchNorm driven by them == nn.BatchNorm1d."""
     from unidistill_b200 import sparse
 
-    if tc_variant == 1 or (cin == 16 and tc_variant != 0):
+    if tc_variant == 1 or (cin == 16 and tc_variant not in (0, 3)):
         pytest.skip("statistics are fused into the TMEM-operand kernels only")
     rng = np.random.default_rng(cin + cout)
     B, shape, n = 2, [7, 24, 24], 2777
@@ -154,3 +156,119 @@ def test_tc_linearity_full_size(cuda, native_lib):
     finally:
         sparse.USE_TENSOR_CORES = True
     assert float((fx - ref).abs().max() / ref.abs().max()) < TC_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core weight gradient (csrc/sparse_conv_wgrad_umma.cu).  Operands are rounded to TF32 (to nearest, 2^-11 each),
+# products are accumulated in fp32: measured 2.5e-4 .. 4.3e-4 relative to the largest |dW| (independent of the row
+# count: error and value both grow as sqrt(rows)); asserted at north_star's 1e-3 for fp32 losses/gradients.
+WGRAD_TOL = 1e-3
+
+
+def _wgrad_both(sparse, f, g, rb, w_shape):
+    """dW through the autograd function with the tensor-core kernel and with the fp32 SIMT kernel."""
+    res = []
+    for tc in (True, False):
+        old = sparse.USE_TC_WGRAD
+        sparse.USE_TC_WGRAD = tc
+        try:
+            w = torch.zeros(w_shape, device=f.device, requires_grad=True)
+            out = sparse.sparse_conv(f, w, None, rb)
+            (dw,) = torch.autograd.grad(out, [w], g)
+        finally:
+            sparse.USE_TC_WGRAD = old
+        res.append(dw)
+    return res
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128),
+                                      (32, 128), (128, 32)])
+def test_tc_wgrad_subm_matches_oracle(cuda, native_lib, cin, cout, tc_variant):
+    from unidistill_b200 import sparse
+
+    if tc_variant != 3:
+        pytest.skip("wgrad does not depend on the forward variant")
+    assert native_lib.ud_sparse_conv_tc_wgrad_supported(27, cin, cout) == 1
+    rng = np.random.default_rng(cin * 5 + cout)
+    B, shape, n = 2, [7, 20, 20], 1931                     # 15 full 128-row tiles + a ragged tail (< 64 rows)
+    coords, feat = _cloud(rng, B, shape, n, cin)
+    gout = rng.standard_normal((n, cout)).astype(np.float32)
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    f, g = torch.from_numpy(feat).to(cuda), torch.from_numpy(gout).to(cuda)
+    dw_tc, dw_simt = _wgrad_both(sparse, f, g, rb, (cout, 3, 3, 3, cin))
+    # oracle: dW[k] = sum over pairs of in[i]^T dout[o]  (float64)
+    rp, rpn = O.rulebook_subm(coords, shape, 3)
+    ref = np.zeros((27, cin, cout))
+    for k in range(27):
+        m = int(rpn[k])
+        if m:
+            ref[k] = feat[rp[0, k, :m]].astype(np.float64).T @ gout[rp[1, k, :m]].astype(np.float64)
+    ref = ref.transpose(2, 0, 1).reshape(cout, 3, 3, 3, cin)
+    assert _rel(dw_simt.cpu().numpy(), ref) < 2e-5
+    err = _rel(dw_tc.cpu().numpy(), ref)
+    assert err < WGRAD_TOL, "tensor-core wgrad rel err %g" % err
+    # no systematic shrinkage (what truncating instead of rounding the TF32 operands would produce)
+    num = float((dw_tc.double().cpu() * torch.from_numpy(ref)).sum())
+    den = float((torch.from_numpy(ref) ** 2).sum())
+    assert abs(num / den - 1.0) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
+                                                       (128, 128, (3, 1, 1), (2, 1, 1), 0)])
+def test_tc_wgrad_strided_matches_simt(cuda, native_lib, cin, cout, ksize, stride, pad, tc_variant):
+    from unidistill_b200 import sparse
+
+    if tc_variant != 3:
+        pytest.skip("wgrad does not depend on the forward variant")
+    rng = np.random.default_rng(29)
+    B, shape, n = 2, [11, 26, 22], 3000
+    coords, feat = _cloud(rng, B, shape, n, cin)
+    ks = O._t3(ksize)
+    rb = sparse.build_conv_rulebook(torch.from_numpy(coords).to(cuda), B, shape, ksize, stride, pad)
+    g = torch.from_numpy(rng.standard_normal((rb.n_out, cout)).astype(np.float32)).to(cuda)
+    dw_tc, dw_simt = _wgrad_both(sparse, torch.from_numpy(feat).to(cuda), g, rb, (cout, ks[0], ks[1], ks[2], cin))
+    assert float((dw_tc - dw_simt).abs().max() / dw_simt.abs().max()) < WGRAD_TOL
+
+
+def test_tc_wgrad_isolated_voxels_and_single_row(cuda, native_lib, tc_variant):
+    """Only the centre tap exists: dW[centre] = in^T dout, every other tap exactly zero."""
+    from unidistill_b200 import sparse
+
+    if tc_variant != 3:
+        pytest.skip("wgrad does not depend on the forward variant")
+    rng = np.random.default_rng(4)
+    for n in (1, 5):
+        coords = np.array([[0, 2 + 3 * i, 2 + 3 * i, 2 + 3 * i] for i in range(n)], np.int32)
+        feat = rng.standard_normal((n, 64)).astype(np.float32)
+        gout = rng.standard_normal((n, 64)).astype(np.float32)
+        rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), 1, [20, 20, 20], 3)
+        dw_tc, _ = _wgrad_both(sparse, torch.from_numpy(feat).to(cuda), torch.from_numpy(gout).to(cuda), rb,
+                               (64, 3, 3, 3, 64))
+        dw = dw_tc.cpu().numpy()                            # (cout, kz, ky, kx, cin)
+        ref = gout.astype(np.float64).T @ feat.astype(np.float64)
+        assert _rel(dw[:, 1, 1, 1, :], ref.astype(np.float32)) < WGRAD_TOL
+        dw[:, 1, 1, 1, :] = 0
+        assert not dw.any()
+
+
+def test_tc_wgrad_linearity_full_size(cuda, native_lib, tc_variant):
+    """Benchmark-sized layer (64->64 on ~180k voxels): dW is linear in dout and equals the SIMT kernel's."""
+    from unidistill_b200 import sparse
+
+    if tc_variant != 3:
+        pytest.skip("wgrad does not depend on the forward variant")
+    rng = np.random.default_rng(31)
+    B, shape, n = 4, [11, 256, 256], 180000
+    coords, _ = _cloud(rng, B, shape, n, 1)
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    x = torch.randn((n, 64), device=cuda, generator=gen)
+    g1 = torch.randn((n, 64), device=cuda, generator=gen)
+    g2 = torch.randn((n, 64), device=cuda, generator=gen)
+    shp = (64, 3, 3, 3, 64)
+    d1, ref1 = _wgrad_both(sparse, x, g1, rb, shp)
+    d2, _ = _wgrad_both(sparse, x, g2, rb, shp)
+    d12, _ = _wgrad_both(sparse, x, 2.0 * g1 + g2, rb, shp)
+    lin = 2.0 * d1 + d2
+    assert float((d12 - lin).abs().max() / lin.abs().max()) < WGRAD_TOL
+    assert float((d1 - ref1).abs().max() / ref1.abs().max()) < WGRAD_TOL
