@@ -283,6 +283,8 @@ class DistillTrainStep:
             "all-reduce, AdamW), bs=4/GPU, 128x128 BEV")
     teacher_modalities = dict(lidar=True, camera=False)
     student_modalities = dict(lidar=False, camera=True)
+    bn_note = ("student: train-mode batch statistics under autograd; teacher: frozen, eval mode, BatchNorm2d folded "
+               "into its convolutions, dense trunk replayed from a CUDA graph")
 
     def __init__(self, device, rank, seed=0):
         import torch
@@ -490,7 +492,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "global_batch": BS_PER_GPU * world, "per_gpu_batch": BS_PER_GPU,
-                   "bn": "train-mode batch statistics, torch.no_grad", "weights": "random init, seed 0",
+                   "bn": getattr(wl, "bn_note", "train-mode batch statistics, torch.no_grad"), "weights": "random init, seed 0",
                    "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed",
                    "dense_convs": "cuDNN fp32 (torch default allow_tf32), NHWC memory format", "parallelism": "dp%d" % world},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d),

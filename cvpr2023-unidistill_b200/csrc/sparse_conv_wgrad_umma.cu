@@ -81,15 +81,16 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                     const unsigned int* __restrict__ tile_masks, int n_rows, int K, int tiles_per_cta, int st_per_cta,
                     float* __restrict__ dw) {
     constexpr int TAPG = 128 / CIN;                   // kernel taps per super-tap (UMMA M = TAPG * CIN = 128)
-    constexpr int NGA = COUT / 32;                    // 32-column sub-tiles of the dout stage
-    constexpr int G_BYTES = WG_RS * COUT * 4;
+    constexpr int NCOL = COUT < 32 ? 32 : COUT;       // UMMA N: a 16-wide dout tile is zero-padded to one 32-column sub-tile
+    constexpr int NGA = NCOL / 32;                    // 32-column sub-tiles of the dout stage
+    constexpr int G_BYTES = WG_RS * NCOL * 4;
     constexpr int G_STEP = WG_GROUP_THREADS / (8 * NGA);     // dout rows covered by one pass of a producer group
     constexpr int G_NJ = WG_RS / G_STEP;
     // kind::tf32, fp32 accumulate, A and B MN-major, N = COUT, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    static_assert(CIN == 32 || CIN == 64 || CIN == 128, "CIN must divide 128 in whole 32-column sub-tiles");
-    static_assert(COUT == 32 || COUT == 64 || COUT == 128, "unsupported COUT");
+                               ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "CIN must divide 128 in whole 16-byte chunks");
+    static_assert(COUT == 16 || COUT == 32 || COUT == 64 || COUT == 128, "unsupported COUT");
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * WG_A_STAGES + 2 * WG_G_STAGES + 1];
@@ -178,7 +179,7 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                     for (int j = 0; j < G_NJ; ++j) {
                         const int grow = row0 + rb + G_STEP * j;
                         v[j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (grow < n_rows)
+                        if (grow < n_rows && atom * 32 + c16 * 4 < COUT)
                             v[j] = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)grow * COUT + atom * 32 + c16 * 4));
                     }
                     mbar_wait(bar_g_empty + 8 * slot, (((uint32_t)(ig / WG_G_STAGES)) & 1u) ^ 1u);
@@ -197,12 +198,14 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                         const int slot = ia % WG_A_STAGES;
                         const int atom = (tg >> 3) & 3;
                         const int rb = tg >> 5;           // rows rb + 4 j
-                        const int tap = (st0 + s) * TAPG + (atom * 32) / CIN;
-                        const int coff = (atom * 32) % CIN + c16 * 4;
-                        const int* col = nbr_t + (size_t)tap * ld_t + row0 + rb;
+                        // this thread's 16-byte chunk = column atom * 32 + c16 * 4 of the stage = (tap, channel offset)
+                        const int tap = (st0 + s) * TAPG + (atom * 32 + c16 * 4) / CIN;
+                        const int coff = (atom * 32 + c16 * 4) % CIN;
+                        const bool tap_ok = tap < K;          // the last super-tap may reach past the kernel's taps
+                        const int* col = nbr_t + (size_t)(tap_ok ? tap : 0) * ld_t + row0 + rb;
                         int idx[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) idx[j] = __ldg(col + 4 * j);
+                        for (int j = 0; j < 16; ++j) idx[j] = tap_ok ? __ldg(col + 4 * j) : -1;
                         uint4 v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -242,7 +245,7 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint32_t a0 = smem_base + aslot * WG_A_BYTES;
-                        const uint32_t d = tmem_acc + (uint32_t)(s * COUT);
+                        const uint32_t d = tmem_acc + (uint32_t)(s * NCOL);
                         const uint32_t first = (started >> s) & 1u;
 #pragma unroll
                         for (int ks = 0; ks < WG_RS / 8; ++ks)      // 8 rows per MMA = two 512-byte swizzle groups
@@ -275,12 +278,12 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
 #pragma unroll 1
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * COUT + c0), v);
+                tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * NCOL + c0), v);
                 tmem_ld_wait();
                 if (tap < K) {
                     float* dst = dw + ((size_t)tap * CIN + ci) * COUT + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < (COUT < 32 ? COUT : 32); ++i) {
                         const float x = __uint_as_float(v[i]);
                         if (x != 0.f) atomicAdd(dst + i, x);
                     }
@@ -298,7 +301,7 @@ int launch_wgrad_umma(const float* in, const float* dout, const int* nbr_t, cons
                       int K, float* dw, cudaStream_t stream) {
     constexpr int TAPG = 128 / CIN;
     const int k_eff = (K + TAPG - 1) / TAPG;
-    const int st_max = 512 / COUT;                               // accumulator slots TMEM holds
+    const int st_max = 512 / (COUT < 32 ? 32 : COUT);            // accumulator slots TMEM holds
     const int ngroups = (k_eff + st_max - 1) / st_max;
     const int st_per_cta = (k_eff + ngroups - 1) / ngroups;
     const int n_tiles = (n_rows + WG_TILE - 1) / WG_TILE;
@@ -307,7 +310,7 @@ int launch_wgrad_umma(const float* in, const float* dout, const int* nbr_t, cons
     if (chunks > n_tiles) chunks = n_tiles;
     const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
     chunks = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    const size_t smem = wg_smem_bytes(COUT);
+    const size_t smem = wg_smem_bytes(COUT < 32 ? 32 : COUT);
     auto kern = k_spconv_wgrad_umma<CIN, COUT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(chunks, (k_eff + st_per_cta - 1) / st_per_cta);
@@ -318,8 +321,9 @@ int launch_wgrad_umma(const float* in, const float* dout, const int* nbr_t, cons
 
 bool wgrad_shape_ok(int K, int cin, int cout) {
     if (K < 1 || K > WG_MAX_TAPS) return false;
-    const bool ci = cin == 32 || cin == 64 || cin == 128;
-    const bool co = cout == 32 || cout == 64 || cout == 128;
+    const bool ci = cin == 16 || cin == 32 || cin == 64 || cin == 128;
+    const bool co = cout == 16 || cout == 32 || cout == 64 || cout == 128;
+    if ((cin == 16 || cout == 16) && (cin > 32 || cout > 32)) return false;     // not instantiated
     return ci && co;
 }
 
@@ -345,6 +349,9 @@ int ud_sparse_conv_tc_wgrad(const float* in, const float* dout, const int* nbr_t
     if (n_rows == 0) return UD_OK;
     if (!in || !dout || !nbr_t || !tile_masks) return UD_ERR_INVALID_ARG;
     if ((((uintptr_t)in | (uintptr_t)dout) & 15u) != 0) return UD_ERR_INVALID_ARG;
+    UD_DISPATCH_WGRAD_UMMA(16, 16)
+    UD_DISPATCH_WGRAD_UMMA(16, 32)
+    UD_DISPATCH_WGRAD_UMMA(32, 16)
     UD_DISPATCH_WGRAD_UMMA(32, 32)
     UD_DISPATCH_WGRAD_UMMA(32, 64)
     UD_DISPATCH_WGRAD_UMMA(32, 128)

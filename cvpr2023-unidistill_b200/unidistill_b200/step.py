@@ -17,6 +17,7 @@ of `load_state_dict` from host memory every step (:465).
 """
 import torch
 import torch.distributed as dist
+import torch.nn as nn
 
 from unidistill.layers.losses import distill as L
 from unidistill.utils import torch_dist
@@ -53,6 +54,42 @@ class FlatGradBucket:
         return self.flat
 
 
+def fold_frozen_batchnorm(module):
+    """Folds every eval-mode BatchNorm2d that directly follows a Conv2d / ConvTranspose2d into that convolution
+    (w' = w * gamma / sqrt(var + eps), b' = beta + (b - mean) * gamma / sqrt(var + eps)) and replaces the norm by
+    nn.Identity.  For a FROZEN network only (the distillation teacher, reference ..._distill_lidar.py:419-433: eval(),
+    requires_grad False): same function up to fp32 rounding, one full pass over every activation less.  Handles
+    nn.Sequential runs and the convN / bnN attribute pairs of torchvision's ResNet blocks.  Returns the count."""
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+
+    def fusable(conv, bn):
+        return (isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)) and type(bn) is nn.BatchNorm2d and not bn.training
+                and bn.track_running_stats and bn.running_mean is not None
+                and (not isinstance(conv, nn.ConvTranspose2d) or conv.groups == 1))
+
+    n = 0
+    for m in list(module.modules()):
+        names = list(m._modules.keys())
+        if isinstance(m, nn.Sequential):
+            pairs = [(names[i], names[i + 1]) for i in range(len(names) - 1)]
+        else:
+            pairs = [(a, "bn" + a[4:]) for a in names if a.startswith("conv") and ("bn" + a[4:]) in m._modules]
+        for a, b in pairs:
+            conv, bn = m._modules[a], m._modules[b]
+            if conv is None or bn is None or not fusable(conv, bn):
+                continue
+            fmt = torch.channels_last if conv.weight.is_contiguous(memory_format=torch.channels_last) and \
+                not conv.weight.is_contiguous() else torch.contiguous_format
+            fused = fuse_conv_bn_eval(conv.eval(), bn, transpose=isinstance(conv, nn.ConvTranspose2d))
+            fused = fused.to(memory_format=fmt)
+            for p in fused.parameters():
+                p.requires_grad = False
+            m._modules[a] = fused
+            m._modules[b] = nn.Identity()
+            n += 1
+    return n
+
+
 def gt_with_labels(gt_boxes, gt_labels):
     """(B,M,9) boxes + 0-based labels -> (B,M,10) with 1-based labels in the last column (:456-458)."""
     return torch.cat([gt_boxes, (gt_labels.to(gt_boxes.dtype) + 1).unsqueeze(2)], dim=2)
@@ -75,7 +112,8 @@ class DistillStep:
     out_size_factor).  Call with a device-resident batch dict (points list | None, imgs | None, mats_dict | None,
     gt_boxes (B,M,9), gt_labels (B,M)); returns a dict of detached loss terms."""
 
-    def __init__(self, student, teacher, geometry, lr=2e-4, weight_decay=1e-2, clamp_min=1e-4, optimizer=True):
+    def __init__(self, student, teacher, geometry, lr=2e-4, weight_decay=1e-2, clamp_min=1e-4, optimizer=True,
+                 fold_teacher_bn=True, teacher_cuda_graph=True):
         self.student, self.teacher = student, teacher
         self.pc_range = list(geometry["pc_range"])
         self.voxel_size = list(geometry["voxel_size"])
@@ -87,6 +125,10 @@ class DistillStep:
             p.requires_grad = False
         teacher.eval()
         teacher.det_head.dense_head.distill = True             # (:419)
+        # the frozen eval-mode teacher: BatchNorm folded into the dense convolutions, dense trunk replayed from a CUDA graph
+        self.folded_bn = fold_frozen_batchnorm(teacher) if fold_teacher_bn else 0
+        if teacher_cuda_graph and next(teacher.parameters()).is_cuda:
+            teacher.use_cuda_graph(True)
         self._teacher_buffers = [(b, b.detach().clone()) for b in teacher.buffers()]
         student.train()
         self.bucket = FlatGradBucket(student.parameters())
@@ -96,6 +138,10 @@ class DistillStep:
             self.opt = torch.optim.AdamW(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused)
 
     def _restore_teacher(self):
+        """The reference reloads the teacher's state_dict every step (:465) because pytorch-lightning may have put it
+        back into train mode; an eval-mode teacher cannot change its buffers, so there is nothing to restore."""
+        if not any(m.training for m in self.teacher.modules()):
+            return
         for b, snap in self._teacher_buffers:
             b.copy_(snap)
 

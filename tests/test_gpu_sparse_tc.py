@@ -181,8 +181,8 @@ def _wgrad_both(sparse, f, g, rb, w_shape):
     return res
 
 
-@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128),
-                                      (32, 128), (128, 32)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (64, 128),
+                                      (128, 64), (128, 128), (32, 128), (128, 32)])
 def test_tc_wgrad_subm_matches_oracle(cuda, native_lib, cin, cout, tc_variant):
     from unidistill_b200 import sparse
 
@@ -213,7 +213,7 @@ def test_tc_wgrad_subm_matches_oracle(cuda, native_lib, cin, cout, tc_variant):
     assert abs(num / den - 1.0) < 1e-4
 
 
-@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
+@pytest.mark.parametrize("cin,cout,ksize,stride,pad", [(16, 32, 3, 2, 1), (32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
                                                        (128, 128, (3, 1, 1), (2, 1, 1), 0)])
 def test_tc_wgrad_strided_matches_simt(cuda, native_lib, cin, cout, ksize, stride, pad, tc_variant):
     from unidistill_b200 import sparse

@@ -87,3 +87,41 @@ def test_one_optimizer_step_changes_student_only(step_and_batch):
     assert all(torch.equal(a, p.detach()) for a, p in zip(t0, step.teacher.parameters()))
     step._restore_teacher()
     assert all(torch.equal(a, b) for a, b in zip(tb0, step.teacher.buffers()))
+
+
+def test_folded_graphed_teacher_equals_plain_teacher(cuda, native_lib):
+    """DistillStep folds the frozen teacher's BatchNorm into its convolutions and replays its dense trunk from a CUDA
+    graph: same teacher outputs as the untouched eval-mode module (plain fp32 convolutions for the comparison)."""
+    import copy
+
+    from unidistill_b200 import models
+    from unidistill_b200.step import DistillStep, gt_with_labels
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+        teacher = models.BEVFusionCenterHead(cfg).to(cuda)
+        for m in teacher.modules():                      # non-trivial running statistics
+            if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        plain = copy.deepcopy(teacher).eval()
+        plain.det_head.dense_head.distill = True
+        student = models.BEVFusionCenterHead(cfg).to(cuda)
+        step = DistillStep(student, teacher, cfg["geometry"], optimizer=False)
+        assert step.folded_bn > 20 and teacher._dense_graph is not None
+        batch = _batch(cuda)
+        gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
+        with torch.no_grad():
+            ref = plain(batch["points"], None, None, gt, return_feature=True)
+            for _ in range(2):                           # capture, then replay
+                got = teacher(batch["points"], None, None, gt, return_feature=True)
+        assert torch.allclose(got[0], ref[0], rtol=1e-4, atol=1e-5)          # sparse encoder: eval-mode BN, deterministic
+        assert torch.allclose(got[1], ref[1], rtol=1e-3, atol=1e-4)
+        for hg, he in zip(got[2], ref[2]):
+            for k in he:
+                assert torch.allclose(hg[k], he[k], rtol=2e-3, atol=2e-4), k
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
