@@ -1,33 +1,29 @@
-"""IouAwareGenProposals -- constructor-compatible holder of the decode/NMS configuration.
+"""IouAwareGenProposals -- CenterPoint decoding whose NMS ranks candidates by the IoU-aware score
+score^(1-a) * iou^a with iou = clamp(iou_head / 2 + 0.5, 0, 1) and a per-task exponent `iou_aware_list[task]`
+(reference generate_proposals/iou_aware_gen_proposals.py:42-139).  The reported `scores` stay the class scores.
+The head also reads `voxel_size` from this object during training (center_head_iou_aware.py:87)."""
+import torch
 
-The decode + rotated-BEV NMS post-processing (reference generate_proposals/iou_aware_gen_proposals.py:141-247,
-backed by the binary-only iou3d_nms_cuda extension) only runs in eval/predict mode and is OUT OF SCOPE of
-the training hot path (SURVEY 2.1 #14, 8f-2 "next").  The head reads `voxel_size` from this object during
-training (center_head_iou_aware.py:87), which is provided.
-"""
-from .base_gen_proposals import BaseGenProposals
+from .centerpoint_gen_proposals import CenterPointGenProposals
 
 
-class IouAwareGenProposals(BaseGenProposals):
+class IouAwareGenProposals(CenterPointGenProposals):
     def __init__(self, dataset_name, class_names, post_center_limit_range, score_threshold, pc_range,
-                 out_size_factor, voxel_size, no_log, iou_aware_list, nms_iou_threshold_train,
-                 nms_pre_max_size_train, nms_post_max_size_train, nms_iou_threshold_test,
-                 nms_pre_max_size_test, nms_post_max_size_test):
-        self.dataset_name = dataset_name
-        self.class_names = class_names
-        self.post_center_limit_range = post_center_limit_range
-        self.score_threshold = score_threshold
-        self.pc_range = pc_range
-        self.out_size_factor = out_size_factor
-        self.voxel_size = voxel_size
-        self.no_log = no_log
+                 out_size_factor, voxel_size, no_log, nms_iou_threshold_train, nms_pre_max_size_train,
+                 nms_post_max_size_train, nms_iou_threshold_test, nms_pre_max_size_test, nms_post_max_size_test,
+                 iou_aware_list):
+        super().__init__(dataset_name, class_names, post_center_limit_range, score_threshold, pc_range,
+                         out_size_factor, voxel_size, no_log, nms_iou_threshold_train, nms_pre_max_size_train,
+                         nms_post_max_size_train, nms_iou_threshold_test, nms_pre_max_size_test,
+                         nms_post_max_size_test)
         self.iou_aware_list = iou_aware_list
         self.nms_cfg = dict(
             train=(nms_iou_threshold_train, nms_pre_max_size_train, nms_post_max_size_train),
             test=(nms_iou_threshold_test, nms_pre_max_size_test, nms_post_max_size_test))
-        self.training = True
 
-    def generate_predicted_boxes(self, forward_ret_dict, data_dict):
-        raise NotImplementedError(
-            "eval-time proposal decoding / rotated NMS is outside the B200 training hot path "
-            "(SURVEY.md 8f-2); run evaluation with the reference's post-processing")
+    def _nms_score(self, scores, inds, task_id, iouhm):
+        batch, K = scores.shape
+        iouscore = self._transpose_and_gather_feat(iouhm, inds).view(batch, K)
+        iouscore = torch.clamp(iouscore / 2 + 0.5, 0, 1)
+        a = self.iou_aware_list[task_id]
+        return (scores ** (1 - a)).mul(iouscore ** a)

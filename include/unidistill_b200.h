@@ -219,6 +219,21 @@ int ud_response_distill_backward(const float* cls_s, const float* cls_t, const f
                                  float clamp_lo, float g_cls, float g_reg, float* d_cls, float* d_reg,
                                  void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Proposal post-processing (inference): rotated-BEV IoU and greedy NMS.  Replaces the binary-only
+ * extension unidistill/layers/head/det3d/generate_proposals/iou3d_nms_cuda*.so:
+ *     boxes_iou_bev_gpu(boxes_a (N,7), boxes_b (M,7), ans_iou (N,M))          -> ud_boxes_iou_bev
+ *     nms_gpu(boxes (N,7) cuda f32 sorted by score, keep int64 CPU, thresh)    -> ud_nms_bev (batched, device-side sweep)
+ * called from generate_proposals/centerpoint_gen_proposals.py:85-106.  Boxes are [x,y,z,dx,dy,dz,heading] f32.
+ * ud_nms_bev processes n_sets independent box lists of n rows each (one (task, sample) pair per set); only the first
+ * n_valid[s] rows (device int32, NULL = n) of set s take part; keep (n_sets,max_keep) int32 = kept row positions in
+ * ascending order padded with -1, num_keep (n_sets) int32 (<= max_keep, == selected[:post_max_size]).
+ * ------------------------------------------------------------------------------------------- */
+int ud_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* ans_iou, void* stream);
+int ud_nms_bev_workspace_bytes(int n_sets, int n, size_t* bytes);
+int ud_nms_bev(const float* boxes, const int* n_valid, int n_sets, int n, float thresh, int max_keep, int* keep,
+               int* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libud_oracle.so")
-SOURCES = ["lidar_ref.c", "camera_ref.c"]
+SOURCES = ["lidar_ref.c", "camera_ref.c", "nms_ref.c"]
 
 
 def build(force=False):

@@ -212,10 +212,69 @@ def golden_dense_blocks():
                         voxel_num=np_(lss.voxel_num), **{k: np_(v) for k, v in mats.items()})
 
 
+def golden_proposals():
+    """IouAwareGenProposals.generate_predicted_boxes of the REAL reference (top-k, decoding, IoU-aware ranking, range /
+    score masks, per-sample NMS calls, roi assembly) on seeded head outputs.  The binary-only `iou3d_nms_cuda.nms_gpu`
+    it calls is replaced by the CPU restatement oracle/nms_ref.c (so this fixture pins everything around the NMS against
+    the reference, and the NMS itself against the oracle)."""
+    import importlib
+
+    from oracle import nms as ON
+
+    nms_mod = importlib.import_module("unidistill.layers.head.det3d.generate_proposals.iou3d_nms_cuda")
+
+    def nms_gpu(boxes, keep, thresh):
+        k = ON.nms_bev(np_(boxes), float(thresh))
+        keep[: len(k)] = torch.from_numpy(k)
+        return len(k)
+
+    nms_mod.nms_gpu = nms_gpu
+    from unidistill.layers.head.det3d.generate_proposals import IouAwareGenProposals
+
+    cfg = dict(dataset_name="nuscenes", class_names=[t["class_names"] for t in TASKS],
+               post_center_limit_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.1,
+               pc_range=PC_RANGE[0:2], out_size_factor=OSF, voxel_size=VOXEL[0:2], no_log=False,
+               iou_aware_list=[0.65, 0.5, 0.65, 0.3, 0.65, 0.65], nms_iou_threshold_train=0.8,
+               nms_pre_max_size_train=300, nms_post_max_size_train=40, nms_iou_threshold_test=0.1,
+               nms_pre_max_size_test=300, nms_post_max_size_test=25)
+    layer = IouAwareGenProposals(**cfg)
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 32, 32
+    feats, out = [], {}
+    for t, task in enumerate(TASKS):
+        nc = task["num_class"]
+        d = {"hm": torch.randn(B, nc, H, W, generator=g) * 1.5 - 1.5, "reg": torch.rand(B, 2, H, W, generator=g),
+             "height": torch.randn(B, 1, H, W, generator=g) * 0.5 - 1.0,
+             "dim": torch.randn(B, 3, H, W, generator=g) * 0.3 + torch.tensor([1.4, 0.6, 0.5]).view(1, 3, 1, 1),
+             "rot": torch.randn(B, 2, H, W, generator=g), "vel": torch.randn(B, 2, H, W, generator=g),
+             "iou": torch.randn(B, 1, H, W, generator=g)}
+        if t == 3:
+            d["hm"][1] = -9.0                     # a (task, sample) pair with no candidate above the score threshold
+        feats.append(d)
+        for k, v in d.items():
+            out["in_%d_%s" % (t, k)] = np_(v)
+    for mode in ("test", "train"):
+        layer.training = mode == "train"
+        res = layer.generate_predicted_boxes({"multi_head_features": [dict(d) for d in feats]}, {})
+        for b, pd in enumerate(res["pred_dicts"]):
+            for k, v in pd.items():
+                out["%s_%s_%d" % (mode, k, b)] = np_(v)
+        for k in ("rois", "roi_scores", "roi_labels"):
+            out["%s_%s" % (mode, k)] = np_(res[k])
+    out["cfg_iou_aware_list"] = np.asarray(cfg["iou_aware_list"], np.float32)
+    np.savez_compressed(os.path.join(HERE, "proposals.npz"), **out)
+    print("proposals: test-mode boxes per sample", [out["test_pred_boxes_%d" % b].shape[0] for b in range(B)],
+          "train-mode", [out["train_pred_boxes_%d" % b].shape[0] for b in range(B)])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "proposals":
+        golden_proposals()
+        sys.exit(0)
     golden_assigner_and_head()
     golden_distill()
     golden_dense_blocks()
+    golden_proposals()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
