@@ -502,7 +502,7 @@ __host__ __device__ constexpr size_t ts_smem_bytes(int cin, int cout, int mode) 
 }
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -1051,15 +1051,375 @@ int launch_umma_ts(const float* in, const float* wpacked, const float* bias, con
     return UD_OK;
 }
 
+// ================================================================================================
+// Variant "DG" (direct gather, variant 4): same arithmetic as MODE_BF3, but the gathered operand never touches shared
+// memory.  ncu showed the L1/shared-memory data pipe (not the tensor pipe) as the busiest unit of the TS kernels: per
+// 64-channel stage 32 KB of gathered rows were written to shared memory by cp.async, read back by the transform warps and
+// 24 KB of weight slices re-read by the MMAs.  Here a gather warp loads its rows straight into registers in the fragment
+// layout of tcgen05.st.16x256b (measured with tools/tmem_layout_probe.cu: thread t holds TMEM lanes t/4 and t/4+8,
+// columns 2(t%4), 2(t%4)+1 of every 8-column unit), so 4 lanes read 64 contiguous bytes of a row (whole 32-byte sectors),
+// splits them into bf16 hi/lo in registers and stores them to the stage's TMEM columns.
+//   warps 0-15 : four gather sets (set = stage % 4 = TMEM A slot; warp & 3 = TMEM lane quadrant); epilogue afterwards
+//   warp 16    : MMA issuer          warp 17 : weight slices (bulk copies)          warp 18 : row-index segments (bulk copies)
+constexpr int DG_THREADS = 608;
+constexpr int DG_SETS = 4;
+constexpr int DG_IDX_STAGES = 16;
+constexpr int DG_B_STAGES = 4;
+__host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout) {
+    return (size_t)DG_B_STAGES * ts_b_bytes(cin, cout, MODE_BF3) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 + 1024;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const float* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(DG_THREADS, 1)
+k_spconv_umma_dg(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
+                 const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
+                 int tiles, float* __restrict__ out, double* __restrict__ stats) {
+    constexpr int TAPG = ts_tapg(CIN);               // kernel taps per 64-channel stage
+    constexpr int KS = 64;
+    constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
+    constexpr int IDX_INTS = TAPG * TILE_M;
+    constexpr int A_COLS = KS;                       // TMEM columns of one A stage: 32 hi | 32 lo (bf16 pairs)
+    constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
+    constexpr int B_BYTES = ts_b_bytes(CIN, COUT, MODE_BF3);
+    constexpr int BBF_BYTES = COUT * KS * 2;
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                  ((uint32_t)(TILE_M >> 4) << 24);
+    static_assert(A_STAGES == DG_SETS, "one gather set per TMEM A slot");
+    static_assert((CIN * TAPG) % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
+    constexpr int NBAR = 2 * A_STAGES + 2 * DG_B_STAGES + 2 * DG_IDX_STAGES + 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[NBAR];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int tile_mask_s[MAX_TILES];
+    __shared__ unsigned short a_sched[MAX_SCHED];          // tap | chunk << 5 | tile << 8
+    __shared__ unsigned short b_sched[MAX_TAPS * 4];
+    __shared__ unsigned short b_count[MAX_TAPS * 4];
+    __shared__ int n_a_s, n_b_s;
+    __shared__ float col_sum_s[2 * 256];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int row0 = blockIdx.x * tiles * TILE_M;
+    const int rows_cta = min(tiles * TILE_M, n_out - row0);
+    const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
+    if (stats != nullptr && tid < 2 * COUT) col_sum_s[(tid / COUT) * 256 + tid % COUT] = 0.f;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t smem_b = smem_base;
+    const uint32_t smem_idx = smem_b + DG_B_STAGES * B_BYTES;
+    const int* const idx_ring = reinterpret_cast<const int*>(smem_al + DG_B_STAGES * B_BYTES);
+    const uint32_t bar_a_full = smem_u32(&bars[0]);
+    const uint32_t bar_a_empty = bar_a_full + 8 * A_STAGES;
+    const uint32_t bar_b_full = bar_a_empty + 8 * A_STAGES;
+    const uint32_t bar_b_empty = bar_b_full + 8 * DG_B_STAGES;
+    const uint32_t bar_idx_full = bar_b_empty + 8 * DG_B_STAGES;
+    const uint32_t bar_idx_empty = bar_idx_full + 8 * DG_IDX_STAGES;
+    const uint32_t bar_acc = bar_idx_empty + 8 * DG_IDX_STAGES;
+
+    if (tid == 0) {
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, TS_GROUP);         // every thread of the owning gather set
+            mbar_init(bar_a_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < DG_B_STAGES; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < DG_IDX_STAGES; ++s) {
+            mbar_init(bar_idx_full + 8 * s, 1);
+            mbar_init(bar_idx_empty + 8 * s, TS_GROUP / 32);   // lane 0 of each warp of the consuming gather set
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    const int K_eff = (K + TAPG - 1) / TAPG;
+    if (tid < MAX_TILES) {
+        const int tile_g = blockIdx.x * tiles + tid;
+        unsigned int m = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+        if (TAPG > 1) {
+            unsigned int me = 0u;
+            for (int j = 0; j < K_eff; ++j)
+                if ((m >> (j * TAPG)) & ((1u << TAPG) - 1u)) me |= 1u << j;
+            m = me;
+        }
+        tile_mask_s[tid] = m;
+    }
+    if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K_eff, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int n_a = n_a_s;
+    const int n_b = n_b_s;
+    const uint32_t tmem_acc = tmem_base_s;
+    const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+
+    if (warp < 16) {
+        // ============ gather sets: global -> registers (st.16x256b fragment layout) -> bf16 hi/lo -> TMEM ============
+        const int set = warp >> 2;
+        const int q = warp & 3;
+        const int rsub = lane >> 2;                      // row within an 8-row group
+        const int csub = (lane & 3) * 4;                 // first of this thread's 4 channels within a 16-channel unit
+        for (int it = set; it < n_a; it += DG_SETS) {
+            const int islot = it % DG_IDX_STAGES;
+            mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / DG_IDX_STAGES)) & 1u);
+            // rows 32 q + 16 h + rsub + 8 rr of the tile, for every tap of the stage
+            int idx[2][2][TAPG];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int g = 0; g < TAPG; ++g)
+                        idx[h][rr][g] = idx_ring[islot * IDX_INTS + g * TILE_M + q * 32 + h * 16 + rr * 8 + rsub];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
+            const int c0 = TAPG == 1 ? ((a_sched[it] >> 5) & 7) * KS : 0;
+            uint4 x[2][2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // unit j = channels [16 j, 16 j + 16) of the stage: TAPG 1: one tap; TAPG 2 (CIN 32): tap j / 2;
+                        // TAPG 4 (CIN 16): tap j
+                        const int g = TAPG == 1 ? 0 : (TAPG == 2 ? (j >> 1) : j);
+                        const int ch = TAPG == 1 ? c0 + 16 * j + csub : (TAPG == 2 ? (j & 1) * 16 + csub : csub);
+                        const int r = idx[h][rr][g];
+                        x[h][rr][j] = make_uint4(0u, 0u, 0u, 0u);
+                        if (r >= 0) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + ch);
+                    }
+            const int aslot = it % A_STAGES;             // == set
+            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const uint4 v = x[h][rr][j];
+                        const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
+                        const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
+                        hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
+                        lo[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                    }
+                const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
+                tmem_st_16x256b_x4(taddr, hi);
+                tmem_st_16x256b_x4(taddr + KS / 2, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * aslot);
+        }
+    } else if (warp == 16) {
+        // ============ MMA issuer ============
+        unsigned int started = 0u;
+        int it = 0;
+        for (int ib = 0; ib < n_b; ++ib) {
+            const int bslot = ib % DG_B_STAGES;
+            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / DG_B_STAGES)) & 1u);
+            const uint32_t b_base = smem_b + bslot * B_BYTES;
+            const uint64_t db_hi = umma_desc_sw128(b_base);
+            const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
+            const int cnt = b_count[ib];
+            for (int c = 0; c < cnt; ++c, ++it) {
+                const int aslot = it % A_STAGES;
+                const int tile = a_sched[it] >> 8;
+                mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
+                    const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
+                    const uint32_t first = (started >> tile) & 1u;
+#pragma unroll
+                    for (int k16 = 0; k16 < KS / 16; ++k16) {
+                        const uint32_t a_hi = a_stage + (uint32_t)(k16 * 8);
+                        const uint32_t a_lo = a_hi + KS / 2;
+                        const uint64_t adv = (uint64_t)(k16 * 2);
+                        umma_bf16_ts(d, a_lo, db_hi + adv, IDESC_BF, (first || k16 > 0) ? 1u : 0u);
+                        umma_bf16_ts(d, a_hi, db_lo + adv, IDESC_BF, 1u);
+                        umma_bf16_ts(d, a_hi, db_hi + adv, IDESC_BF, 1u);
+                    }
+                    umma_commit(bar_a_empty + 8 * aslot);
+                }
+                started |= 1u << tile;
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(bar_b_empty + 8 * bslot);
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        // ============ warp 17: weight slices, warp 18: per-stage row-index segments (bulk async copies) ============
+        if (warp == 17 && lane == 0) {
+            for (int ib = 0; ib < n_b; ++ib) {
+                const int bslot = ib % DG_B_STAGES;
+                mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / DG_B_STAGES)) & 1u) ^ 1u);
+                const unsigned e = b_sched[ib];
+                const int tap = e & 31, ch = e >> 5;
+                const float* src = wpacked + (size_t)(tap * NCHUNK + ch) * (B_BYTES / 4);
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
+                bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
+            }
+        } else if (warp == 18 && lane == 0) {
+            for (int it = 0; it < n_a; ++it) {
+                const int islot = it % DG_IDX_STAGES;
+                mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / DG_IDX_STAGES)) & 1u) ^ 1u);
+                const unsigned e = a_sched[it];
+                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, IDX_INTS * 4);
+#pragma unroll
+                for (int g = 0; g < TAPG; ++g) {
+                    const int* seg = nbr_t + (size_t)((e & 31) * TAPG + g) * ld_t + row0 + (e >> 8) * TILE_M;
+                    bulk_g2s(smem_idx + (islot * TAPG + g) * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
+    if (warp < 16) {
+        if (n_a > 0) {
+            mbar_wait(bar_acc, 0u);
+            tc_fence_after();
+        }
+        const int q = warp & 3;
+        constexpr int CW = COUT >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int t = warp >> 2; t < tiles; t += DG_SETS) {
+            if (t * TILE_M >= rows_cta) break;
+            const bool has_acc = tile_mask_s[t] != 0u;
+            const int r_local = t * TILE_M + q * 32 + lane;
+            const int row = row0 + r_local;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                uint32_t v[32];
+                if (has_acc) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = 0u;
+                }
+                const bool row_ok = r_local < rows_cta;
+                float* dst = out + (size_t)row * COUT + c0;
+#pragma unroll
+                for (int i = 0; i < CW; i += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[i + 0]);
+                    o.y = __uint_as_float(v[i + 1]);
+                    o.z = __uint_as_float(v[i + 2]);
+                    o.w = __uint_as_float(v[i + 3]);
+                    if (bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
+                    if (stats != nullptr) {
+                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
+                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
+                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
+                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
+                    }
+                }
+                if (stats != nullptr) {
+                    float a[32], sq[32];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        a[i] = __uint_as_float(v[i]);
+                        sq[i] = a[i] * a[i];
+                    }
+                    int col = 0;
+#pragma unroll
+                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float sa = up ? a[i] : a[i + sft];
+                            const float sb = up ? sq[i] : sq[i + sft];
+                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
+                            const float rq = __shfl_xor_sync(0xffffffffu, sb, sft);
+                            a[i] = (up ? a[i + sft] : a[i]) + ra;
+                            sq[i] = (up ? sq[i + sft] : sq[i]) + rq;
+                        }
+                        if (up) col += sft;
+                    }
+                    if (CW == 16) {
+                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+                        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 16);
+                    }
+                    if (CW == 32 || lane < 16) {
+                        atomicAdd(&col_sum_s[c0 + col], a[0]);
+                        atomicAdd(&col_sum_s[256 + c0 + col], sq[0]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (stats != nullptr && tid < 2 * COUT) {
+        const float vsum = col_sum_s[(tid / COUT) * 256 + tid % COUT];
+        if (vsum != 0.f) atomicAdd(stats + tid, (double)vsum);
+    }
+    if (warp == 16) tmem_dealloc(tmem_acc, 512);
+}
+
+template <int CIN, int COUT>
+int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                   const unsigned int* tile_masks, int n_out, int K, float* out, double* stats, cudaStream_t stream) {
+    const size_t smem = dg_smem_bytes(CIN, COUT);
+    auto kern = k_spconv_umma_dg<CIN, COUT>;
+    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    const int tmax = ts_tiles_max(COUT);
+    const int waves = (n_tiles + UD_NUM_SMS * tmax - 1) / (UD_NUM_SMS * tmax);
+    int tiles = (n_tiles + UD_NUM_SMS * waves - 1) / (UD_NUM_SMS * waves);
+    if (tiles < 1) tiles = 1;
+    if (tiles > tmax) tiles = tmax;
+    const int ctas = (n_tiles + tiles - 1) / tiles;
+    kern<<<ctas, DG_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
 // forward shapes of VoxelResBackBone8x and the dgrad (cin/cout swapped) of every layer but the first; the CIN = 16
 // shapes exist only in the default variant (multi-tap stages)
 bool tc_shape_ok(int K, int cin, int cout, int variant) {
     static const int shapes[][2] = {{32, 16}, {32, 32}, {32, 64}, {64, 32}, {64, 64}, {64, 128}, {128, 64}, {128, 128}};
     static const int narrow[][2] = {{16, 16}, {16, 32}};
-    if (K < 1 || K > MAX_TAPS || variant < 0 || variant > 3) return false;
+    if (K < 1 || K > MAX_TAPS || variant < 0 || variant > 4) return false;
     for (const auto& s : shapes)
         if (s[0] == cin && s[1] == cout) return true;
-    if (variant == 0 || variant == 3)
+    if (variant == 0 || variant >= 3)
         for (const auto& s : narrow)
             if (s[0] == cin && s[1] == cout) return true;
     return false;
@@ -1072,6 +1432,7 @@ bool tc_shape_ok(int K, int cin, int cout, int variant) {
         return variant == 1   ? launch_umma<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stream)            \
                : variant == 2 ? launch_umma_ts<CI, CO, MODE_3XTF32>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
                : variant == 3 ? launch_umma_ts<CI, CO, MODE_BF3>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
+               : variant == 4 ? launch_umma_dg<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
                               : launch_umma_ts<CI, CO, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
 
 extern "C" {
@@ -1096,7 +1457,7 @@ int ud_sparse_conv_tc_supported(int K, int cin, int cout, int variant) {
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, int variant, size_t* bytes) {
     if (!bytes) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
-    const int tapg = (variant == 0 || variant == 3) ? ts_tapg(cin) : 1;     // variant 3 needs half of this
+    const int tapg = (variant == 0 || variant >= 3) ? ts_tapg(cin) : 1;     // variants 3 and 4 need half of this
     *bytes = (size_t)((K + tapg - 1) / tapg) * (cin * tapg) * cout * 2 * sizeof(float);
     return UD_OK;
 }
@@ -1109,7 +1470,7 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     if (!w || !packed) return UD_ERR_INVALID_ARG;
     if (!tc_shape_ok(K, cin, cout, variant)) return UD_ERR_UNSUPPORTED;
     if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
-    if (variant == 3) {
+    if (variant == 3 || variant == 4) {          // same bf16 hi/lo image
         const int tapg = ts_tapg(cin);
         const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
         k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, tapg, (unsigned char*)packed);
@@ -1148,7 +1509,8 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
 // nbr_t (K, n_out) int32 tap-major gather table and tile_masks (ceil(n_out/128)) from ud_rulebook_transpose;
 // out (n_out, cout) f32.
 // variant: 0 = A through TMEM, tf32 hi*hi + bf16 correction MMAs, 1 = A through shared memory, 3xTF32 ("SS"),
-//          2 = A through TMEM, 3xTF32, 3 = A through TMEM, bf16x3 (bf16 hi/lo split of both operands).
+//          2 = A through TMEM, 3xTF32, 3 = A through TMEM, bf16x3 (bf16 hi/lo split of both operands),
+//          4 = bf16x3 with the gathered operand loaded straight into registers and stored to TMEM (no shared-memory staging).
 //          The weights must have been packed for the same variant.
 // bn_sums (nullable, variants 0, 2 and 3): double[2 * cout] that the kernel ADDS the per-channel sum and sum of squares of
 // `out` to (the statistics pass of the BatchNorm that follows, fused into the epilogue); the caller zeroes it.
@@ -1168,6 +1530,12 @@ int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float
             return launch_umma_ts<16, 16, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
         if (cin == 16 && cout == 32)
             return launch_umma_ts<16, 32, MODE_BF16C>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+    }
+    if (variant == 4) {
+        if (cin == 16 && cout == 16)
+            return launch_umma_dg<16, 16>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+        if (cin == 16 && cout == 32)
+            return launch_umma_dg<16, 32>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
     }
     if (variant == 3) {
         if (cin == 16 && cout == 16)

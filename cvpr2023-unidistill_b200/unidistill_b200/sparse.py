@@ -149,9 +149,9 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 # tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
 # every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
-# 3: A through TMEM, bf16x3 operand split (default), 0: A through TMEM, tf32 + bf16 correction MMAs,
-# 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
-TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "3"))
+# 4: bf16x3 operand split, gathered rows go global -> registers -> TMEM (default), 3: bf16x3 with the rows staged in
+# shared memory, 0: A through TMEM, tf32 + bf16 correction MMAs, 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
+TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "4"))
 # the tensor-core kernel's epilogue also accumulates the per-channel sum / sum of squares of its output, so the
 # BatchNorm1d that follows skips its statistics pass (attribute `_ud_bn_sums` on the conv output, see batch_norm_act)
 FUSE_BN_STATS = os.environ.get("UD_FUSE_BN_STATS", "1") != "0"
@@ -195,7 +195,7 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
     if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout, TC_VARIANT):
         packed = _packed_weights(w_k, K, cin, cout, sp, weight)
         if meta is not None:
-            meta["kernel"] = "k_spconv_umma" if TC_VARIANT == 1 else "k_spconv_umma_ts"
+            meta["kernel"] = {1: "k_spconv_umma", 4: "k_spconv_umma_dg"}.get(TC_VARIANT, "k_spconv_umma_ts")
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
         sums = None
         if want_stats and FUSE_BN_STATS and TC_VARIANT != 1:

@@ -109,8 +109,9 @@ int ud_debug_umma_flags(int flags);
  * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
  * tensor-core kernel reads */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
-/* variant 3 = default kernel (A operand staged through TMEM; both operands split into bf16 hi + bf16 lo, three bf16 MMAs
- * per 16 channels), 0 = A through TMEM, hi*hi in TF32 + the two correction products as bf16 MMAs,
+/* variant 4 = default kernel (both operands split into bf16 hi + bf16 lo, three bf16 MMAs per 16 channels; the gathered
+ * rows go global -> registers -> TMEM without shared-memory staging), 3 = the same arithmetic with the rows staged in shared
+ * memory (cp.async ring + transform warps; weights packed identically), 0 = A through TMEM, hi*hi in TF32 + the two correction products as bf16 MMAs,
  * 1 = A through shared memory with 3xTF32, 2 = A through TMEM with 3xTF32; pack the weights for the same variant */
 /* bn_sums (nullable; not with variant 1): double[2*cout]; the kernel adds the per-channel sum and sum of squares of `out`
  * to it, i.e. the statistics pass of the BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113) */

@@ -26,8 +26,8 @@ def _cloud(rng, B, shape, n, C):
     return coords, feat
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["TMEM-A+bf16-corrections", "smem-A-3xTF32", "TMEM-A-3xTF32", "TMEM-A-bf16x3"],
-                autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["TMEM-A+bf16-corrections", "smem-A-3xTF32", "TMEM-A-3xTF32", "TMEM-A-bf16x3",
+                                                "direct-gather-bf16x3"], autouse=True)
 def tc_variant(request):
     from unidistill_b200 import sparse
 
@@ -48,6 +48,7 @@ def test_tc_subm_matches_oracle(cuda, native_lib, cin, cout):
 
     assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 0) == 1
     assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 3) == 1
+    assert native_lib.ud_sparse_conv_tc_supported(27, cin, cout, 4) == 1
     rng = np.random.default_rng(cin * 7 + cout)
     B, shape, n = 2, [7, 20, 20], 1931                     # 1931 rows: 15 full tiles + a ragged tail
     coords, feat = _cloud(rng, B, shape, n, cin)
@@ -95,7 +96,7 @@ def test_tc_fused_batchnorm_statistics(cuda, native_lib, cin, cout, tc_variant):
     and the bias included), and BatchNorm driven by them == nn.BatchNorm1d."""
     from unidistill_b200 import sparse
 
-    if tc_variant == 1 or (cin == 16 and tc_variant not in (0, 3)):
+    if tc_variant == 1 or (cin == 16 and tc_variant not in (0, 3, 4)):
         pytest.skip("statistics are fused into the TMEM-operand kernels only")
     rng = np.random.default_rng(cin + cout)
     B, shape, n = 2, [7, 24, 24], 2777
