@@ -1071,7 +1071,7 @@ __host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout) {
 
 __device__ __forceinline__ uint4 ldg_stream(const float* p) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
