@@ -16,11 +16,16 @@ Semantics kept on purpose:
     infs, BEVFusion_nuscenes_centerhead_fusion_exp.py:125-127).
 """
 import math
+import os
 
 import numpy as np
 import torch
 
 from .base_assigner import BaseAssigner
+
+# CUDA inputs go through the fused assignment kernel (csrc/fcos_assign.cu); UD_FCOS_KERNEL=0 keeps the tensor program
+# (which is also what runs for CPU tensors, e.g. in the golden-fixture tests)
+USE_ASSIGN_KERNEL = os.environ.get("UD_FCOS_KERNEL", "1") != "0"
 
 
 class FCOSAssigner(BaseAssigner):
@@ -70,6 +75,44 @@ class FCOSAssigner(BaseAssigner):
             self._lut_cache[key] = (task_of.to(device), offset_of.to(device))
         return self._lut_cache[key]
 
+    def _assign_kernel(self, boxes, task_id, cls_off, anchors, fw, fh, stride, max_objs):
+        """The per-task part of assign_targets as ONE kernel launch for the whole batch and all tasks
+        (csrc/fcos_assign.cu, `ud_fcos_assign`); bit-identical to the tensor program below."""
+        from unidistill_b200 import native
+
+        lib = native.load()
+        dev = boxes.device
+        B, M, NB = boxes.shape
+        T = len(self.tasks)
+        n_anchor = fw * fh
+        prefix = [0]
+        for task in self.tasks:
+            prefix.append(prefix[-1] + len(task["class_names"]))
+        boxes = boxes.contiguous()
+        tid = task_id.to(torch.int32).contiguous()
+        coff = cls_off.to(torch.int32).contiguous()
+        anchors = anchors.float().contiguous()
+        heat = torch.zeros((B * prefix[-1] * n_anchor,), dtype=torch.float32, device=dev)
+        ind = torch.empty((T, B, max_objs), dtype=torch.long, device=dev)
+        mask = torch.empty((T, B, max_objs), dtype=torch.bool, device=dev)
+        cat = torch.empty((T, B, max_objs), dtype=torch.long, device=dev)
+        enc = torch.empty((T, B, max_objs, NB + 1), dtype=torch.float32, device=dev)
+        if NB + 1 != self.default_box_dims:
+            raise RuntimeError("box encoding width %d != %d" % (NB + 1, self.default_box_dims))
+        pre = native.host_ints(prefix)
+        rc = lib.ud_fcos_assign(native.ptr(boxes), native.ptr(tid), native.ptr(coff), native.ptr(anchors), int(B), int(M),
+                                int(NB), int(fw), int(fh), float(stride), T, native.host_ptr(pre), int(self.assign_topk),
+                                int(max_objs), float(self.voxel_size[0]), float(self.voxel_size[1]),
+                                float(self.out_size_factor), native.ptr(heat), native.ptr(ind), native.ptr(mask),
+                                native.ptr(cat), native.ptr(enc), native.stream_ptr(dev))
+        native.check(rc, "ud_fcos_assign")
+        heatmaps, inds, masks, cats, encs = {}, {}, {}, {}, {}
+        for t, task in enumerate(self.tasks):
+            n_cls = prefix[t + 1] - prefix[t]
+            heatmaps[t] = heat[B * n_anchor * prefix[t]: B * n_anchor * prefix[t + 1]].view(B, n_cls, fh, fw)
+            inds[t], masks[t], cats[t], encs[t] = ind[t], mask[t], cat[t], enc[t]
+        return {"heatmap": heatmaps, "ind": inds, "mask": masks, "cat": cats, "box_encoding": encs}
+
     @torch.no_grad()
     def assign_targets(self, gt_boxes):
         """gt_boxes (B, M, C + 1) with the 1-based class in the last column."""
@@ -111,6 +154,9 @@ class FCOSAssigner(BaseAssigner):
         boxes[:, :, 3] = boxes[:, :, 3] / self.voxel_size[0]
         boxes[:, :, 4] = boxes[:, :, 4] / self.voxel_size[1]
         boxes[:, :, 6] = self.limit_period(boxes[:, :, 6], offset=0.5, period=math.pi * 2)
+
+        if gt_boxes.is_cuda and USE_ASSIGN_KERNEL and M <= 128 and n_anchor <= 32768 and topk <= 9:
+            return self._assign_kernel(boxes, task_id, cls_off, anchors, fw, fh, stride, max_objs)
 
         # squared centre distance anchor <-> GT: (B, M, A)
         d2 = torch.pow(anchors.view(1, 1, n_anchor, 2) - boxes[:, :, None, :2], 2).sum(dim=3)

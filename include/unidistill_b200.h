@@ -235,6 +235,19 @@ int ud_nms_bev_workspace_bytes(int n_sets, int n, size_t* bytes);
 int ud_nms_bev(const float* boxes, const int* n_valid, int n_sets, int n, float thresh, int max_keep, int* keep,
                int* num_keep, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * FCOS-style target assignment of the CenterPoint head: replaces FCOSAssigner.assign_targets,
+ * layers/head/det3d/target_assigner/fcos_assigner.py:73-285, for the whole batch and all tasks in one launch.
+ * boxes (B,M,NB) f32 in feature-map units [x,y,z,dx,dy,dz,yaw,(vx,vy)] in the reference's task order; task_id / cls_off
+ * (B,M) int32 (task of the row or -1, class index inside the task); anchors (fw*fh,2) f32 (x,y), a = i*fw + j, regular
+ * grid of pitch `stride`; cls_prefix: n_tasks+1 HOST ints.  heat: concatenation over tasks of (B,n_cls_t,fh*fw) f32 blocks,
+ * zeroed by the caller; ind / cat (n_tasks,B,max_objs) int64, mask (n_tasks,B,max_objs) u8, enc (n_tasks,B,max_objs,NB+1).
+ * ------------------------------------------------------------------------------------------- */
+int ud_fcos_assign(const float* boxes, const int* task_id, const int* cls_off, const float* anchors, int B, int M, int NB,
+                   int fw, int fh, float stride, int n_tasks, const int* cls_prefix, int topk, int max_objs, float vs0,
+                   float vs1, float osf, float* heat, long long* ind, unsigned char* mask, long long* cat, float* enc,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
