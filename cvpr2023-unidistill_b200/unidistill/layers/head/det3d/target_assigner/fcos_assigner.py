@@ -200,7 +200,9 @@ class FCOSAssigner(BaseAssigner):
             masks[t] = keep.contiguous()
             cats[t] = torch.where(keep, tgt_cls, torch.zeros_like(tgt_cls)).long().contiguous()
             heat = torch.zeros((B, n_cls, n_anchor), dtype=torch.float32, device=device)
-            cls_of_anchor = torch.gather(cls_off, 1, gt_of_anchor)            # (B, A)
+            # (B, A); a sample without a GT of this task points every anchor at row 0, whose class offset may not exist
+            # in this task: clamp (those anchors are not positive, the scattered value is 0)
+            cls_of_anchor = torch.gather(cls_off, 1, gt_of_anchor).clamp(max=n_cls - 1)
             heat.scatter_(1, cls_of_anchor.unsqueeze(1), pos.unsqueeze(1).float())
             heatmaps[t] = heat.view(B, n_cls, fh, fw).contiguous()
             if enc.shape[2] != dims:
