@@ -178,6 +178,81 @@ def _gt_with_labels(batch):
     return torch.cat([batch["gt_boxes"], (batch["gt_labels"].float() + 1).unsqueeze(-1)], dim=-1)
 
 
+class PipelinedE2E:
+    """End-to-end stepping for the forward workloads: every step copies ITS inputs from pinned host memory and reads ITS
+    result back to pinned host memory, but the copies run on a second stream so that the host->device copy of step i+1 and
+    the device->host read of step i-1 overlap the kernels of step i (double-buffered device inputs / host outputs).
+    All K copies in and K reads out happen between the start and the end event of the timed region."""
+
+    def __init__(self, device, host_inputs, forward, result_of):
+        import torch
+
+        self.device, self.host_inputs, self.forward, self.result_of = device, host_inputs, forward, result_of
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.dev_in = [None, None]
+        self.in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.in_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.out_host = [None, None]
+        self.out_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self.prefetched = False
+
+    def _h2d(self, slot):
+        import torch
+
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.in_free[slot])            # the step that last read this buffer is done
+            if self.dev_in[slot] is None:
+                self.dev_in[slot] = [t.to(self.device, non_blocking=True) for t in self.host_inputs]
+            else:
+                for d, h in zip(self.dev_in[slot], self.host_inputs):
+                    d.copy_(h, non_blocking=True)
+            self.in_ready[slot].record(self.copy_stream)
+
+    def begin(self):
+        """Start of a timed region: nothing is in flight; the first step's copy is issued inside the region."""
+        import torch
+
+        self.i = 0
+        self.prefetched = False
+        cur = torch.cuda.current_stream(self.device)
+        for e in self.in_free:
+            e.record(cur)
+
+    def step(self, last=False):
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        slot = self.i % 2
+        if not self.prefetched:
+            self._h2d(slot)
+        if not last:
+            self._h2d(1 - slot)                                        # next step's inputs, overlapping this step
+            self.prefetched = True
+        cur.wait_event(self.in_ready[slot])
+        res = self.result_of(self.forward(*self.dev_in[slot]))
+        self.in_free[slot].record(cur)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(done)
+            if self.out_host[slot] is None:
+                self.out_host[slot] = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+            self.out_host[slot].copy_(res, non_blocking=True)
+            self.out_done[slot].record(self.copy_stream)
+        res.record_stream(self.copy_stream)
+        self.i += 1
+        return self.out_host[slot]
+
+    def end(self):
+        """Joins the copy stream into the current stream (before the closing event of the timed region)."""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        for e in self.out_done:
+            cur.wait_event(e)
+
+
 class LidarForward:
     """configs[1]: BEVFusion-LiDAR SparseEncoder + CenterHead fwd, synthetic 40k pts x 10 sweeps, bs=4."""
 
@@ -200,8 +275,12 @@ class LidarForward:
         self.points_dev = self.points_host.to(device)
         self.gt_dev = self.gt_host.to(device)
         self.h2d = self.points_host.numel() * 4 + self.gt_host.numel() * 4
-        self.d2h = 0
+        self.d2h = BS_PER_GPU * 10 * 128 * 128 * 4                          # class heat-maps (B, 10, 128, 128) f32
         self.samples = BS_PER_GPU
+        import torch as _t
+
+        self.pipe = PipelinedE2E(device, [self.points_host, self.gt_host], self._forward,
+                                 lambda r: _t.cat([h["hm"] for h in r[2]], dim=1))
 
     def _forward(self, points, gt):
         import torch
@@ -251,8 +330,15 @@ class CameraForward:
         self.gt_dev = self.gt_host.to(device)
         self.h2d = (self.imgs_host.numel() + sum(v.numel() for v in self.mats_host.values())
                     + self.gt_host.numel()) * 4
-        self.d2h = 0
+        self.d2h = BS_PER_GPU * 10 * 128 * 128 * 4
         self.samples = BS_PER_GPU
+        self._mat_keys = sorted(self.mats_host)
+        import torch as _t
+
+        self.pipe = PipelinedE2E(
+            device, [self.imgs_host, self.gt_host] + [self.mats_host[k] for k in self._mat_keys],
+            lambda imgs, gt, *mats: self._forward(imgs, dict(zip(self._mat_keys, mats)), gt),
+            lambda r: _t.cat([h["hm"] for h in r[2]], dim=1))
 
     def _forward(self, imgs, mats, gt):
         import torch
@@ -468,20 +554,34 @@ def run_ours(args):
         roof_step_ms, records, _, _, _ = timed_pass(True, False)
 
     # ---- end-to-end: pinned host -> device copy + step + result read-back, every step -------------
-    for _ in range(0 if args.profile else 2):
-        wl.step_e2e()
-    torch.cuda.synchronize()
-    ev = []
-    _barrier(world)
-    for _ in range(1 if args.profile else args.steps):
-        flush()
+    # One event pair around the K steps (copies of neighbouring steps overlap on a second stream for the forward
+    # workloads, see PipelinedE2E; the distillation steps copy, run and read back in order on one stream).
+    pipe = getattr(wl, "pipe", None)
+    n_e2e = 1 if args.profile else args.steps
+
+    def e2e_pass(n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        _barrier(world)
+        if pipe is not None:
+            pipe.begin()
         e0.record()
-        wl.step_e2e()
+        for i in range(n):
+            flush()
+            if pipe is not None:
+                pipe.step(last=(i == n - 1))
+            else:
+                wl.step_e2e()
+        if pipe is not None:
+            pipe.end()
         e1.record()
-        ev.append((e0, e1))
-    _barrier(world)
-    e2e_ms = _max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world, device)
+        _barrier(world)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    if not args.profile:
+        e2e_pass(2)
+    e2e_ms = _max_over_ranks(e2e_pass(n_e2e), world, device) * (args.steps / n_e2e)
     gc.enable()
     e2e_value = samples_all / (e2e_ms / 1e3)
 
@@ -493,7 +593,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "global_batch": BS_PER_GPU * world, "per_gpu_batch": BS_PER_GPU,
                    "bn": getattr(wl, "bn_note", "train-mode batch statistics, torch.no_grad"), "weights": "random init, seed 0",
-                   "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed",
+                   "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed (e2e: one event pair around "
+                         "the K steps, flushes included)",
                    "dense_convs": "cuDNN fp32 (torch default allow_tf32), NHWC memory format", "parallelism": "dp%d" % world},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(wl.h2d),
                 "d2h_bytes_per_step": int(wl.d2h), "ms_per_step": round(e2e_ms / args.steps, 3)},
