@@ -293,17 +293,6 @@ class LidarForward:
     def step(self):
         return self._forward(self.points_dev, self.gt_dev)
 
-    def step_e2e(self):
-        import torch
-
-        pts = self.points_host.to(self.device, non_blocking=True)
-        gt = self.gt_host.to(self.device, non_blocking=True)
-        _, _, heads = self._forward(pts, gt)
-        hm = torch.cat([h["hm"] for h in heads], dim=1)          # (B, 10, 128, 128) class heat-maps
-        out = hm.cpu()
-        self.d2h = out.numel() * 4
-        return out
-
 
 class CameraForward:
     """configs[2]: BEVFusion-camera LSS (fused lift-splat) + CenterHead fwd, 6 x 256x704, bs=4."""
@@ -348,17 +337,6 @@ class CameraForward:
 
     def step(self):
         return self._forward(self.imgs_dev, self.mats_dev, self.gt_dev)
-
-    def step_e2e(self):
-        import torch
-
-        imgs = self.imgs_host.to(self.device, non_blocking=True)
-        mats = {k: v.to(self.device, non_blocking=True) for k, v in self.mats_host.items()}
-        gt = self.gt_host.to(self.device, non_blocking=True)
-        _, _, heads = self._forward(imgs, mats, gt)
-        out = torch.cat([h["hm"] for h in heads], dim=1).cpu()
-        self.d2h = out.numel() * 4
-        return out
 
 
 class DistillTrainStep:
