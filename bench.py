@@ -651,13 +651,67 @@ class CpuLidarForward:
     samples = 1
 
 
+class CpuCameraForward:
+    """Port of the reference's camera forward for one sample (bs=1, 6 cameras): image backbone / neck / depth net and
+    LSS geometry on torch CPU (the reference's own Python, mirrored), then the reference's pooling path as written --
+    the lifted (6*112*16*44, 256) volume is materialised (lss_fpn.py:289-310) and scattered by the C restatement of
+    voxel_pooling_ext (oracle/camera_ref.c) -- then BEV backbone and head on torch CPU."""
+
+    sample = "1 sample (6 cams 256x704) per step, bs=1, same generator and weights as the GPU arm"
+
+    def __init__(self, seed=0):
+        import torch
+
+        from oracle import camera as OC
+        from unidistill_b200 import models, synthetic as S
+
+        torch.manual_seed(0)
+        self.OC = OC
+        cfg = models.make_model_cfg(bev=128, lidar=False, camera=True)
+        self.model = models.BEVFusionCenterHead(cfg).train()
+        self.lss = self.model.camera_encoder.backbone
+        cam = S.camera_batch(BS_PER_GPU, seed=seed)
+        lid = S.lidar_batch(BS_PER_GPU, seed=seed, points_per_sweep=64, sweeps=1)
+        self.imgs, self.mats = cam["imgs"], cam["mats_dict"]
+        self.gt = _gt_with_labels(lid)
+        self.i = 0
+
+    def step(self):
+        import torch
+
+        OC, lss = self.OC, self.lss
+        b = self.i % self.imgs.shape[0]
+        self.i += 1
+        with torch.no_grad():
+            imgs = self.imgs[b:b + 1, 0:1]
+            mats = {k: v[b:b + 1] for k, v in self.mats.items()}
+            src = lss.get_cam_feats(imgs)[:, 0]
+            ncam = src.shape[1]
+            feat = lss._forward_depth_net(src.reshape(ncam, src.shape[2], src.shape[3], src.shape[4]), mats, 0)
+            depth = feat[:, : lss.depth_channels].softmax(1)
+            ctx = feat[:, lss.depth_channels: lss.depth_channels + lss.output_channels]
+            geom = lss.get_geometry(mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0],
+                                    mats.get("bda_mat", None))
+            geom_xyz = OC.voxel_indices(geom, lss.voxel_coord, lss.voxel_size)
+            bev = torch.from_numpy(OC.lift_splat_reference(depth, ctx, geom_xyz.numpy(), [int(v) for v in lss.voxel_num]))
+            x = self.model.bev_encoder(bev)
+            ret = self.model.det_head(x[0], self.gt[b:b + 1])
+        return ret
+
+    samples = 1
+
+
+CPU_WORKLOADS = {"lidar": CpuLidarForward, "camera": CpuCameraForward}
+
+
 def cpu_baseline(workload, budget_s=25.0):
     import torch
 
-    if workload != "lidar":
-        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "not implemented"}
+    if workload not in CPU_WORKLOADS:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": "not implemented for the training-step workloads"}
     torch.set_num_threads(os.cpu_count() or 1)
-    wl = CpuLidarForward()
+    wl = CPU_WORKLOADS[workload]()
     wl.step()                                   # warm-up (builds the C oracle, primes torch's thread pool)
     t0 = time.perf_counter()
     n = 0
@@ -680,10 +734,10 @@ def run_reference(args):
     import torch
 
     torch.set_num_threads(os.cpu_count() or 1)
-    if args.workload != "lidar":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm implements the lidar workload only"}))
+    if args.workload not in CPU_WORKLOADS:
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm implements the forward workloads only"}))
         return
-    wl = CpuLidarForward()
+    wl = CPU_WORKLOADS[args.workload]()
     for _ in range(max(1, min(args.warmup, 2))):      # bounded: one CPU step is seconds long
         wl.step()
     t0 = time.perf_counter()
@@ -696,7 +750,7 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
         "ms_per_step": round(el / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": LidarForward.name, "sample_per_step": wl.sample},
+        "config": {"workload": WORKLOADS[args.workload].name, "sample_per_step": wl.sample},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d x [%s]" % (args.steps, wl.sample)},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

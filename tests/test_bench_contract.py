@@ -10,9 +10,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+import pytest
+
+
+@pytest.mark.parametrize("workload", ["lidar", "camera"])
+def test_reference_arm_json_line(workload):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--workload", workload], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["scaling"] == "weak"
@@ -28,6 +32,13 @@ def test_reference_arm_other_ranks_print_nothing():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_declines_training_steps():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "distill"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0 and line["impl"] == "reference" and "unavailable" in line
 
 
 def test_gpu_arm_has_no_cpu_fallback():
