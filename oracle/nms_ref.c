@@ -13,7 +13,10 @@
  *   - IoU = overlap / max(area_a + area_b - overlap, 1e-8),
  *   - NMS: boxes arrive sorted by descending score; box i is kept unless an earlier KEPT box j has IoU(j, i) > thresh.
  * Parity unpinned against the binary (cp36 / torch-1.9 ABI, sm_61-86 cubins: cannot be loaded here); pinned instead
- * by known answers and by exact float64 polygon clipping in tests/test_oracle_nms.py.
+ * by known answers and by exact float64 polygon clipping in tests/test_oracle_nms.py.  What the binary itself shows
+ * (objdump / byte search, no execution): its .rodata holds the float constants 1e-8 and 1e-2 side by side (EPS and the
+ * in-box MARGIN of this algorithm), and boxes_iou_bev_cpu calls sincosf / sinf, atan2f and fmaxf -- the corner
+ * rotation, the polar-angle comparison and the max(union, EPS) of the restatement below.
  */
 #include <math.h>
 #include <stdint.h>
