@@ -12,8 +12,12 @@
  *   - the points sorted by polar angle about their mean (bubble sort, strict >), fan area, |area| / 2,
  *   - IoU = overlap / max(area_a + area_b - overlap, 1e-8),
  *   - NMS: boxes arrive sorted by descending score; box i is kept unless an earlier KEPT box j has IoU(j, i) > thresh.
- * Parity unpinned against the binary (cp36 / torch-1.9 ABI, sm_61-86 cubins: cannot be loaded here); pinned instead
- * by known answers and by exact float64 polygon clipping in tests/test_oracle_nms.py.  What the binary itself shows
+ * PINNED AGAINST THE REFERENCE BINARY: the extension cannot be imported (cp36 / torch-1.9 ABI, sm_61-86 cubins), but
+ * its CPU routine boxes_iou_bev_cpu can be executed in the build container through oracle/refshim/iou3d_shim.cpp;
+ * tests/golden/iou3d_ref.npz holds its output for 78 000 box pairs (random + degenerate cases) and
+ * ud_ref_boxes_iou_bev reproduces every value bit for bit (tests/test_oracle_nms.py).  The GPU routines nms_gpu /
+ * boxes_iou_bev_gpu of the binary cannot run here (no cubin for sm_100); the sweep restated in ud_ref_nms_bev is the
+ * published one.  Further checks: known answers, exact float64 polygon clipping.  What the binary itself shows
  * (objdump / byte search, no execution): its .rodata holds the float constants 1e-8 and 1e-2 side by side (EPS and the
  * in-box MARGIN of this algorithm), and boxes_iou_bev_cpu calls sincosf / sinf, atan2f and fmaxf -- the corner
  * rotation, the polar-angle comparison and the max(union, EPS) of the restatement below.

@@ -267,7 +267,45 @@ def golden_proposals():
           "train-mode", [out["train_pred_boxes_%d" % b].shape[0] for b in range(B)])
 
 
+def golden_iou3d():
+    """Rotated-BEV IoU matrices computed by the REFERENCE BINARY's own CPU routine boxes_iou_bev_cpu (executed through
+    oracle/refshim): pins oracle/nms_ref.c and, through it, the CUDA kernels."""
+    from oracle import refshim
+
+    rng = np.random.default_rng(2023)
+    n = 260
+    b = np.zeros((n, 7), np.float32)
+    b[:, 0:2] = rng.uniform(-12, 12, (n, 2))
+    b[:, 2] = rng.normal(-1, 0.5, n)
+    b[:, 3] = rng.uniform(0.3, 7, n)
+    b[:, 4] = rng.uniform(0.3, 3, n)
+    b[:, 5] = rng.uniform(0.5, 3, n)
+    b[:, 6] = rng.uniform(-3.3, 3.3, n)
+    # special cases: identical boxes, the same rectangle described with a quarter / half turn, nested, edge-touching,
+    # axis-aligned grids (many collinear edges), tiny and huge boxes, shared centres
+    b[1] = b[0]
+    b[2] = b[0]; b[2, 3], b[2, 4], b[2, 6] = b[0, 4], b[0, 3], b[0, 6] + np.float32(np.pi / 2)
+    b[3] = b[0]; b[3, 6] = b[0, 6] + np.float32(np.pi)
+    b[4] = b[0]; b[4, 3:5] *= 0.5
+    b[5] = [0, 0, 0, 4, 2, 1, 0]; b[6] = [4, 0, 0, 4, 2, 1, 0]; b[7] = [2, 0, 0, 4, 2, 1, 0]; b[8] = [0, 2, 0, 4, 2, 1, 0]
+    b[9] = [0, 0, 0, 2, 2, 1, np.pi / 4]; b[10] = [0, 0, 0, 4, 4, 1, 0]
+    b[11] = [1, 1, 0, 0.05, 0.05, 1, 0.3]; b[12] = [1, 1, 0, 40, 30, 1, 0.3]
+    for i in range(13, 33):
+        b[i] = [float((i - 13) % 5) * 1.5, float((i - 13) // 5) * 1.0, 0, 2.0, 1.2, 1, 0]
+    b[33:60, 0:2] = b[60:87, 0:2]
+    iou = refshim.reference_boxes_iou_bev_cpu(b, b)
+    a2 = b[:40].copy()
+    a2[:, 0:2] += rng.normal(0, 0.3, (40, 2)).astype(np.float32)
+    iou2 = refshim.reference_boxes_iou_bev_cpu(a2, b)
+    np.savez_compressed(os.path.join(HERE, "iou3d_ref.npz"), boxes=b, iou=iou, boxes_a2=a2, iou_a2=iou2)
+    print("iou3d_ref: %d x %d and %d x %d matrices from the reference binary; nonzero pairs %d" % (
+        n, n, 40, n, int((iou > 0).sum())))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "iou3d":
+        golden_iou3d()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "proposals":
         golden_proposals()
         sys.exit(0)
@@ -275,6 +313,7 @@ if __name__ == "__main__":
     golden_distill()
     golden_dense_blocks()
     golden_proposals()
+    golden_iou3d()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
