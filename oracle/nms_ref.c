@@ -20,7 +20,10 @@
  * published one.  Further checks: known answers, exact float64 polygon clipping.  What the binary itself shows
  * (objdump / byte search, no execution): its .rodata holds the float constants 1e-8 and 1e-2 side by side (EPS and the
  * in-box MARGIN of this algorithm), and boxes_iou_bev_cpu calls sincosf / sinf, atan2f and fmaxf -- the corner
- * rotation, the polar-angle comparison and the max(union, EPS) of the restatement below.
+ * rotation, the polar-angle comparison and the max(union, EPS) of the restatement below.  The sm_86 SASS of its
+ * nms_kernel (cuobjdump -sass) compares with FSETP.GT against the threshold parameter (strict >) and selects the
+ * first column of a diagonal 64x64 block by ISETP.NE on (blockIdx.y, blockIdx.x) (start = threadIdx.x + 1 there, else 0):
+ * the suppression rule restated in ud_ref_nms_bev.
  */
 #include <math.h>
 #include <stdint.h>
