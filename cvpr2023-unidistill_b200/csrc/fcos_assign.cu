@@ -10,8 +10,10 @@
 //   * outputs listed in ascending anchor order, truncated / zero padded to max_objs; the heat-map is one-hot at ALL
 //     positives;  box code = [(x-ax)/osf, (y-ay)/osf, z, log(dx*vs0), log(dy*vs1), log(dz), sin(yaw), cos(yaw), rest...].
 // Anchors form a regular fw x fh grid (anchor a = i*fw + j); the `topk` (<= 9) nearest anchors of a point always lie in
-// the 9x9 window around the nearest grid node (radius 4 covers the degenerate case of a point far outside the map,
-// whose 9 nearest anchors sit in one border column), so 81 candidates per GT are ranked instead of all fw*fh.
+// the 17x17 window around the (clamped) nearest grid node: inside the map they are within 2 cells, and for a point far
+// off a map corner they are 9 consecutive anchors of one border row, i.e. at most 8 columns from the corner (a 9x9 window
+// is exact only up to ~7 cells outside the map; tests/test_fcos_window.py checks the property on the CPU).  So 289
+// candidates per GT are ranked instead of all fw*fh.
 // grid (n_tasks, B), 256 threads; one warp per GT for the top-k, bitmap + popcount scan for the ordered compaction.
 #include "common.cuh"
 
@@ -21,8 +23,9 @@ constexpr int FA_THREADS = 256;
 constexpr int FA_MAX_GT = 128;          // GT rows per sample
 constexpr int FA_MAX_WORDS = 1024;      // anchors / 32  (<= 32768 anchors)
 constexpr int FA_MAX_TASKS = 16;
-constexpr int FA_RADIUS = 4;
+constexpr int FA_RADIUS = 8;
 constexpr int FA_WIN = 2 * FA_RADIUS + 1;
+constexpr int FA_SLOTS = (FA_WIN * FA_WIN + 31) / 32;   // window candidates per lane
 
 struct FaParams {
     int cls_prefix[FA_MAX_TASKS + 1];   // classes before task t
@@ -78,10 +81,10 @@ k_fcos_assign(const float* __restrict__ boxes, const int* __restrict__ task_id, 
         if (!(py == py)) ci = 0;
         cj = min(max(cj, 0), fw - 1);
         ci = min(max(ci, 0), fh - 1);
-        float cd[3];
-        int ca[3];
+        float cd[FA_SLOTS];
+        int ca[FA_SLOTS];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < FA_SLOTS; ++s) {
             const int c = lane + 32 * s;
             cd[s] = INFINITY;
             ca[s] = 0x7fffffff;
@@ -99,7 +102,7 @@ k_fcos_assign(const float* __restrict__ boxes, const int* __restrict__ task_id, 
             // lane-local best, then warp argmin on (distance, anchor index)
             int bs = 0;
 #pragma unroll
-            for (int s = 1; s < 3; ++s)
+            for (int s = 1; s < FA_SLOTS; ++s)
                 if (cd[s] < cd[bs] || (cd[s] == cd[bs] && ca[s] < ca[bs])) bs = s;
             float d = cd[bs];
             int a = ca[bs];

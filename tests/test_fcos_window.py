@@ -1,0 +1,69 @@
+"""The fused assignment kernel (csrc/fcos_assign.cu) ranks only the 289 anchors of the 17x17 window (radius 8) around the
+grid node nearest to a GT centre instead of all fw*fh anchors.  Property checked here on the CPU: for points inside, on the
+border of and arbitrarily far outside the map, the `topk` = 9 nearest anchors of the full grid (ties broken by anchor index)
+all lie in that window, so the restricted ranking selects the same set.  (Inside the map they are within 2 cells; off a map
+corner they are up to 9 consecutive anchors of one border row, i.e. at most 8 columns from the corner.  A 9x9 window would be
+exact only up to ~7 cells outside the map -- less than half the diagonal of a bus or trailer whose corner is still inside,
+which the reference's range filter keeps (quirk 13) -- as the last test shows.)"""
+import numpy as np
+
+
+def _topk_full(px, py, fw, fh, stride, k):
+    j, i = np.meshgrid(np.arange(fw), np.arange(fh))
+    ax, ay = (j * stride).astype(np.float32).ravel(), (i * stride).astype(np.float32).ravel()
+    d2 = (ax - np.float32(px)) ** 2 + (ay - np.float32(py)) ** 2
+    order = np.lexsort((np.arange(d2.size), d2))
+    return set(order[:k].tolist()), d2
+
+
+def _topk_window(px, py, fw, fh, stride, k, radius=8):
+    cj = int(np.clip(np.rint(np.float32(px) / np.float32(stride)), 0, fw - 1))
+    ci = int(np.clip(np.rint(np.float32(py) / np.float32(stride)), 0, fh - 1))
+    cand = []
+    for di in range(-radius, radius + 1):
+        for dj in range(-radius, radius + 1):
+            i, j = ci + di, cj + dj
+            if 0 <= i < fh and 0 <= j < fw:
+                d2 = (np.float32(j * stride) - np.float32(px)) ** 2 + (np.float32(i * stride) - np.float32(py)) ** 2
+                cand.append((np.float32(d2), i * fw + j))
+    cand.sort()
+    return set(a for _, a in cand[:k])
+
+
+def test_window_contains_the_nine_nearest_anchors():
+    rng = np.random.default_rng(0)
+    fw = fh = 128
+    stride = 8.0
+    pts = np.concatenate([
+        rng.uniform(0, (fw - 1) * stride, (300, 2)),                       # inside the map
+        rng.uniform(-12 * stride, (fw - 1 + 12) * stride, (400, 2)),       # up to 12 cells outside, corners included
+        np.stack([rng.uniform(-3000, 4000, 150), rng.uniform(-3000, 4000, 150)], 1),   # far outside
+        np.array([[512.0, 512.0], [0.0, 0.0], [1016.0, 1016.0], [-96.0, -96.0], [1112.0, -96.0], [1016.0, 1112.0],
+                  [3.9, 4.1], [-96.0, 500.0], [-1e4, 500.0], [500.0, 2e4], [-5e3, -5e3], [1212.5, 2606.8],
+                  [-4.773005, -84.656433]]),
+    ])
+    for px, py in pts:
+        full, d2 = _topk_full(px, py, fw, fh, stride, 9)
+        win = _topk_window(px, py, fw, fh, stride, 9)
+        if full != win:
+            # only an exact distance tie at the 9th place may differ (then both choices are equally near)
+            kth = np.sort(d2)[8]
+            assert all(d2[a] == kth for a in full ^ win), (px, py)
+
+
+def test_window_on_small_and_rectangular_grids():
+    rng = np.random.default_rng(1)
+    for fw, fh in ((9, 9), (16, 40), (180, 180)):
+        for px, py in np.stack([rng.uniform(-400, (fw - 1) * 8 + 400, 150), rng.uniform(-400, (fh - 1) * 8 + 400, 150)], 1):
+            full, d2 = _topk_full(px, py, fw, fh, 8.0, 9)
+            win = _topk_window(px, py, fw, fh, 8.0, 9)
+            if full != win:
+                kth = np.sort(d2)[8]
+                assert all(d2[a] == kth for a in full ^ win), (fw, fh, px, py)
+
+
+def test_a_9x9_window_would_not_be_enough():
+    """10.6 cells off the map in y and 0.6 in x: the ninth nearest anchor is 5 columns from the corner."""
+    full, _ = _topk_full(-4.773005, -84.656433, 128, 128, 8.0, 9)
+    assert full != _topk_window(-4.773005, -84.656433, 128, 128, 8.0, 9, radius=4)
+    assert full == _topk_window(-4.773005, -84.656433, 128, 128, 8.0, 9, radius=8)
