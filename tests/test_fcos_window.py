@@ -67,3 +67,60 @@ def test_a_9x9_window_would_not_be_enough():
     full, _ = _topk_full(-4.773005, -84.656433, 128, 128, 8.0, 9)
     assert full != _topk_window(-4.773005, -84.656433, 128, 128, 8.0, 9, radius=4)
     assert full == _topk_window(-4.773005, -84.656433, 128, 128, 8.0, 9, radius=8)
+
+
+def _kernel_selection(px, py, fw, fh, stride, topk, radius=8):
+    """Lane-for-lane emulation of the selection loop of k_fcos_assign (csrc/fcos_assign.cu): 32 lanes, candidate c = lane + 32 s,
+    per-lane best slot, butterfly arg-min on (distance, anchor), the owner retires its candidate."""
+    win = 2 * radius + 1
+    slots = (win * win + 31) // 32
+    inf, big = np.float32(np.inf), 0x7FFFFFFF
+    px, py, stride = np.float32(px), np.float32(py), np.float32(stride)
+    cj = min(max(int(np.rint(px / stride)), 0), fw - 1)
+    ci = min(max(int(np.rint(py / stride)), 0), fh - 1)
+    cd = np.full((32, slots), inf, np.float32)
+    ca = np.full((32, slots), big, np.int64)
+    for lane in range(32):
+        for s in range(slots):
+            c = lane + 32 * s
+            if c < win * win:
+                i, j = ci + c // win - radius, cj + c % win - radius
+                if 0 <= i < fh and 0 <= j < fw:
+                    dx, dy = np.float32(np.float32(j * stride) - px), np.float32(np.float32(i * stride) - py)
+                    cd[lane, s] = np.float32(np.float32(dx * dx) + np.float32(dy * dy))
+                    ca[lane, s] = i * fw + j
+    chosen = set()
+    lanes = np.arange(32)
+    for _ in range(topk):
+        bs = np.zeros(32, int)
+        for lane in range(32):
+            for s in range(1, slots):
+                b = bs[lane]
+                if cd[lane, s] < cd[lane, b] or (cd[lane, s] == cd[lane, b] and ca[lane, s] < ca[lane, b]):
+                    bs[lane] = s
+        d, a = cd[lanes, bs].copy(), ca[lanes, bs].copy()
+        for o in (16, 8, 4, 2, 1):
+            od, oa = d[lanes ^ o], a[lanes ^ o]
+            take = (od < d) | ((od == d) & (oa < a))
+            d, a = np.where(take, od, d), np.where(take, oa, a)
+        assert len(set(a.tolist())) == 1
+        if a[0] == big:
+            break
+        for lane in range(32):
+            if ca[lane, bs[lane]] == a[lane]:
+                cd[lane, bs[lane]], ca[lane, bs[lane]] = inf, big
+                chosen.add(int(a[lane]))
+    return chosen
+
+
+def test_lane_level_emulation_of_the_kernel_selection():
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.uniform(0, 1016, (12, 2)), rng.uniform(-200, 1216, (12, 2)),
+                          np.stack([rng.uniform(-3000, 4000, 8), rng.uniform(-3000, 4000, 8)], 1),
+                          np.array([[512.0, 512.0], [-4.773005, -84.656433], [1212.5, 2606.8], [0.0, 0.0], [1016.0, 1016.0]])])
+    for px, py in pts:
+        full, d2 = _topk_full(px, py, 128, 128, 8.0, 9)
+        got = _kernel_selection(px, py, 128, 128, 8.0, 9)
+        if got != full:
+            kth = np.sort(d2)[8]
+            assert all(d2[a] == kth for a in got ^ full), (px, py)
