@@ -4,7 +4,11 @@ border of and arbitrarily far outside the map, the `topk` = 9 nearest anchors of
 all lie in that window, so the restricted ranking selects the same set.  (Inside the map they are within 2 cells; off a map
 corner they are up to 9 consecutive anchors of one border row, i.e. at most 8 columns from the corner.  A 9x9 window would be
 exact only up to ~7 cells outside the map -- less than half the diagonal of a bus or trailer whose corner is still inside,
-which the reference's range filter keeps (quirk 13) -- as the last test shows.)"""
+which the reference's range filter keeps (quirk 13) -- as a test below shows.)
+
+Why radius 8 is exact for k = 9: d^2 = dx(j)^2 + dy(i)^2, and |x_j - px| does not decrease as j moves away from the clamped
+nearest column cj.  If a node (i, j) with |j - cj| >= 9 were among the 9 nearest, the 9 nodes (i, cj) ... (i, j -+ 1) of the
+same row would all be at least as near, so (i, j) could at best tie for the 10th place.  The same holds for rows."""
 import numpy as np
 
 
