@@ -61,7 +61,27 @@ def stats(coords, shape, name):
         name, n, pairs / n, distinct / tiles, pairs / max(1, distinct)))
 
 
+def real_layer_sets():
+    """The ACTUAL active sets of the sparse encoder (strided convolutions dilate them): bs=1, via the rulebook oracle."""
+    batch = S.lidar_batch(1, seed=0)
+    _, coords, _, _ = O.voxelize([batch["points"][0].numpy()], S.VOXEL_SIZE_128, S.PC_RANGE_128, S.GRID_SIZE_128, 10, 120000)
+    shape = [41, 1024, 1024]
+    sets = [("stage 1 (subm1/res1, C=16)", coords, shape)]
+    cur, cur_shape = coords, shape
+    for name, pad in (("stage 2 (res2, C=32)", 1), ("stage 3 (res3, C=64)", 1), ("stage 4 (res4, C=128)", (0, 1, 1))):
+        out_coords, _, _, out_shape = O.rulebook_conv(cur, cur_shape, 3, 2, pad)
+        cur, cur_shape = np.ascontiguousarray(out_coords), [int(v) for v in out_shape]
+        sets.append((name, cur, cur_shape))
+    return sets
+
+
 def main():
+    if os.environ.get("UD_REAL_SETS", "1") != "0":
+        print("active sets of the real encoder (bs=1, strided convs dilate the sets):")
+        for name, c, sh in real_layer_sets():
+            stats(c, sh, name + ", current order")
+            stats(c[np.argsort(morton(c), kind="stable")], sh, name + ", Morton order")
+        print()
     bs = int(os.environ.get("UD_BS", "2"))
     batch = S.lidar_batch(bs, seed=0)
     clouds = [batch["points"][b].numpy() for b in range(bs)]
