@@ -1,12 +1,14 @@
-"""The fused assignment kernel (csrc/fcos_assign.cu) ranks only the 289 anchors of the 17x17 window (radius 8) around the
-grid node nearest to a GT centre instead of all fw*fh anchors.  Property checked here on the CPU: for points inside, on the
-border of and arbitrarily far outside the map, the `topk` = 9 nearest anchors of the full grid (ties broken by anchor index)
-all lie in that window, so the restricted ranking selects the same set.  (Inside the map they are within 2 cells; off a map
-corner they are up to 9 consecutive anchors of one border row, i.e. at most 8 columns from the corner.  A 9x9 window would be
-exact only up to ~7 cells outside the map -- less than half the diagonal of a bus or trailer whose corner is still inside,
-which the reference's range filter keeps (quirk 13) -- as a test below shows.)
+"""The fused assignment kernel (csrc/fcos_assign.cu) ranks only the anchors of a (2R+1)^2 window around the grid node nearest
+to a GT centre instead of all fw*fh anchors.  Properties checked here on the CPU:
+  * R = 8 (17x17): for points inside, on the border of and arbitrarily far outside the map the `topk` = 9 nearest anchors of
+    the full grid (ties broken by anchor index) all lie in the window -- exact for any input;
+  * R = 4 (9x9, the build validated on B200 in round 1 and shipped): exact inside the map and up to 7 cells outside it, not
+    beyond (a bus or trailer whose corner is still inside the map -- which the reference's range filter keeps, quirk 13 -- can
+    have its centre up to ~9 cells outside at the 0.6 m pitch of the 180^2 config);
+  * a lane-for-lane emulation of the kernel's selection loop with R = 8 agrees with the brute-force ranking, so switching the
+    constant is safe; it waits for the first GPU run of round 2 (validation debts).
 
-Why radius 8 is exact for k = 9: d^2 = dx(j)^2 + dy(i)^2, and |x_j - px| does not decrease as j moves away from the clamped
+Why R = 8 is exact for k = 9: d^2 = dx(j)^2 + dy(i)^2, and |x_j - px| does not decrease as j moves away from the clamped
 nearest column cj.  If a node (i, j) with |j - cj| >= 9 were among the 9 nearest, the 9 nodes (i, cj) ... (i, j -+ 1) of the
 same row would all be at least as near, so (i, j) could at best tie for the 10th place.  The same holds for rows."""
 import numpy as np
@@ -128,3 +130,18 @@ def test_lane_level_emulation_of_the_kernel_selection():
         if got != full:
             kth = np.sort(d2)[8]
             assert all(d2[a] == kth for a in got ^ full), (px, py)
+
+
+def test_shipped_9x9_window_is_exact_up_to_seven_cells_outside():
+    rng = np.random.default_rng(5)
+    fw = fh = 128
+    stride = 8.0
+    lo, hi = -7 * stride, (fw - 1 + 7) * stride
+    pts = np.concatenate([rng.uniform(lo, hi, (500, 2)),
+                          np.array([[lo, lo], [hi, hi], [lo, hi], [hi, lo], [lo, 500.3], [500.3, hi], [lo + 3.9, lo + 4.1]])])
+    for px, py in pts:
+        full, d2 = _topk_full(px, py, fw, fh, stride, 9)
+        win = _topk_window(px, py, fw, fh, stride, 9, radius=4)
+        if full != win:
+            kth = np.sort(d2)[8]
+            assert all(d2[a] == kth for a in full ^ win), (px, py)
