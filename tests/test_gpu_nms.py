@@ -40,17 +40,6 @@ def test_iou_bev_matches_oracle(cuda, native_lib):
     assert nms.boxes_iou_bev(torch.from_numpy(a[:0]).to(cuda), torch.from_numpy(b).to(cuda)).shape == (0, 300)
 
 
-def test_iou_bev_matches_reference_binary_golden(cuda, native_lib):
-    """Random boxes of tests/golden/iou3d_ref.npz (values computed by the reference binary's boxes_iou_bev_cpu)."""
-    from unidistill_b200 import nms
-
-    g = np.load(os.path.join(os.path.dirname(GOLDEN), "iou3d_ref.npz"))
-    b, ref = g["boxes"][87:], g["iou"][87:, 87:]
-    got = nms.boxes_iou_bev(torch.from_numpy(b).to(cuda), torch.from_numpy(b).to(cuda)).cpu().numpy()
-    assert np.abs(got - ref).max() < 2e-5
-    assert (got[ref == 0] == 0).all()
-
-
 def _ref_keep(boxes, n_valid, thresh, max_keep):
     return ON.nms_bev(boxes[:n_valid], thresh)[:max_keep]
 
