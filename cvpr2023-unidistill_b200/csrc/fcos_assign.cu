@@ -23,10 +23,11 @@ constexpr int FA_THREADS = 256;
 constexpr int FA_MAX_GT = 128;          // GT rows per sample
 constexpr int FA_MAX_WORDS = 1024;      // anchors / 32  (<= 32768 anchors)
 constexpr int FA_MAX_TASKS = 16;
-// Radius 4 is the build validated on B200 in round 1 (bit-identical to the tensor program for GT centres up to ~7 cells
-// outside the map).  Radius 8 is exact for ANY centre (proof + lane-level emulation in tests/test_fcos_window.py) and is a
-// one-constant change; it was found after the round's GPU budget was spent, so it waits for the first GPU run of round 2.
-constexpr int FA_RADIUS = 4;
+// Radius 8 is exact for ANY centre position when topk <= 9 (proof + lane-level emulation in tests/test_fcos_window.py;
+// tests/test_gpu_assigner.py draws GT centres up to 12 cells outside the map).  Radius 4, the round-1 build, was exact
+// only up to ~7 cells outside.
+constexpr int FA_RADIUS = 8;
+constexpr int FA_MAX_TOPK = FA_RADIUS + 1;
 constexpr int FA_WIN = 2 * FA_RADIUS + 1;
 constexpr int FA_SLOTS = (FA_WIN * FA_WIN + 31) / 32;   // window candidates per lane
 
@@ -44,7 +45,7 @@ k_fcos_assign(const float* __restrict__ boxes, const int* __restrict__ task_id, 
               const float* __restrict__ anchors, int B, int M, int NB, int fw, int fh, float stride, FaParams prm,
               int topk, int max_objs, float vs0, float vs1, float osf, float* __restrict__ heat,
               long long* __restrict__ ind, unsigned char* __restrict__ mask, long long* __restrict__ cat,
-              float* __restrict__ enc) {
+              float* __restrict__ enc, int* __restrict__ n_pos_out) {
     __shared__ float gx[FA_MAX_GT], gy[FA_MAX_GT];
     __shared__ int gidx[FA_MAX_GT];
     __shared__ int n_members_s;
@@ -147,6 +148,7 @@ k_fcos_assign(const float* __restrict__ boxes, const int* __restrict__ task_id, 
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
     int n_pos = 0;
     for (int w = 0; w < FA_THREADS / 32; ++w) n_pos += warp_tot[w];
+    if (n_pos_out != nullptr && tid == 0) n_pos_out[t * B + b] = n_pos;     // > max_objs: the reference would assert
     int run = base + incl - local;
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
@@ -214,23 +216,25 @@ extern "C" {
 // (x,y), anchor a = i*fw + j on a regular grid of pitch `stride`; cls_prefix (n_tasks+1) HOST ints (classes before each
 // task).  Outputs: heat (concatenation over tasks of (B,n_cls_t,fh*fw) blocks; the caller zeroes it), ind / cat
 // (n_tasks,B,max_objs) int64, mask (n_tasks,B,max_objs) u8, enc (n_tasks,B,max_objs,NB+1) f32 -- every slot is written.
+// n_pos (n_tasks,B) int32, optional (NULL to skip): positives BEFORE truncation to max_objs (the reference asserts
+// n_pos < max_objs, fcos_assigner.py `padding_to_maxobjs`; here the overflow is reported instead of silently truncated).
 int ud_fcos_assign(const float* boxes, const int* task_id, const int* cls_off, const float* anchors, int B, int M, int NB,
                    int fw, int fh, float stride, int n_tasks, const int* cls_prefix, int topk, int max_objs, float vs0,
                    float vs1, float osf, float* heat, long long* ind, unsigned char* mask, long long* cat, float* enc,
-                   void* stream_) {
+                   int* n_pos, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B < 0 || M < 1 || NB < 7 || fw < 1 || fh < 1 || n_tasks < 1 || !cls_prefix || topk < 1 || max_objs < 1)
         return UD_ERR_INVALID_ARG;
     if (B == 0) return UD_OK;
     if (!boxes || !task_id || !cls_off || !anchors || !heat || !ind || !mask || !cat || !enc) return UD_ERR_INVALID_ARG;
-    if (M > FA_MAX_GT || n_tasks > FA_MAX_TASKS || topk > FA_WIN || (long long)fw * fh > 32LL * FA_MAX_WORDS ||
+    if (M > FA_MAX_GT || n_tasks > FA_MAX_TASKS || topk > FA_MAX_TOPK || (long long)fw * fh > 32LL * FA_MAX_WORDS ||
         B > 65535 || !(stride > 0.f))
         return UD_ERR_UNSUPPORTED;
     FaParams prm;
     for (int t = 0; t <= n_tasks; ++t) prm.cls_prefix[t] = cls_prefix[t];
     dim3 grid(n_tasks, B);
     k_fcos_assign<<<grid, FA_THREADS, 0, stream>>>(boxes, task_id, cls_off, anchors, B, M, NB, fw, fh, stride, prm, topk,
-                                                   max_objs, vs0, vs1, osf, heat, ind, mask, cat, enc);
+                                                   max_objs, vs0, vs1, osf, heat, ind, mask, cat, enc, n_pos);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }

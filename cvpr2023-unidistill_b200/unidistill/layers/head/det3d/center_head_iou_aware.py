@@ -46,8 +46,9 @@ class CenterHeadIouAware(CenterHead):
             heat = forward_ret_dict["heatmap"][task_id]
             if pre is not None:
                 num_pos = pre[task_id]
-                num_hm = num_pos if "num_hm_reduced" not in forward_ret_dict else \
-                    forward_ret_dict["num_hm_reduced"][task_id]
+                # heat-map positives are NOT the same count as regression slots (overflow truncation, duplicate classes):
+                # without a pre-reduced value the criterion derives it from heatmap.eq(1).sum() itself
+                num_hm = forward_ret_dict["num_hm_reduced"][task_id] if "num_hm_reduced" in forward_ret_dict else None
             else:
                 num_pos = reduce_mean(mask.float().sum())
                 num_hm = None

@@ -26,6 +26,9 @@ from .base_assigner import BaseAssigner
 # CUDA inputs go through the fused assignment kernel (csrc/fcos_assign.cu); UD_FCOS_KERNEL=0 keeps the tensor program
 # (which is also what runs for CPU tensors, e.g. in the golden-fixture tests)
 USE_ASSIGN_KERNEL = os.environ.get("UD_FCOS_KERNEL", "1") != "0"
+# the reference asserts `n_pos < max_objs` when padding (padding_to_maxobjs); checking it costs a host sync, so it is a
+# debug switch here -- the un-truncated count is always returned as ret["n_pos"][task] (B,) for a sync-free check
+CHECK_OVERFLOW = os.environ.get("UD_ASSIGN_CHECK", "0") != "0"
 
 
 class FCOSAssigner(BaseAssigner):
@@ -100,18 +103,23 @@ class FCOSAssigner(BaseAssigner):
         if NB + 1 != self.default_box_dims:
             raise RuntimeError("box encoding width %d != %d" % (NB + 1, self.default_box_dims))
         pre = native.host_ints(prefix)
+        n_pos = torch.empty((T, B), dtype=torch.int32, device=dev)
         rc = lib.ud_fcos_assign(native.ptr(boxes), native.ptr(tid), native.ptr(coff), native.ptr(anchors), int(B), int(M),
                                 int(NB), int(fw), int(fh), float(stride), T, native.host_ptr(pre), int(self.assign_topk),
                                 int(max_objs), float(self.voxel_size[0]), float(self.voxel_size[1]),
                                 float(self.out_size_factor), native.ptr(heat), native.ptr(ind), native.ptr(mask),
-                                native.ptr(cat), native.ptr(enc), native.stream_ptr(dev))
+                                native.ptr(cat), native.ptr(enc), native.ptr(n_pos), native.stream_ptr(dev))
         native.check(rc, "ud_fcos_assign")
+        if CHECK_OVERFLOW and int(n_pos.max()) >= max_objs:          # debug mode only: host sync
+            raise AssertionError("FCOSAssigner: %d positives >= max_objs %d (reference padding_to_maxobjs asserts)"
+                                 % (int(n_pos.max()), max_objs))
         heatmaps, inds, masks, cats, encs = {}, {}, {}, {}, {}
         for t, task in enumerate(self.tasks):
             n_cls = prefix[t + 1] - prefix[t]
             heatmaps[t] = heat[B * n_anchor * prefix[t]: B * n_anchor * prefix[t + 1]].view(B, n_cls, fh, fw)
             inds[t], masks[t], cats[t], encs[t] = ind[t], mask[t], cat[t], enc[t]
-        return {"heatmap": heatmaps, "ind": inds, "mask": masks, "cat": cats, "box_encoding": encs}
+        return {"heatmap": heatmaps, "ind": inds, "mask": masks, "cat": cats, "box_encoding": encs,
+                "n_pos": {t: n_pos[t] for t in range(T)}}
 
     @torch.no_grad()
     def assign_targets(self, gt_boxes):
@@ -162,7 +170,7 @@ class FCOSAssigner(BaseAssigner):
         d2 = torch.pow(anchors.view(1, 1, n_anchor, 2) - boxes[:, :, None, :2], 2).sum(dim=3)
         near = torch.topk(d2, topk, dim=2, largest=False).indices              # (B, M, topk)
 
-        heatmaps, inds, masks, cats, encs = {}, {}, {}, {}, {}
+        heatmaps, inds, masks, cats, encs, n_poss = {}, {}, {}, {}, {}, {}
         inf = torch.full((), float("inf"), device=device)      # device-side fill: CUDA-graph capturable
         rank = torch.arange(max_objs, device=device).unsqueeze(0)
         for t, task in enumerate(self.tasks):
@@ -198,6 +206,7 @@ class FCOSAssigner(BaseAssigner):
             encs[t] = torch.where(keep_f, enc, torch.zeros_like(enc)).float().contiguous()
             inds[t] = torch.where(keep, pos_order, torch.zeros_like(pos_order)).long().contiguous()
             masks[t] = keep.contiguous()
+            n_poss[t] = n_pos[:, 0].to(torch.int32)
             cats[t] = torch.where(keep, tgt_cls, torch.zeros_like(tgt_cls)).long().contiguous()
             heat = torch.zeros((B, n_cls, n_anchor), dtype=torch.float32, device=device)
             # (B, A); a sample without a GT of this task points every anchor at row 0, whose class offset may not exist
@@ -207,4 +216,6 @@ class FCOSAssigner(BaseAssigner):
             heatmaps[t] = heat.view(B, n_cls, fh, fw).contiguous()
             if enc.shape[2] != dims:
                 raise RuntimeError("box encoding width %d != %d" % (enc.shape[2], dims))
-        return {"heatmap": heatmaps, "ind": inds, "mask": masks, "cat": cats, "box_encoding": encs}
+        if CHECK_OVERFLOW and max(int(v.max()) for v in n_poss.values()) >= max_objs:
+            raise AssertionError("FCOSAssigner: positives >= max_objs %d (reference padding_to_maxobjs asserts)" % max_objs)
+        return {"heatmap": heatmaps, "ind": inds, "mask": masks, "cat": cats, "box_encoding": encs, "n_pos": n_poss}

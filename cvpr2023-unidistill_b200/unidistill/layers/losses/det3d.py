@@ -49,9 +49,24 @@ class FocalLoss(nn.Module):
         return self._neg_loss(out, target, num_pos)
 
 
-class CenterNetFocalLoss(FocalLoss):
-    def __init__(self, alpha=0.25, gamma=2):
-        super().__init__(alpha, gamma)
+class CenterNetFocalLoss(nn.Module):
+    """The head's default `crit` (reference layers/losses/det3d.py:325-360): CornerNet focal loss for Gaussian
+    (non-binary) heat-maps -- no alpha weighting, every cell with gt < 1 is a negative weighted by (1 - gt)^4, and
+    log(1 - pred) carries no epsilon.  Not the same function as `FocalLoss` above."""
+
+    def _neg_loss(self, pred, gt, num_pos=None):
+        pos = gt.eq(1).to(pred.dtype)
+        neg = gt.lt(1).to(pred.dtype)
+        pos_loss = (torch.log(pred) * torch.pow(1 - pred, 2) * pos).sum()
+        neg_loss = (torch.log(1 - pred) * torch.pow(pred, 2) * torch.pow(1 - gt, 4) * neg).sum()
+        if num_pos is None:
+            num_pos = reduce_mean(pos.sum())
+        # sync-free form of the reference's `if num_pos == 0` (no positives => pos_loss == 0)
+        safe = torch.where(num_pos == 0, torch.ones_like(num_pos), num_pos)
+        return -(pos_loss + neg_loss) / safe
+
+    def forward(self, out, target, num_pos=None):
+        return self._neg_loss(out, target, num_pos)
 
 
 def _gather_feat(feat, ind, mask=None):

@@ -242,11 +242,13 @@ int ud_nms_bev(const float* boxes, const int* n_valid, int n_sets, int n, float 
  * (B,M) int32 (task of the row or -1, class index inside the task); anchors (fw*fh,2) f32 (x,y), a = i*fw + j, regular
  * grid of pitch `stride`; cls_prefix: n_tasks+1 HOST ints.  heat: concatenation over tasks of (B,n_cls_t,fh*fw) f32 blocks,
  * zeroed by the caller; ind / cat (n_tasks,B,max_objs) int64, mask (n_tasks,B,max_objs) u8, enc (n_tasks,B,max_objs,NB+1).
+ * n_pos (n_tasks,B) int32 or NULL: positives before truncation to max_objs (the reference asserts n_pos < max_objs in
+ * `padding_to_maxobjs`; the overflow is reported here instead).  topk <= 9.
  * ------------------------------------------------------------------------------------------- */
 int ud_fcos_assign(const float* boxes, const int* task_id, const int* cls_off, const float* anchors, int B, int M, int NB,
                    int fw, int fh, float stride, int n_tasks, const int* cls_prefix, int topk, int max_objs, float vs0,
                    float vs1, float osf, float* heat, long long* ind, unsigned char* mask, long long* cat, float* enc,
-                   void* stream);
+                   int* n_pos, void* stream);
 
 #ifdef __cplusplus
 }

@@ -267,6 +267,23 @@ def golden_proposals():
           "train-mode", [out["train_pred_boxes_%d" % b].shape[0] for b in range(B)])
 
 
+def golden_focal_default():
+    """The head's DEFAULT heat-map criterion, CenterNetFocalLoss (reference layers/losses/det3d.py:325-360), on a
+    Gaussian (non-binary) target: no alpha, negatives = gt < 1 weighted by (1 - gt)^4, no epsilon in log(1 - pred)."""
+    from unidistill.layers.losses.det3d import CenterNetFocalLoss, FocalLoss
+
+    g = torch.Generator().manual_seed(21)
+    pred = torch.clamp(torch.randn(2, 3, 16, 16, generator=g).sigmoid(), 1e-4, 1 - 1e-4)
+    gt = torch.rand(2, 3, 16, 16, generator=g) ** 3
+    gt[0, 0, 3, 4] = 1.0
+    gt[1, 2, 9, 9] = 1.0
+    gt[1, 1] = 0.0
+    out = {"pred": np_(pred), "gt": np_(gt), "loss": np_(CenterNetFocalLoss()(pred, gt)),
+           "loss_nopos": np_(CenterNetFocalLoss()(pred[1:, 1:2], gt[1:, 1:2])),
+           "loss_focal_025_2": np_(FocalLoss(0.25, 2)(pred, (gt == 1).float()))}
+    np.savez_compressed(os.path.join(HERE, "focal_default.npz"), **out)
+
+
 def golden_iou3d():
     """Rotated-BEV IoU matrices computed by the REFERENCE BINARY's own CPU routine boxes_iou_bev_cpu (executed through
     oracle/refshim): pins oracle/nms_ref.c and, through it, the CUDA kernels."""
@@ -306,6 +323,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "iou3d":
         golden_iou3d()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "focal":
+        golden_focal_default()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "proposals":
         golden_proposals()
         sys.exit(0)
@@ -314,6 +334,7 @@ if __name__ == "__main__":
     golden_dense_blocks()
     golden_proposals()
     golden_iou3d()
+    golden_focal_default()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -164,3 +164,20 @@ def test_lss_geometry_matches_reference():
     assert np.allclose(og.numpy(), g["geom"], rtol=1e-5, atol=1e-4)
     oi = OC.voxel_indices(og, torch.from_numpy(g["voxel_coord"]), torch.from_numpy(g["voxel_size"]))
     assert (oi.numpy() != g["idx"]).mean() < 1e-4
+
+
+def test_default_centernet_focal_loss_matches_reference():
+    """CenterHead.build_losses() installs CenterNetFocalLoss (reference layers/losses/det3d.py:325-360): Gaussian
+    targets, no alpha, (1 - gt)^4 negative weights -- a different function from FocalLoss(0.25, 2)."""
+    from unidistill.layers.losses.det3d import CenterNetFocalLoss, FocalLoss
+
+    g = _load("focal_default.npz")
+    pred, gt = torch.from_numpy(g["pred"]), torch.from_numpy(g["gt"])
+    crit = CenterNetFocalLoss()
+    assert abs(float(crit(pred, gt)) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert abs(float(crit(pred[1:, 1:2], gt[1:, 1:2])) - float(g["loss_nopos"])) <= 1e-6 * abs(float(g["loss_nopos"]))
+    # pre-reduced normaliser path gives the same value
+    assert abs(float(crit(pred, gt, torch.tensor(2.0))) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    f = FocalLoss(0.25, 2)(pred, (gt == 1).float())
+    assert abs(float(f) - float(g["loss_focal_025_2"])) <= 1e-6 * abs(float(g["loss_focal_025_2"]))
+    assert abs(float(f) - float(g["loss"])) > 1e-3            # the two criteria are not interchangeable

@@ -73,6 +73,50 @@ def test_kernel_equals_tensor_program(cuda, native_lib, seed, B, M, max_objs):
     assert sum(int(a["mask"][t].sum()) for t in range(6)) > 0
 
 
+@pytest.mark.parametrize("grid,voxel", [([1024, 1024, 40], [0.1, 0.1]), ([1440, 1440, 40], [0.075, 0.075])])
+def test_centres_far_outside_the_map(cuda, native_lib, grid, voxel):
+    """GT centres 8-12 (and up to 40) feature-map cells outside the map, along edges and off all four corners: the
+    17x17 candidate window (FA_RADIUS = 8) must reproduce the full-grid top-9 of the tensor program (SURVEY quirk 13:
+    the reference's range filter keeps boxes whose centre lies outside as long as a corner is inside)."""
+    rng = np.random.default_rng(13)
+    cell = voxel[0] * 8
+    half = 51.2 if grid[0] == 1024 else 54.0
+    B, M = 4, 48
+    gt = np.zeros((B, M, 10), np.float32)
+    for b in range(B):
+        n = 40
+        out = rng.uniform(8, 12 if b < 3 else 40, (n, 2)) * cell            # distance outside, per axis
+        side = rng.integers(0, 3, (n, 2))                                   # 0: low side, 1: inside, 2: high side
+        inside = rng.uniform(-half, half, (n, 2))
+        xy = np.where(side == 0, -half - out, np.where(side == 2, half + out, inside))
+        if grid[0] != 1024:
+            xy = xy + (half - 51.2)                                         # _assigner's map starts at -51.2: centre +2.8
+        gt[b, :n, 0:2] = xy
+        gt[b, :n, 2] = rng.normal(-1, 0.5, n)
+        gt[b, :n, 3:6] = rng.uniform(0.3, 12, (n, 3))
+        gt[b, :n, 6] = rng.uniform(-3.2, 3.2, n)
+        gt[b, :n, 9] = rng.integers(1, 11, n)
+        gt[b, n:, 9] = 1
+    a, b_ = _both(_assigner(grid, voxel, 2500), torch.from_numpy(gt).to(cuda))
+    _assert_same(a, b_)
+    for t in range(6):
+        assert torch.equal(a["n_pos"][t].long(), a["mask"][t].sum(1)), "un-truncated count, task %d" % t
+
+
+def test_overflow_is_reported_not_silent(cuda, native_lib):
+    """More positives than max_objs: outputs are truncated like the tensor program, and the un-truncated count is
+    returned (the reference asserts in padding_to_maxobjs)."""
+    rng = np.random.default_rng(5)
+    gt = np.zeros((1, 30, 10), np.float32)
+    gt[0, :, 0:2] = rng.uniform(-45, 45, (30, 2))
+    gt[0, :, 3:6] = 2.0
+    gt[0, :, 9] = 1                                                          # all cars -> ~270 positives in task 0
+    a, b_ = _both(_assigner([1024, 1024, 40], [0.1, 0.1], 60), torch.from_numpy(gt).to(cuda))
+    _assert_same(a, b_)
+    assert int(a["n_pos"][0][0]) > 60 and int(a["mask"][0].sum()) == 60
+    assert int(a["n_pos"][0][0]) == int(b_["n_pos"][0][0]) == int(a["heatmap"][0].eq(1).sum())
+
+
 def test_kernel_matches_reference_golden(cuda, native_lib):
     """The fixture was produced by the reference's own FCOSAssigner (tests/golden/make_golden.py)."""
     g = np.load(GOLDEN)
