@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(256)
 k_response(const float* __restrict__ cls_s, const float* __restrict__ cls_t, const float* __restrict__ reg_s,
            const float* __restrict__ reg_t, int n_cls, int n_reg, int H, int W, const float* __restrict__ boxes,
            int M, int stride, const int* __restrict__ n_rows, float x0, float y0, float cell_x, float cell_y,
-           float clamp_lo, float* __restrict__ partial, float* __restrict__ mask_out, float g_cls, float g_reg,
-           float* __restrict__ d_cls, float* __restrict__ d_reg) {
+           float clamp_lo, float* __restrict__ partial, float* __restrict__ mask_out,
+           const float* __restrict__ upstream, float* __restrict__ d_cls, float* __restrict__ d_reg) {
     extern __shared__ __align__(16) unsigned char raw[];
     GaussBox* gb = reinterpret_cast<GaussBox*>(raw);
     __shared__ float red[8];
@@ -392,6 +392,7 @@ k_response(const float* __restrict__ cls_s, const float* __restrict__ cls_t, con
             dreg = acc / (float)n_reg * m;
             if (mask_out) mask_out[(size_t)b * plane + pix] = m;
         } else {
+            const float g_cls = __ldg(upstream), g_reg = __ldg(upstream + 1);
             float* dc = d_cls + (size_t)b * n_cls * plane + pix;
             float d = ms - mt;
             float g = (d > 0.f ? g_cls : (d < 0.f ? -g_cls : 0.f)) * m;
@@ -491,25 +492,26 @@ int ud_response_distill_forward(const float* cls_s, const float* cls_t, const fl
     size_t smem = (size_t)M * sizeof(GaussBox);
     k_response<0><<<B * bps, 256, smem, stream>>>(cls_s, cls_t, reg_s, reg_t, n_cls, n_reg, H, W, boxes, M, stride,
                                                   n_rows, x_min, y_min, cell_x, cell_y, clamp_lo, partial, mask_out,
-                                                  0.f, 0.f, nullptr, nullptr);
+                                                  nullptr, nullptr, nullptr);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
 
-// d_cls (B,n_cls,H,W), d_reg (B,n_reg,H,W) fully written; g_cls / g_reg = dL/d(sum_cls), dL/d(sum_reg)
+// d_cls (B,n_cls,H,W), d_reg (B,n_reg,H,W) fully written; upstream: DEVICE pointer to [dL/d(sum_cls), dL/d(sum_reg)]
+// (the gradient of the (3,) forward result: no host read of the two scalars in the middle of a backward pass)
 int ud_response_distill_backward(const float* cls_s, const float* cls_t, const float* reg_s, const float* reg_t,
                                  int B, int n_cls, int n_reg, int H, int W, const float* boxes, int M, int stride,
                                  const int* n_rows, float x_min, float y_min, float cell_x, float cell_y,
-                                 float clamp_lo, float g_cls, float g_reg, float* d_cls, float* d_reg,
+                                 float clamp_lo, const float* upstream, float* d_cls, float* d_reg,
                                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!cls_s || !cls_t || !reg_s || !reg_t || !boxes || !n_rows || !d_cls || !d_reg || B < 1 || M < 1 || stride < 5)
+    if (!cls_s || !cls_t || !reg_s || !reg_t || !boxes || !n_rows || !upstream || !d_cls || !d_reg || B < 1 || M < 1 || stride < 5)
         return UD_ERR_INVALID_ARG;
     int bps = (H * W + 255) / 256;
     size_t smem = (size_t)M * sizeof(GaussBox);
     k_response<1><<<B * bps, 256, smem, stream>>>(cls_s, cls_t, reg_s, reg_t, n_cls, n_reg, H, W, boxes, M, stride,
                                                   n_rows, x_min, y_min, cell_x, cell_y, clamp_lo, nullptr, nullptr,
-                                                  g_cls, g_reg, d_cls, d_reg);
+                                                  upstream, d_cls, d_reg);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }

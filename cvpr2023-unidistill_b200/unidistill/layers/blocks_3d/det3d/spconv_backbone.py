@@ -109,10 +109,12 @@ class VoxelResBackBone8x(nn.Module):
         )
         self.num_point_features = 128
 
-    def forward(self, voxel_features, voxel_coords, batch_size):
-        """voxel_features (M,C), voxel_coords (M,4) [b,z,y,x] -> (SparseConvTensor, 8, {x_conv1..4})"""
+    def forward(self, voxel_features, voxel_coords, batch_size, indice_dict=None):
+        """voxel_features (M,C), voxel_coords (M,4) [b,z,y,x] -> (SparseConvTensor, 8, {x_conv1..4}).
+        `indice_dict` (extension, default = the reference's behaviour): rulebook cache to start from / fill -- a second
+        encoder run over the SAME voxel_coords tensor reuses the tables instead of rebuilding them."""
         x = spconv.SparseConvTensor(features=voxel_features, indices=voxel_coords.int(),
-                                    spatial_shape=self.sparse_shape, batch_size=batch_size)
+                                    spatial_shape=self.sparse_shape, batch_size=batch_size, indice_dict=indice_dict)
         x = self.conv_input(x)
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)

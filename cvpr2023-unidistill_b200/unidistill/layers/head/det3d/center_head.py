@@ -111,14 +111,16 @@ class CenterHead(nn.Module):
     def assign_targets(self, gt_boxes):
         return self.target_assigner.assign_targets(gt_boxes)
 
-    def forward(self, spatial_features_2d, gt_boxes=None):
+    def forward(self, spatial_features_2d, gt_boxes=None, targets=None):
+        """`targets`: optional result of `assign_targets(gt_boxes)` computed by the caller (the assignment depends on
+        the ground truth only; a distillation step shares one between student and teacher) -- same dict either way."""
         ret = {}
         x = self.shared_conv(spatial_features_2d)
         if self.upsample_for_pedestrian:
             x = self.upsample_conv(x)
         ret["multi_head_features"] = [task(x) for task in self.tasks]
         if self.training or self.distill:
-            ret.update(self.assign_targets(gt_boxes))
+            ret.update(targets if targets is not None else self.assign_targets(gt_boxes))
             return ret
         return self.proposal_layer.generate_predicted_boxes(ret, {})
 

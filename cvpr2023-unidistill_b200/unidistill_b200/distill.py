@@ -110,13 +110,13 @@ class ResponseDistill(Function):
         n_reg = int(rs.shape[1])
         M, S = int(gt.shape[1]), int(gt.shape[2])
         x0, y0, cell_x, cell_y, clamp_lo = ctx.geom
-        g = grad.detach().float().cpu()      # two scalars; the only host read of the distill backward
+        g = grad.detach().float().contiguous()      # (3,) on the device: [dL/dsum_cls, dL/dsum_reg, dL/dsum_mask]
         d_cls = torch.empty_like(cs)
         d_reg = torch.empty_like(rs)
         rc = lib.ud_response_distill_backward(native.ptr(cs), native.ptr(ct), native.ptr(rs), native.ptr(rt), B,
                                               n_cls, n_reg, H, W, native.ptr(gt), M, S, native.ptr(n_rows),
                                               float(x0), float(y0), float(cell_x), float(cell_y), float(clamp_lo),
-                                              float(g[0]), float(g[1]), native.ptr(d_cls), native.ptr(d_reg),
+                                              native.ptr(g), native.ptr(d_cls), native.ptr(d_reg),
                                               native.stream_ptr(cs.device))
         native.check(rc, "ud_response_distill_backward")
         return d_cls, None, d_reg, None, None, None, None

@@ -127,15 +127,36 @@ class LidarEncoder(BaseEncoder):
                                       max_num_points=cfg.max_num_points, max_voxels=tuple(cfg.max_voxels)
                                       if isinstance(cfg.max_voxels, (list, tuple)) else cfg.max_voxels,
                                       num_point_features=cfg.src_num_point_features, device=torch.device("cuda"))
+        self.voxelizer.materialize_voxels = False      # MeanVFE below takes the mean fused into the voxelize kernel
         self.vfe = MeanVFE(num_point_features=cfg.use_num_point_features)
         self.backbone_3d = VoxelResBackBone8x(input_channels=self.vfe.get_output_feature_dim(),
                                               grid_size=np.array(cfg.grid_size), last_pad=0)
         self.map_to_bev = HeightCompression(num_bev_features=cfg.map_to_bev_num_features)
 
-    def forward(self, lidar_points):
-        voxels, coords, num = self.voxelizer(lidar_points)
-        feats = self.vfe(voxels, num)
-        sp, stride, _ = self.backbone_3d(feats, coords, len(lidar_points))
+    def _geometry_key(self):
+        v = self.voxelizer
+        return (tuple(v.voxel_size.tolist()), tuple(v.point_cloud_range.tolist()), v.max_num_points, v.max_voxels,
+                tuple(int(s) for s in self.backbone_3d.sparse_shape))
+
+    def forward(self, lidar_points, geometry=None):
+        """`geometry`: optional dict shared between the LiDAR encoders of ONE step that see the same clouds with the
+        same voxel grid (student and teacher of a distillation step): voxelization and the rulebooks depend on the
+        points only, so the second encoder reuses the first one's (deterministic kernels => identical tables)."""
+        hit = None
+        if geometry is not None:
+            hit = geometry.get("lidar")
+            if hit is not None and (hit["key"] != self._geometry_key() or hit["points"] is not lidar_points):
+                hit = None
+        if hit is None:
+            voxels, coords, num = self.voxelizer(lidar_points)
+            feats = self.vfe(voxels, num)
+            indice_dict = {}
+            if geometry is not None:
+                geometry["lidar"] = dict(key=self._geometry_key(), points=lidar_points, feats=feats, coords=coords,
+                                         indice_dict=indice_dict)
+        else:
+            feats, coords, indice_dict = hit["feats"], hit["coords"], hit["indice_dict"]
+        sp, stride, _ = self.backbone_3d(feats, coords, len(lidar_points), indice_dict=indice_dict)
         bev, _ = self.map_to_bev(sp, stride)
         return bev
 
@@ -216,7 +237,9 @@ class DetHead(nn.Module):
         self.dense_head.add_module("crit_reg", CenterNetRegLoss())
         self.dense_head.add_module("crit_iou_aware", CenterNetRegLoss())
 
-    def forward(self, x, gt_boxes):
+    def forward(self, x, gt_boxes, targets=None):
+        if targets is not None:
+            return self.dense_head(x, gt_boxes, targets=targets)      # caller-assigned targets: infs already zeroed
         ret = self.dense_head(x, gt_boxes)
         if self.training:
             for _, enc in ret["box_encoding"].items():
@@ -319,10 +342,10 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self._channels_last = bool(enable)
         return self
 
-    def extract_bev(self, lidar_points, cameras_imgs, metas):
+    def extract_bev(self, lidar_points, cameras_imgs, metas, geometry=None):
         out = None
         if self.with_lidar_encoder:
-            lidar_out = self.lidar_encoder(lidar_points)
+            lidar_out = self.lidar_encoder(lidar_points, geometry=geometry)
             out = lidar_out
         if self.with_camera_encoder:
             camera_out = self.camera_encoder(cameras_imgs, metas)
@@ -332,27 +355,32 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         return out
 
     def forward(self, lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False, normalisers=None,
-                **kwargs):
+                targets=None, geometry=None, **kwargs):
         """`normalisers`: optional callable(ret_dict) run between target assignment and get_loss; it may put
         pre-reduced `num_pos_reduced` / `num_hm_reduced` tensors into ret_dict (one fused all-reduce per step
-        instead of the reference's per-loss scalar reduce_mean calls; unidistill_b200.step uses it)."""
-        model_output = self.extract_bev(lidar_points, cameras_imgs, metas)
+        instead of the reference's per-loss scalar reduce_mean calls; unidistill_b200.step uses it).
+        `geometry`: optional per-step dict through which LiDAR encoders fed the same clouds share voxels + rulebooks.
+        `targets`: optional pre-computed `assign_targets(gt_boxes)` dict (infs zeroed), shared by student and teacher."""
+        model_output = self.extract_bev(lidar_points, cameras_imgs, metas, geometry=geometry)
         if self._channels_last:
             model_output = model_output.contiguous(memory_format=torch.channels_last)
         if self._dense_graph is not None and not torch.is_grad_enabled() and model_output.is_cuda:
-            feats, pyramid, ret = self._dense_graph(model_output, gt_boxes)
+            feats, pyramid, ret = self._dense_graph(model_output, None if targets is not None else gt_boxes)
             x = (feats, pyramid)
             head = self.det_head.dense_head
+            if targets is not None:
+                ret = dict(ret, **targets)
             if not (head.training or head.distill):
                 ret = head.proposal_layer.generate_predicted_boxes(ret, {})
         else:
             x = self.bev_encoder(model_output)
-            ret = self.det_head(x[0], gt_boxes)
+            ret = self.det_head(x[0], gt_boxes, targets=targets)
         if return_feature:
             return model_output, x[0], ret["multi_head_features"]
         if self.training:
-            for _, enc in ret["box_encoding"].items():
-                enc.masked_fill_(torch.isinf(enc), 0)
+            if targets is None:
+                for _, enc in ret["box_encoding"].items():
+                    enc.masked_fill_(torch.isinf(enc), 0)
             if normalisers is not None:
                 normalisers(ret)
             loss_rpn, tb_dict = self.det_head.dense_head.get_loss(ret)

@@ -73,13 +73,34 @@ def load():
                 "unidistill_b200: %s is missing -- run `python cvpr2023-unidistill_b200/build.py` "
                 "(or __graft_entry__.build()); there is no fallback path" % LIB_PATH
             )
-        lib = ctypes.CDLL(LIB_PATH)
+        cdll = ctypes.CDLL(LIB_PATH)
+        lib = _Lib(cdll)
         for name, (ret, spec) in parse_header().items():
-            fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+            fn = getattr(cdll, name)  # AttributeError here == header/library mismatch
             fn.argtypes = [_CT[c] for c in spec]
             fn.restype = ctypes.c_char_p if ret == "s" else _I
+            launches = spec.endswith("p") and not name.endswith(("_bytes", "_sizes", "_supported")) \
+                and name not in ("ud_debug_umma_prof",)
+            setattr(lib, name, _timed(name, fn) if launches else fn)
         _lib = lib
     return _lib
+
+
+class _Lib:
+    """Attribute bag of the bound entry points (kernel-launching ones pass through the KernelTimer hook)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+
+def _timed(name, fn):
+    def call(*args):
+        if not TIMER.enabled:
+            return fn(*args)
+        return TIMER.call(name, fn, args)
+
+    call.__name__ = name
+    return call
 
 
 def check(rc, what):
@@ -145,13 +166,14 @@ def launch_count(reset=False):
 
 
 class KernelTimer:
-    """CUDA-event timing of single C-ABI calls on the stream they are launched on (bench.py's roofline
+    """CUDA-event timing of every kernel-launching C-ABI call on the stream it is launched on (bench.py's roofline
     numbers are taken live, inside the timed region, through this hook).  Disabled by default."""
 
     def __init__(self):
         self.enabled = False
         self.records = []
         self._pool = []
+        self.meta = None            # optional dict a call site attaches to the NEXT timed call (tensors for lazy counts)
 
     def prepare(self, n_pairs):
         """Creates (and materialises, by recording once) n_pairs event pairs ahead of the timed region:
@@ -165,9 +187,8 @@ class KernelTimer:
             self._pool.append((e0, e1))
         torch.cuda.synchronize()
 
-    def call(self, key, meta, fn, *args):
-        if not self.enabled:
-            return fn(*args)
+    def call(self, key, fn, args):
+        meta, self.meta = self.meta, None
         if self._pool:
             e0, e1 = self._pool.pop()
         else:
@@ -176,13 +197,14 @@ class KernelTimer:
         e0.record()
         rc = fn(*args)
         e1.record()
-        self.records.append((key, meta, e0, e1))
+        ints = tuple(a if isinstance(a, (int, float)) else None for a in args)
+        self.records.append((key, meta, ints, e0, e1))
         return rc
 
     def drain(self):
-        """-> [(key, meta, milliseconds)], after a device synchronize."""
+        """-> [(entry point, meta, scalar args (pointers -> None), milliseconds)], after a device synchronize."""
         torch.cuda.synchronize()
-        out = [(k, m, e0.elapsed_time(e1)) for k, m, e0, e1 in self.records]
+        out = [(k, m, a, e0.elapsed_time(e1)) for k, m, a, e0, e1 in self.records]
         self.records = []
         return out
 

@@ -103,6 +103,8 @@ def build_subm_rulebook(coords, batch_size, spatial_shape, ksize, dilation=1):
     nbytes = native.query_bytes("ud_rulebook_subm_workspace_bytes", n)
     ws = native.WORKSPACE.get(nbytes, dev)
     shp, ks, dl = native.host_ints(spatial_shape), native.host_ints(ksize), native.host_ints(dilation)
+    if native.TIMER.enabled:
+        native.TIMER.meta = {"K": K}
     rc = lib.ud_rulebook_subm(native.ptr(coords), n, int(batch_size), native.host_ptr(shp), native.host_ptr(ks),
                               native.host_ptr(dl), native.ptr(nbr), native.ptr(ws), ws.numel(),
                               native.stream_ptr(dev))
@@ -127,6 +129,8 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
     ws = native.WORKSPACE.get(nbytes, dev, slot=_WS_RULEBOOK)
     n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
     sp = native.stream_ptr(dev)
+    if native.TIMER.enabled:
+        native.TIMER.meta = {"K": K}
     rc = lib.ud_rulebook_conv_count(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
                                     native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
                                     native.host_ptr(pd), native.host_ptr(dl), native.ptr(n_out_dev),
@@ -136,6 +140,8 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
     out_coords = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((n_in, K), dtype=torch.int32, device=dev)
     nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
+    if native.TIMER.enabled:
+        native.TIMER.meta = {"K": K}
     rc = lib.ud_rulebook_conv_fill(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
                                    native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
                                    native.host_ptr(pd), native.host_ptr(dl), n_out, native.ptr(out_coords),
@@ -200,9 +206,10 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
         sums = None
         if want_stats and FUSE_BN_STATS and TC_VARIANT != 1:
             sums = torch.zeros((2, cout), dtype=torch.float64, device=dev)
-        rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_tc_forward, native.ptr(feats),
-                               native.ptr(packed), native.ptr(bias), native.ptr(table_t), native.ptr(masks), n_out, K,
-                               cin, cout, native.ptr(out), native.ptr(sums), TC_VARIANT, sp)
+        native.TIMER.meta = meta
+        rc = lib.ud_sparse_conv_tc_forward(native.ptr(feats), native.ptr(packed), native.ptr(bias), native.ptr(table_t),
+                                           native.ptr(masks), n_out, K, cin, cout, native.ptr(out), native.ptr(sums),
+                                           TC_VARIANT, sp)
         native.check(rc, "ud_sparse_conv_tc_forward")
         if sums is not None:
             out._ud_bn_sums = sums
@@ -211,9 +218,9 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
         meta["kernel"] = "k_spconv_gather_gemm"
     if callable(w_k):
         w_k = w_k()
-    rc = native.TIMER.call("sparse_conv_forward", meta, lib.ud_sparse_conv_forward, native.ptr(feats),
-                           native.ptr(w_k), native.ptr(bias), native.ptr(table),
-                           n_out, K, cin, cout, native.ptr(out), sp)
+    native.TIMER.meta = meta
+    rc = lib.ud_sparse_conv_forward(native.ptr(feats), native.ptr(w_k), native.ptr(bias), native.ptr(table),
+                                    n_out, K, cin, cout, native.ptr(out), sp)
     native.check(rc, "ud_sparse_conv_forward")
     return out
 
@@ -282,10 +289,14 @@ class SparseConvFunction(Function):
             sp = native.stream_ptr(grad_out.device)
             if USE_TENSOR_CORES and USE_TC_WGRAD and n_rows > 0 and lib.ud_sparse_conv_tc_wgrad_supported(K, cin, cout):
                 table_t, masks = rb.tap_major(table)           # cached by the forward pass (same table)
+                if native.TIMER.enabled:
+                    native.TIMER.meta = {"n_in": int(features.shape[0]), "table": table}
                 rc = lib.ud_sparse_conv_tc_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table_t),
                                                  native.ptr(masks), n_rows, K, cin, cout, native.ptr(dw), sp)
                 native.check(rc, "ud_sparse_conv_tc_wgrad")
             else:
+                if native.TIMER.enabled:
+                    native.TIMER.meta = {"n_in": int(features.shape[0]), "table": table}
                 rc = lib.ud_sparse_conv_wgrad(native.ptr(features), native.ptr(grad_out), native.ptr(table),
                                               n_rows, K, cin, cout, native.ptr(dw), sp)
                 native.check(rc, "ud_sparse_conv_wgrad")

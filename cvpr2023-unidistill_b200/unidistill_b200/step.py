@@ -2,18 +2,22 @@
 
 Restates `Exp.training_step` of the reference's distill scripts
 (exps/multisensor_fusion/nuscenes/BEVFusion/BEVFusion_nuscenes_centerhead_camera_exp_distill_lidar.py:438-513 and
-its three siblings) plus the optimiser/all-reduce work pytorch-lightning's DDP does around it:
+its three siblings) plus what pytorch-lightning's DDP trainer does around it (exps/base_cli.py:43-44,
+BEVFusion_nuscenes_base_exp.py:436-441):
 
+    target assignment (GT only; ONE for student and teacher)  -> one fused, asynchronous normaliser all-reduce
     student forward (train) -> detection loss                        (:463-465)
-    teacher forward (frozen, `distill=True` so it still assigns targets, return_feature=True)   (:466-469)
+    teacher forward (frozen, `distill=True`, return_feature=True)    (:466-469)
     GT boxes -> BEV corners in cell units, valid-box prefix          (:447-455, :470-483)
-    loss = det + 100 * feature + 40 * relation + 10 * (resp_cls + resp_reg)                       (:484-510)
-    backward, ONE gradient all-reduce over NCCL (flat bucket), AdamW
+    loss = det + w_f * feature + w_r * relation + w_p * (resp_cls + resp_reg)                     (:484-510)
+    backward with the gradient all-reduce overlapped bucket by bucket (NCCL over NVLink, DDP's job in the reference)
+    gradient-norm clip 0.1 (base_cli.py:43, `gradient_clip_val`), AdamW(weight_decay=1e-7), MultiStepLR([10, 15])
 
 What changes operationally (same numbers): no `.cpu()` / numpy hop for the corners, no Python loops over the batch,
 all GT-only normalisers (6 x num_pos, 6 x num_hm, #valid boxes, Gaussian-mask sum) travel in ONE 14-float all-reduce
-instead of ~27 scalar `reduce_mean`s, and the teacher's buffers are restored from a device-side snapshot instead
-of `load_state_dict` from host memory every step (:465).
+issued BEFORE the student forward (they depend on the ground truth only) instead of ~27 blocking scalar
+`reduce_mean`s inside it, and the teacher's buffers are restored from a device-side snapshot instead of
+`load_state_dict` from host memory every step (:465).
 """
 import torch
 import torch.distributed as dist
@@ -24,34 +28,112 @@ from unidistill.utils import torch_dist
 
 from . import distill as D
 
-DISTILL_WEIGHTS = (100.0, 40.0, 10.0)      # feature, relation, response (:505-509)
+# (feature, relation, response) loss weights, clamp of the teacher's heat-map sigmoid and learning rate of the reference's
+# four distillation experiments (same directory, `training_step` / `__init__` of each script)
+PRESETS = {
+    "camera_exp_distill_lidar": dict(weights=(100.0, 40.0, 10.0), clamp_min=1e-4, lr=2e-4),
+    "camera_exp_distill_fusion": dict(weights=(10.0, 5.0, 10.0), clamp_min=1e-3, lr=2e-4),
+    "lidar_exp_distill_camera": dict(weights=(10.0, 5.0, 1.0), clamp_min=1e-4, lr=1e-3),
+    "lidar_exp_distill_fusion": dict(weights=(10.0, 1.0, 10.0), clamp_min=1e-4, lr=1e-3),
+}
+DISTILL_WEIGHTS = PRESETS["camera_exp_distill_lidar"]["weights"]      # kept for callers of round 1
 
 
 class FlatGradBucket:
-    """All student gradients live in one flat fp32 buffer (param.grad are views), so the data-parallel exchange is a
-    single all-reduce over NVLink.  Works with any backend (gloo in the CPU tests)."""
+    """All student gradients live in one flat fp32 buffer (param.grad are views), cut into contiguous buckets in
+    REVERSE registration order -- the order backward produces them.  With `overlap`, a bucket's all-reduce is issued
+    (asynchronously, on the process group's own stream) from a post-accumulate hook as soon as its last gradient has
+    landed, so the exchange runs under the rest of the backward pass; `finish()` waits for the stragglers.  Works with
+    any backend (gloo in the CPU tests)."""
 
-    def __init__(self, params):
+    def __init__(self, params, bucket_bytes=16 << 20, overlap=True):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.numel = n
+        self.overlap = overlap
+        self.buckets = []            # (lo, hi) element ranges of self.flat, in expected completion order
+        self._bucket_of = {}
+        self._pending = []
+        self._works = []
+        self._hooks = []
+        self.enabled = True
+        # lay the parameters out back to front so that bucket 0 (completed first) holds the LAST layers
         off = 0
-        for p in self.params:
+        lo, cnt = 0, 0
+        for p in reversed(self.params):
             # same strides as the parameter (NHWC-format conv weights stay NHWC): dense, so the segment is exact
             p.grad = self.flat[off: off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
-        self.numel = n
+            self._bucket_of[id(p)] = len(self.buckets)
+            cnt += 1
+            if (off - lo) * 4 >= bucket_bytes:
+                self.buckets.append((lo, off, cnt))
+                lo, cnt = off, 0
+        if off > lo or not self.buckets:
+            self.buckets.append((lo, off, cnt))
+        if overlap:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._reset()
+
+    def _reset(self):
+        self._pending = [c for _, _, c in self.buckets]
+        self._works = []
+        self._fired = [False] * len(self.buckets)
 
     def zero(self):
         self.flat.zero_()
+        self._reset()
+
+    def _fire(self, b):
+        if self._fired[b]:
+            return
+        self._fired[b] = True
+        lo, hi, _ = self.buckets[b]
+        if torch_dist.get_world_size() > 1 and hi > lo:
+            self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _on_grad(self, p):
+        if not self.enabled:
+            return
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._fire(b)
+
+    def finish(self):
+        """Issues the all-reduce of every bucket that has not fired (parameters without a gradient this step, or
+        overlap off), waits for all of them and returns the flat buffer holding the SUM over ranks."""
+        for b in range(len(self.buckets)):
+            self._fire(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        return self.flat
 
     def all_reduce_mean(self):
         world = torch_dist.get_world_size()
+        self.finish()
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.mul_(1.0 / world)
         return self.flat
+
+
+def clip_and_average_(flat, world, max_norm):
+    """flat holds the gradient SUM over `world` ranks.  In place: average, then scale so that the global L2 norm is at
+    most `max_norm` (torch.nn.utils.clip_grad_norm_ semantics, coefficient max_norm / (norm + 1e-6) clamped to 1; what
+    pytorch-lightning's gradient_clip_val does after DDP's averaging).  One reduction + one scaling pass over the
+    bucket, no host synchronisation.  Returns the (pre-clip) norm as a 0-dim tensor."""
+    norm = torch.linalg.vector_norm(flat) / float(world)
+    if max_norm is None:
+        if world > 1:
+            flat.mul_(1.0 / world)
+        return norm
+    coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0) / float(world)
+    flat.mul_(coef)
+    return norm
 
 
 def fold_frozen_batchnorm(module):
@@ -95,52 +177,94 @@ def gt_with_labels(gt_boxes, gt_labels):
     return torch.cat([gt_boxes, (gt_labels.to(gt_boxes.dtype) + 1).unsqueeze(2)], dim=2)
 
 
+class AsyncNormalisers:
+    """mean over ranks of [num_pos (T), num_hm (T), #valid boxes, Gaussian-mask sum] in ONE all-reduce that is in flight
+    while the student forward runs; `get()` (first consumer: get_loss, after the whole forward) waits for it."""
+
+    def __init__(self, targets, valid, mask_sum):
+        tasks = sorted(targets["mask"].keys()) if isinstance(targets["mask"], dict) else list(range(len(targets["mask"])))
+        parts = [targets["mask"][t].float().sum() for t in tasks]
+        parts += [targets["heatmap"][t].eq(1).float().sum() for t in tasks]
+        parts += [valid.float().sum(), mask_sum]
+        self.T = len(tasks)
+        self.vec = torch.stack([p.reshape(()) for p in parts])
+        self.world = torch_dist.get_world_size()
+        self.work = dist.all_reduce(self.vec, op=dist.ReduceOp.SUM, async_op=True) if self.world > 1 else None
+
+    def get(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+            self.vec = self.vec / float(self.world)
+        T, v = self.T, self.vec
+        return v[:T], v[T: 2 * T], v[2 * T], v[2 * T + 1]
+
+
 def fused_normalisers(ret, valid, mask_sum):
-    """-> mean over ranks of [num_pos (T), num_hm (T), #valid boxes, Gaussian-mask sum] in one all-reduce."""
-    tasks = sorted(ret["mask"].keys()) if isinstance(ret["mask"], dict) else list(range(len(ret["mask"])))
-    parts = [ret["mask"][t].float().sum() for t in tasks]
-    parts += [ret["heatmap"][t].eq(1).float().sum() for t in tasks]
-    parts += [valid.float().sum(), mask_sum]
-    vec = torch.stack([p.reshape(()) for p in parts])
-    vec = torch_dist.reduce_mean(vec)
-    T = len(tasks)
-    return vec[:T], vec[T: 2 * T], vec[2 * T], vec[2 * T + 1]
+    """Blocking form (kept for callers of round 1): -> (num_pos (T), num_hm (T), n_valid, mask_sum), rank-averaged."""
+    return AsyncNormalisers(ret, valid, mask_sum).get()
 
 
 class DistillStep:
     """student / teacher: BEVFusionCenterHead models on the same device.  `geometry`: dict(pc_range, voxel_size,
     out_size_factor).  Call with a device-resident batch dict (points list | None, imgs | None, mats_dict | None,
-    gt_boxes (B,M,9), gt_labels (B,M)); returns a dict of detached loss terms."""
+    gt_boxes (B,M,9), gt_labels (B,M)); returns a dict of detached loss terms.
 
-    def __init__(self, student, teacher, geometry, lr=2e-4, weight_decay=1e-2, clamp_min=1e-4, optimizer=True,
-                 fold_teacher_bn=True, teacher_cuda_graph=True):
+    preset: one of PRESETS (weights / clamp_min / lr of the reference's four experiments); explicit arguments win.
+    teacher_mode: "eval" -- frozen teacher in eval mode (what freeze_model + .eval() at :419-433 ask for), BatchNorm2d
+    folded into its convolutions; "train" -- the teacher's BatchNorms use batch statistics, which is what happens in the
+    reference when pytorch-lightning puts the whole LightningModule into train mode before the step (the
+    reference reloads the teacher's state_dict every step to undo the running-statistics updates, :465): no folding,
+    buffers restored from a device-side snapshot after the forward."""
+
+    def __init__(self, student, teacher, geometry, lr=None, weight_decay=1e-7, clamp_min=None, optimizer=True,
+                 fold_teacher_bn=True, teacher_cuda_graph=True, weights=None, preset="camera_exp_distill_lidar",
+                 grad_clip=0.1, lr_milestones=(10, 15), lr_gamma=0.1, teacher_mode="eval", overlap_allreduce=True,
+                 bucket_bytes=16 << 20):
+        cfg = PRESETS[preset]
+        self.weights = tuple(float(w) for w in (weights if weights is not None else cfg["weights"]))
+        self.clamp_min = float(clamp_min if clamp_min is not None else cfg["clamp_min"])
+        lr = float(lr if lr is not None else cfg["lr"])
+        assert teacher_mode in ("eval", "train")
+        self.teacher_mode = teacher_mode
         self.student, self.teacher = student, teacher
         self.pc_range = list(geometry["pc_range"])
         self.voxel_size = list(geometry["voxel_size"])
         self.osf = int(geometry["out_size_factor"])
-        self.clamp_min = clamp_min
+        self.grad_clip = grad_clip
         self.keep_features = False          # tests: keep the student/teacher tensors of the last step in self.last
         self.last = None
+        self.grad_norm = None
         for p in teacher.parameters():                         # freeze_model (:427-433)
             p.requires_grad = False
-        teacher.eval()
         teacher.det_head.dense_head.distill = True             # (:419)
-        # the frozen eval-mode teacher: BatchNorm folded into the dense convolutions, dense trunk replayed from a CUDA graph
-        self.folded_bn = fold_frozen_batchnorm(teacher) if fold_teacher_bn else 0
+        self.folded_bn = 0
+        if teacher_mode == "eval":
+            teacher.eval()
+            # the frozen eval-mode teacher: BatchNorm folded into the dense convolutions
+            self.folded_bn = fold_frozen_batchnorm(teacher) if fold_teacher_bn else 0
+        else:
+            teacher.train()
         if teacher_cuda_graph and next(teacher.parameters()).is_cuda:
-            teacher.use_cuda_graph(True)
+            teacher.use_cuda_graph(True)                       # dense trunk replayed from a CUDA graph
         self._teacher_buffers = [(b, b.detach().clone()) for b in teacher.buffers()]
         student.train()
-        self.bucket = FlatGradBucket(student.parameters())
-        self.opt = None
+        self.bucket = FlatGradBucket(student.parameters(), bucket_bytes=bucket_bytes, overlap=overlap_allreduce)
+        self.opt = self.sched = None
         if optimizer:
             fused = self.bucket.flat.is_cuda
             self.opt = torch.optim.AdamW(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused)
+            self.sched = torch.optim.lr_scheduler.MultiStepLR(self.opt, list(lr_milestones), gamma=lr_gamma)
+
+    def epoch_end(self):
+        """MultiStepLR([10, 15]) steps once per epoch (pytorch-lightning's default scheduler interval)."""
+        if self.sched is not None:
+            self.sched.step()
 
     def _restore_teacher(self):
         """The reference reloads the teacher's state_dict every step (:465) because pytorch-lightning may have put it
         back into train mode; an eval-mode teacher cannot change its buffers, so there is nothing to restore."""
-        if not any(m.training for m in self.teacher.modules()):
+        if self.teacher_mode == "eval" and not any(m.training for m in self.teacher.modules()):
             return
         for b, snap in self._teacher_buffers:
             b.copy_(snap)
@@ -150,30 +274,39 @@ class DistillStep:
         gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
         valid = D.valid_box_prefix(batch["gt_boxes"])                               # (:447-455)
         corners = D.box_corners_bev(gt, self.pc_range, self.voxel_size, self.osf)   # (:470-483)
-        hw = None
+        # ---- everything that depends on the ground truth only: ONE target assignment (the reference runs the same
+        # assignment twice, in the student's and the teacher's head) and the normalisers' all-reduce, in flight from here
+        head = self.student.det_head.dense_head
+        with torch.no_grad():
+            targets = head.assign_targets(gt)
+            for _, enc in targets["box_encoding"].items():
+                enc.masked_fill_(torch.isinf(enc), 0)                               # log(0) of padded boxes (quirk 10)
+            h, w = targets["heatmap"][0].shape[-2:]
+            mask = D.response_mask(gt, (h, w), self.pc_range, self.voxel_size, self.osf)
+            pending = AsyncNormalisers(targets, valid, mask.sum())
         norm = {}
 
         def normalisers(ret):
-            h, w = ret["heatmap"][0].shape[-2:]
-            mask = D.response_mask(gt, (h, w), self.pc_range, self.voxel_size, self.osf)
-            num_pos, num_hm, n_valid, mask_sum = fused_normalisers(ret, valid, mask.sum())
+            num_pos, num_hm, n_valid, mask_sum = pending.get()
             ret["num_pos_reduced"], ret["num_hm_reduced"] = num_pos, num_hm
             norm["n_valid"], norm["mask_sum"] = n_valid, mask_sum
 
-        ret_dict, tb, feat_s, bev_s, resp_s, _ = self.student(points, imgs, metas, gt, normalisers=normalisers)
+        geometry = {}       # voxels + rulebooks of the step's clouds, shared by the two LiDAR encoders (if there are two)
+        ret_dict, tb, feat_s, bev_s, resp_s, _ = self.student(points, imgs, metas, gt, normalisers=normalisers,
+                                                              targets=targets, geometry=geometry)
         with torch.no_grad():
+            feat_t, bev_t, resp_t = self.teacher(points, imgs, metas, gt, return_feature=True, targets=targets,
+                                                 geometry=geometry)
             self._restore_teacher()
-            feat_t, bev_t, resp_t = self.teacher(points, imgs, metas, gt, return_feature=True)
         loss_feature = L.FeatureDistillLoss(feat_s, feat_t, corners, valid, weight=norm["n_valid"])
         loss_rel = L.BEVDistillLoss(bev_s, bev_t, corners, valid, weight=norm["n_valid"])
         loss_cls, loss_reg = L.ResponseDistillLoss(resp_s, resp_t, gt, self.pc_range, self.voxel_size, self.osf,
                                                    clamp_min=self.clamp_min, mask_weight=norm["mask_sum"])
-        wf, wr, wp = DISTILL_WEIGHTS
+        wf, wr, wp = self.weights
         loss = ret_dict["loss"].mean() + wf * loss_feature + wr * loss_rel + wp * (loss_cls + loss_reg)
         terms = {"loss": loss, "loss_det": ret_dict["loss"].detach(), "loss_feature": loss_feature.detach(),
                  "loss_bev_rel": loss_rel.detach(), "loss_resp_cls": loss_cls.detach(),
                  "loss_resp_reg": loss_reg.detach()}
-        del hw
         if self.keep_features:
             self.last = dict(feat_s=feat_s, bev_s=bev_s, resp_s=resp_s, feat_t=feat_t, bev_t=bev_t, resp_t=resp_t,
                              gt=gt, valid=valid, corners=corners, norm=dict(norm))
@@ -182,9 +315,11 @@ class DistillStep:
     def __call__(self, batch):
         self.bucket.zero()
         terms = self.losses(batch)
-        terms["loss"].backward()
-        self.bucket.all_reduce_mean()
+        terms["loss"].backward()                 # bucket all-reduces fire from the gradient hooks, under the backward
+        flat = self.bucket.finish()
+        self.grad_norm = clip_and_average_(flat, torch_dist.get_world_size(), self.grad_clip)
         if self.opt is not None:
             self.opt.step()
         terms["loss"] = terms["loss"].detach()
+        terms["grad_norm"] = self.grad_norm
         return terms

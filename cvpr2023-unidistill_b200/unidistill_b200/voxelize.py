@@ -44,6 +44,8 @@ def hard_voxelize(points, voxel_size, point_cloud_range, grid_size, max_num_poin
     vs = native.host_floats(voxel_size)
     pr = native.host_floats(point_cloud_range)
     gs = native.host_ints(grid_size)
+    if native.TIMER.enabled:
+        native.TIMER.meta = {"n_points": n_total, "counts": counts, "voxels": want_voxels}
     rc = lib.ud_hard_voxelize(
         native.ptr(flat), native.host_ptr(offs), batch_size, C, native.host_ptr(vs), native.host_ptr(pr),
         native.host_ptr(gs), int(max_num_points), int(max_voxels), cap, native.ptr(voxels),

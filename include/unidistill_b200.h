@@ -201,7 +201,8 @@ int ud_lift_splat_backward(int batch_size, int num_cams, int D, int H, int W, in
  * (identical in the three sibling scripts; camera_exp_distill_fusion uses clamp_lo = 1e-3).
  * Maps are (B,C,H,W) f32; corners (B,M,4,2) f32 in BEV cells; valid (B,M) u8.  Per-box / per-block partial
  * results are returned so the caller applies the (all-reduced) normalisers; backward entry points give
- * gradients w.r.t. the student tensors only.
+ * gradients w.r.t. the student tensors only; `upstream` of both backward entry points is a DEVICE pointer (per-box
+ * upstream gradients / [dL/dsum_cls, dL/dsum_reg]) so that a backward pass never reads scalars back to the host.
  * ------------------------------------------------------------------------------------------- */
 int ud_box_corners_bev(const float* boxes, int n, int stride, float x_min, float y_min, float cell_x,
                        float cell_y, float* corners, void* stream);
@@ -217,7 +218,7 @@ int ud_response_distill_forward(const float* cls_s, const float* cls_t, const fl
 int ud_response_distill_backward(const float* cls_s, const float* cls_t, const float* reg_s, const float* reg_t,
                                  int B, int n_cls, int n_reg, int H, int W, const float* boxes, int M, int stride,
                                  const int* n_rows, float x_min, float y_min, float cell_x, float cell_y,
-                                 float clamp_lo, float g_cls, float g_reg, float* d_cls, float* d_reg,
+                                 float clamp_lo, const float* upstream, float* d_cls, float* d_reg,
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------

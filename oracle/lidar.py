@@ -51,6 +51,7 @@ def voxelize_one(points, voxel_size, pc_range, grid_size, max_points, max_voxels
     """First-come hard voxelization of one cloud -> (voxels (M,P,C), coords (M,3) zyx, num (M,), mean (M,C))."""
     pts = _f32(points)
     n, C = pts.shape
+    max_voxels = max(1, min(int(max_voxels), n))     # n points cannot open more than n voxels: same result, less zeroing
     voxels = np.zeros((max_voxels, max_points, C), np.float32)
     coords = np.zeros((max_voxels, 3), np.int32)
     num = np.zeros((max_voxels,), np.int32)

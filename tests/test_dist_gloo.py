@@ -31,7 +31,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from unidistill.utils import torch_dist
-        from unidistill_b200.step import FlatGradBucket, fused_normalisers
+        from unidistill_b200.step import AsyncNormalisers, FlatGradBucket, clip_and_average_, fused_normalisers
 
         assert torch_dist.get_world_size() == world and torch_dist.get_rank() == rank
         # reduce_mean == sum / world, input untouched
@@ -55,6 +55,41 @@ def _worker(rank, world, port, out_dir):
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         assert torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-6)
+
+        # overlapped path: 3 buckets (tiny bucket size), all-reduces fired from the gradient hooks during backward,
+        # then average + global-norm clip in place == clip_grad_norm_ of the averaged gradients
+        torch.manual_seed(0)
+        net2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        b2 = FlatGradBucket(net2.parameters(), bucket_bytes=16, overlap=True)
+        assert len(b2.buckets) >= 3 and sum(hi - lo for lo, hi, _ in b2.buckets) == b2.numel
+        for _ in range(2):                                   # two steps: the per-step hook state resets
+            b2.zero()
+            net2(x).square().sum().backward()
+            assert all(b2._fired), "every bucket's all-reduce was issued from the hooks"
+            summed = b2.finish()
+            assert torch.allclose(summed, sum(gathered), atol=1e-5)
+        ref = (sum(gathered) / world).clone()
+        ref_norm = ref.norm()
+        norm = clip_and_average_(b2.flat, world, 0.1)
+        assert torch.allclose(norm, ref_norm, rtol=1e-5)
+        assert torch.allclose(b2.flat, ref * min(1.0, 0.1 / (float(ref_norm) + 1e-6)), atol=1e-6)
+        assert float(b2.flat.norm()) <= 0.1 + 1e-5
+        for p_ in net2.parameters():                         # param.grad still views the (clipped) flat buffer
+            assert float(p_.grad.abs().sum()) > 0
+        # a parameter that receives no gradient: its bucket is reduced by finish()
+        net3 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(6, 5))
+        b3 = FlatGradBucket(net3.parameters(), bucket_bytes=64, overlap=True)
+        b3.zero()
+        net3[0](x).sum().backward()
+        assert not all(b3._fired)
+        b3.finish()
+        assert all(b3._fired)
+
+        # asynchronous normalisers: issued early, waited for at first use
+        pend = AsyncNormalisers({"mask": [torch.ones(2, 3) > 0], "heatmap": [torch.ones(1, 1, 2, 2)]},
+                                torch.ones(1, 4, dtype=torch.bool), torch.tensor(float(rank)))
+        np_, nh_, nv_, ms_ = pend.get()
+        assert float(np_[0]) == 6.0 and float(nh_[0]) == 4.0 and float(nv_) == 4.0 and float(ms_) == pytest.approx(0.5)
 
         # fused normalisers: one all-reduce for 2*T + 2 scalars
         ret = {"mask": [torch.full((2, 4), float(rank + t)) > 0.5 for t in range(3)],
