@@ -1,3 +1,3 @@
 from unidistill._overlay import extend as _extend
 
-_extend(__path__, __name__)
+_extend(__path__, __name__, globals())

@@ -71,6 +71,47 @@ class SparseBasicBlock(spconv.SparseModule):
         return out
 
 
+class VoxelBackBone8x(nn.Module):
+    """Plain (non-residual) variant, reference :116-250: conv-bn-relu blocks only, batch_dict in / batch_dict out.  Not used
+    by the BEVFusion experiments; kept so that `unidistill.layers.blocks_3d.det3d` exports what the reference's does."""
+
+    # (attribute, cin, cout, padding of the strided conv | None for the SubM-only stage, strided key, SubM key, #SubM)
+    _PLAN = (("conv1", 16, 16, None, None, "subm1", 1), ("conv2", 16, 32, 1, "spconv2", "subm2", 2),
+             ("conv3", 32, 64, 1, "spconv3", "subm3", 2), ("conv4", 64, 64, (0, 1, 1), "spconv4", "subm4", 2))
+
+    def __init__(self, input_channels, grid_size, last_pad=0):
+        super().__init__()
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        self.sparse_shape = np.asarray(grid_size)[::-1] + [1, 0, 0]
+        self.conv_input = spconv.SparseSequential(
+            spconv.SubMConv3d(input_channels, 16, 3, padding=1, bias=False, indice_key="subm1"), norm_fn(16), nn.ReLU())
+        for name, cin, cout, pad, down_key, subm_key, n_subm in self._PLAN:
+            blocks = []
+            if down_key is not None:
+                blocks.append(post_act_block(cin, cout, 3, norm_fn=norm_fn, stride=2, padding=pad, indice_key=down_key,
+                                             conv_type="spconv"))
+            blocks += [post_act_block(cout, cout, 3, norm_fn=norm_fn, padding=1, indice_key=subm_key)
+                       for _ in range(n_subm)]
+            setattr(self, name, spconv.SparseSequential(*blocks))
+        self.conv_out = spconv.SparseSequential(
+            spconv.SparseConv3d(64, 128, (3, 1, 1), stride=(2, 1, 1), padding=last_pad, bias=False,
+                                indice_key="spconv_down2", algo=SPCONV_ALGO_TYPE),
+            norm_fn(128), nn.ReLU())
+        self.num_point_features = 128
+
+    def forward(self, batch_dict):
+        x = spconv.SparseConvTensor(features=batch_dict["voxel_features"], indices=batch_dict["voxel_coords"].int(),
+                                    spatial_shape=self.sparse_shape, batch_size=batch_dict["batch_size"])
+        x = self.conv_input(x)
+        scales = {}
+        for name in ("conv1", "conv2", "conv3", "conv4"):
+            x = getattr(self, name)(x)
+            scales["x_" + name] = x
+        batch_dict.update({"encoded_spconv_tensor": self.conv_out(x), "encoded_spconv_tensor_stride": 8,
+                           "multi_scale_3d_features": scales})
+        return batch_dict
+
+
 class VoxelResBackBone8x(nn.Module):
     # (attribute name, in, out, padding of the strided conv, indice keys)
     _STAGES = (

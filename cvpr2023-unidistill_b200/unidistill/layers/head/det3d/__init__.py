@@ -1,6 +1,6 @@
 from unidistill._overlay import extend as _extend
 
-_extend(__path__, __name__)
+_extend(__path__, __name__, globals())
 
 from .center_head import CenterHead, SepHead  # noqa: E402
 from .center_head_iou_aware import CenterHeadIouAware  # noqa: E402

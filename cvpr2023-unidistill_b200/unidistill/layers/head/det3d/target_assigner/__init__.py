@@ -1,6 +1,6 @@
 from unidistill._overlay import extend as _extend
 
-_extend(__path__, __name__)
+_extend(__path__, __name__, globals())
 
 from .base_assigner import BaseAssigner  # noqa: E402
 from .fcos_assigner import FCOSAssigner  # noqa: E402

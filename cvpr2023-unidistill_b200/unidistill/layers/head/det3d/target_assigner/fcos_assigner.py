@@ -187,6 +187,8 @@ class FCOSAssigner(BaseAssigner):
             n_pos = pos.sum(dim=1, keepdim=True)
             # positives first, ascending anchor index
             pos_order = torch.sort((~pos).to(torch.uint8), dim=1, stable=True).indices[:, :max_objs]
+            if pos_order.shape[1] < max_objs:                                  # fewer anchors than slots (tiny maps)
+                pos_order = torch.nn.functional.pad(pos_order, (0, max_objs - pos_order.shape[1]))
             keep = rank < n_pos                                                # (B, max_objs)
             gt_sel = torch.gather(gt_of_anchor, 1, pos_order)
             tgt_box = torch.gather(boxes, 1, gt_sel.unsqueeze(2).expand(B, max_objs, boxes.shape[2]))

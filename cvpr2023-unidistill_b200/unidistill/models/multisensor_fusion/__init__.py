@@ -1,3 +1,7 @@
-from .base import BaseEncoder, BaseMultiSensorFusion
+from unidistill._overlay import extend as _extend
+
+_extend(__path__, __name__, globals())
+
+from .base import BaseEncoder, BaseMultiSensorFusion  # noqa: E402
 
 __all__ = ["BaseMultiSensorFusion", "BaseEncoder"]

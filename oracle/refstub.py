@@ -113,15 +113,24 @@ class _StubFinder(object):
         return None
 
 
-def install():
+AttrDict = _AttrDict
+
+
+def install(overlay=False):
     """Puts the reference on sys.path (first) and registers the third-party stubs.  Must run in a process
-    that has NOT imported this repo's own `unidistill` mirror."""
+    that has NOT imported this repo's own `unidistill` mirror.
+    overlay=True: the repo's `unidistill` mirror and `spconv` shim stay in front (they must already be on sys.path) and
+    the reference is reached through UNIDISTILL_REFERENCE_ROOT (unidistill/_overlay.py) -- the deployment of
+    INTEGRATION.md section 1; only the packages absent from this image are stubbed."""
     if not available():
         raise RuntimeError("reference checkout not found at %s" % REFERENCE_ROOT)
-    if "unidistill" in sys.modules and not sys.modules["unidistill"].__file__.startswith(REFERENCE_ROOT):
-        raise RuntimeError("the mirror package is already imported in this process")
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if overlay:
+        os.environ["UNIDISTILL_REFERENCE_ROOT"] = REFERENCE_ROOT
+    else:
+        if "unidistill" in sys.modules and not sys.modules["unidistill"].__file__.startswith(REFERENCE_ROOT):
+            raise RuntimeError("the mirror package is already imported in this process")
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
     if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
         sys.meta_path.append(_StubFinder())
 
@@ -138,14 +147,17 @@ def install():
     class _SparseModule(nn.Module):
         pass
 
-    spt = importlib.import_module("spconv.pytorch")
-    spt.SparseModule = _SparseModule
-    spt.SparseSequential = nn.Sequential
-    importlib.import_module("spconv.core").ConvAlgo = types.SimpleNamespace(Native=0)
-    for so in ("unidistill.layers.blocks_3d.mmdet3d.voxel_pooling_ext",
-               "unidistill.layers.head.det3d.generate_proposals.iou3d_nms_cuda",
-               "unidistill.utils.det3d_utils.roiaware_pool3d_cuda"):
-        _mod(so)
+    if overlay:
+        _mod("unidistill.utils.det3d_utils.roiaware_pool3d_cuda")      # data augmentation only; no mirror module
+    else:
+        spt = importlib.import_module("spconv.pytorch")
+        spt.SparseModule = _SparseModule
+        spt.SparseSequential = nn.Sequential
+        importlib.import_module("spconv.core").ConvAlgo = types.SimpleNamespace(Native=0)
+        for so in ("unidistill.layers.blocks_3d.mmdet3d.voxel_pooling_ext",
+                   "unidistill.layers.head.det3d.generate_proposals.iou3d_nms_cuda",
+                   "unidistill.utils.det3d_utils.roiaware_pool3d_cuda"):
+            _mod(so)
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
     return _AttrDict

@@ -117,6 +117,23 @@ def test_overflow_is_reported_not_silent(cuda, native_lib):
     assert int(a["n_pos"][0][0]) == int(b_["n_pos"][0][0]) == int(a["heatmap"][0].eq(1).sum())
 
 
+def test_fewer_anchors_than_slots(cuda, native_lib):
+    """A 16x16 map has 256 anchors but max_objs = 2500 slots: both paths zero-pad the tail."""
+    gt = np.zeros((2, 6, 10), np.float32)
+    gt[:, :3, 0:2] = np.array([[1.0, 2.0], [-3.0, 0.5], [4.0, -4.0]], np.float32)
+    gt[:, :3, 3:6] = 1.5
+    gt[:, :, 9] = 1
+    gt[0, 1, 9] = 9
+    from unidistill.layers.head.det3d import FCOSAssigner
+
+    assigner = FCOSAssigner(out_size_factor=8, tasks=TASKS, dense_reg=1, gaussian_overlap=0.1, max_objs=2500, min_radius=2,
+                            mapping={n: i + 1 for i, n in enumerate(CLASS_NAMES)}, grid_size=[128, 128, 40],
+                            pc_range=[-6.4, -6.4], voxel_size=[0.1, 0.1], assign_topk=9, no_log=False, with_velocity=True)
+    a, b_ = _both(assigner, torch.from_numpy(gt).to(cuda))
+    _assert_same(a, b_)
+    assert a["ind"][0].shape == (2, 2500)
+
+
 def test_kernel_matches_reference_golden(cuda, native_lib):
     """The fixture was produced by the reference's own FCOSAssigner (tests/golden/make_golden.py)."""
     g = np.load(GOLDEN)
