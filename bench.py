@@ -711,6 +711,8 @@ def measure(wl, args, world, rank, local, device, peaks, with_roofline=True):
         res["own_kernels_ms_per_step"] = round(sum(e["ms_per_step"] for e in roof_all), 3)
     step_fn = getattr(wl, "step_fn", None)
     if step_fn is not None:
+        terms = wl.step()                   # one more step: the loss terms the optimisation is at (finite = training is alive)
+        res["loss_terms_after_timed_steps"] = {k: round(float(v), 6) for k, v in terms.items()}
         res["allreduce"] = _allreduce_report(step_fn, wl, world, device, args)
     return res
 

@@ -9,7 +9,7 @@ uses the fused lift-splat: softmax(depth) (x) context is consumed inside the poo
 import torch
 from torch import nn
 
-from unidistill_b200.camera import VoxelPooling, lift_splat, voxel_pooling
+from unidistill_b200.camera import VoxelPooling, lift_splat, lss_geometry_index, voxel_pooling
 
 try:  # the reference builds these through the OpenMMLab registries (lss_fpn.py:2-3,143-149)
     from mmdet.models import build_backbone
@@ -43,6 +43,7 @@ class LSSFPN(nn.Module):
         self.img_neck.init_weights()
         self.img_backbone.init_weights()
         self.fuse_lift_splat = True
+        self.fuse_geometry = True
 
     def _configure_timestamp_net(self):
         if self.timestamp_net_conf is None:
@@ -97,11 +98,14 @@ class LSSFPN(nn.Module):
             src.reshape(batch * ncam, src.shape[2], src.shape[3], src.shape[4]), mats_dict, sweep_index)
         depth = depth_feature[:, : self.depth_channels].softmax(1)
         context = depth_feature[:, self.depth_channels: self.depth_channels + self.output_channels]
-        geom = self.get_geometry(
-            mats_dict["sensor2ego_mats"][:, sweep_index, ...], mats_dict["intrin_mats"][:, sweep_index, ...],
-            mats_dict["ida_mats"][:, sweep_index, ...], mats_dict.get("bda_mat", None))
-        # .int() truncates toward zero, as in the reference (:311-313)
-        geom_xyz = ((geom - (self.voxel_coord - self.voxel_size / 2.0)) / self.voxel_size).int()
+        mats = (mats_dict["sensor2ego_mats"][:, sweep_index, ...], mats_dict["intrin_mats"][:, sweep_index, ...],
+                mats_dict["ida_mats"][:, sweep_index, ...], mats_dict.get("bda_mat", None))
+        if self.fuse_geometry and self.frustum.is_cuda:
+            # get_geometry + the truncating index in one kernel (.int() truncates toward zero, as in the reference :311-313)
+            geom_xyz = lss_geometry_index(self.frustum, *mats, self.voxel_coord, self.voxel_size)
+        else:
+            geom = self.get_geometry(*mats)
+            geom_xyz = ((geom - (self.voxel_coord - self.voxel_size / 2.0)) / self.voxel_size).int()
         fused_ok = (self.fuse_lift_splat and type(self)._forward_voxel_net is LSSFPN._forward_voxel_net
                     and self.output_channels in (128, 256))
         if fused_ok:

@@ -4,10 +4,12 @@ Dense 3x3 convolutions stay on cuDNN; module tree and parameter 
 (`shared_conv.{0,1}`, `tasks.<t>.<head>.{0,1,3}`) so checkpoints load by key.
 """
 import copy
+import os
 from collections import OrderedDict
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from unidistill.layers.losses import det3d as loss_utils
 from unidistill.utils.det3d_utils.initialize_utils import kaiming_init
@@ -52,6 +54,70 @@ class SepHead(nn.Module):
 
     def forward(self, x):
         return {head: self.__getattr__(head)(x) for head in self.heads}
+
+
+# the 6 tasks x 7 targets = 42 towers of a CenterHead all read the same 64-channel map and have the same shape
+# up to the class count of the last conv, so they can run as ONE 64 -> 42*64 convolution, ONE BatchNorm over 2688 channels
+# (per-channel statistics: identical to 42 separate norms), ONE ReLU and ONE grouped convolution (42 groups, 64 -> 3 with
+# zero-padded rows) instead of 42 x (conv, BN, ReLU, conv).  Parameters stay where the reference keeps them
+# (`tasks.<t>.<head>.{0,1,3}`), gradients flow back to them through the concatenations.  UD_BATCH_TOWERS=0 disables it.
+BATCH_TOWERS = os.environ.get("UD_BATCH_TOWERS", "1") != "0"
+
+
+def batched_towers(tasks, x):
+    """tasks: the ModuleList of SepHeads of one CenterHead; x (B, C, H, W).  Returns [ {head: (B, classes, H, W)} per task ]
+    == [task(x) for task in tasks], or None when the towers do not have the regular conv-BN-ReLU-conv shape."""
+    towers, names = [], []
+    for t, task in enumerate(tasks):
+        for head in task.heads:
+            tw = getattr(task, head)
+            if len(tw) != 4 or not isinstance(tw[0], nn.Conv2d) or not isinstance(tw[3], nn.Conv2d) \
+                    or not isinstance(tw[1], (nn.BatchNorm2d, nn.Identity)) or not isinstance(tw[2], nn.ReLU):
+                return None
+            towers.append(tw)
+            names.append((t, head))
+    c1, c2 = towers[0][0], towers[0][3]
+    same = all(tw[0].weight.shape == c1.weight.shape and tw[0].padding == c1.padding and tw[0].stride == (1, 1)
+               and tw[0].bias is not None and tw[3].kernel_size == c2.kernel_size and tw[3].padding == c2.padding
+               and tw[3].in_channels == c2.in_channels and tw[3].bias is not None and type(tw[1]) is type(towers[0][1])
+               for tw in towers)
+    if not same:
+        return None
+    n, mid = len(towers), c1.out_channels
+    # ---- layer 1: one convolution for all towers
+    w1 = torch.cat([tw[0].weight for tw in towers], dim=0)
+    b1 = torch.cat([tw[0].bias for tw in towers], dim=0)
+    if w1.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        w1 = w1.contiguous(memory_format=torch.channels_last)
+    y = F.conv2d(x, w1, b1, stride=1, padding=c1.padding)
+    # ---- one BatchNorm over all 42*64 channels (identity when the norms were folded into the convolutions)
+    bns = [tw[1] for tw in towers]
+    if isinstance(bns[0], nn.BatchNorm2d):
+        training = bns[0].training
+        gamma = torch.cat([bn.weight for bn in bns])
+        beta = torch.cat([bn.bias for bn in bns])
+        rm = torch.cat([bn.running_mean for bn in bns])
+        rv = torch.cat([bn.running_var for bn in bns])
+        y = F.batch_norm(y, rm, rv, gamma, beta, training, bns[0].momentum, bns[0].eps)
+        if training:
+            with torch.no_grad():                                   # running statistics back into the 42 modules
+                torch._foreach_copy_([bn.running_mean for bn in bns], list(rm.split(mid)))
+                torch._foreach_copy_([bn.running_var for bn in bns], list(rv.split(mid)))
+                torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
+    y = F.relu(y)
+    # ---- layer 2: one grouped convolution, every tower padded to the widest output (zero rows)
+    outs = [tw[3].out_channels for tw in towers]
+    cmax = max(outs)
+    rows = torch.tensor([i * cmax + c for i, c_ in enumerate(outs) for c in range(c_)], device=x.device)
+    w2_all = torch.cat([tw[3].weight for tw in towers], dim=0)
+    b2_all = torch.cat([tw[3].bias for tw in towers], dim=0)
+    w2 = w2_all.new_zeros((n * cmax,) + tuple(w2_all.shape[1:])).index_copy(0, rows, w2_all)
+    b2 = b2_all.new_zeros((n * cmax,)).index_copy(0, rows, b2_all)
+    z = F.conv2d(y, w2, b2, stride=1, padding=c2.padding, groups=n)
+    ret = [dict() for _ in tasks]
+    for i, (t, head) in enumerate(names):
+        ret[t][head] = z[:, i * cmax: i * cmax + outs[i]]
+    return [OrderedDict((h, d[h]) for h in task.heads) for task, d in zip(tasks, ret)]
 
 
 class CenterHead(nn.Module):
@@ -118,11 +184,19 @@ class CenterHead(nn.Module):
         x = self.shared_conv(spatial_features_2d)
         if self.upsample_for_pedestrian:
             x = self.upsample_conv(x)
-        ret["multi_head_features"] = [task(x) for task in self.tasks]
+        ret["multi_head_features"] = self.run_towers(x)
         if self.training or self.distill:
             ret.update(targets if targets is not None else self.assign_targets(gt_boxes))
             return ret
         return self.proposal_layer.generate_predicted_boxes(ret, {})
+
+    def run_towers(self, x):
+        """[task(x) for task in self.tasks]; on a CUDA device the 42 towers run batched (see batched_towers)."""
+        if BATCH_TOWERS and x.is_cuda:
+            out = batched_towers(self.tasks, x)
+            if out is not None:
+                return out
+        return [task(x) for task in self.tasks]
 
     def build_losses(self):
         self.add_module("crit", loss_utils.CenterNetFocalLoss())

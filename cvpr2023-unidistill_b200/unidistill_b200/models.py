@@ -268,7 +268,7 @@ class GraphedDenseTrunk:
         h = head.shared_conv(feats)
         if head.upsample_for_pedestrian:
             h = head.upsample_conv(h)
-        ret = {"multi_head_features": [task(h) for task in head.tasks]}
+        ret = {"multi_head_features": head.run_towers(h)}
         if gt is not None and (head.training or head.distill):
             # FCOSAssigner.assign_targets is a static-shape, sync-free tensor program: it rides in the same graph
             ret.update(head.assign_targets(gt))

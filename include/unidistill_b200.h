@@ -177,6 +177,18 @@ int ud_voxel_pooling_backward(int batch_size, int num_points, int num_channels, 
                               size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LSS frustum geometry -> BEV voxel index in one kernel.  Replaces LSSFPN.get_geometry (three batched 4x4 mat-vec
+ * products over the (B,ncam,D,H,W) frustum, lss_fpn.py:200-240) and the index computation
+ * `((geom - (voxel_coord - voxel_size / 2)) / voxel_size).int()` (lss_fpn.py:311-313; truncation toward zero).
+ * frustum (D*H*W,4) f32 [u,v,depth,1]; ida_inv = ida_mat^-1 and cam2ego = sensor2ego @ intrin^-1, both (B*ncam,4,4) f32
+ * row-major (computed by the caller: B*ncam tiny matrices); bda (B,4,4) f32 or NULL; voxel_lo / voxel_size HOST float[3].
+ * idx (B,ncam,D*H*W,3) int32 and/or geom (same shape, f32); either output may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int ud_lss_geometry(const float* frustum, int num_frustum_points, int batch_size, int num_cams, const float* ida_inv,
+                    const float* cam2ego, const float* bda, const float* voxel_lo, const float* voxel_size, int* idx,
+                    float* geom, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused LSS lift-splat: out[b,:,y,x] = sum over frustum points p in cell (y,x) of depth[p] * ctx[pix(p),:].
  * Replaces the materialised outer product + permute + pooling of lss_fpn.py:289-316 (484 MB/sample x2).
  * geom_xyz (B, ncam*D*H*W, 3) int32 (lss_fpn.py:311-313); depth (B*ncam,D,H,W) f32 (already softmaxed);

@@ -1,0 +1,33 @@
+"""GPU debugging aid: runs the distillation step a few times printing every loss term, the gradient norm and the number
+of non-finite student parameters, then an aten-op table (torch.profiler, grouped by op + input shapes) of one step."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "cvpr2023-unidistill_b200")):
+    sys.path.insert(0, p)
+import bench  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "distill_lidar"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+dev = torch.device("cuda:0")
+torch.backends.cudnn.benchmark = True
+wl = bench.WORKLOADS[name](dev, 0)
+st = wl.step_fn
+for i in range(steps):
+    t = wl.step()
+    bad = sum(int((~torch.isfinite(p)).sum()) for p in st.student.parameters())
+    badb = sum(int((~torch.isfinite(b)).sum()) for b in st.student.buffers() if b.is_floating_point())
+    print("step %2d  " % i + "  ".join("%s=%.5g" % (k, float(v)) for k, v in t.items()) + "  nonfinite params=%d buffers=%d"
+          % (bad, badb), flush=True)
+if "--profile" in sys.argv:
+    from torch.profiler import ProfilerActivity, profile
+
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+        wl.step()
+        torch.cuda.synchronize()
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=70,
+                                                             max_name_column_width=50, max_shapes_column_width=70))
