@@ -507,7 +507,7 @@ def _algorithmic(name, a, meta, cache):
     if name == "ud_bn_apply":
         return "BN1d apply (+res)+ReLU", "hbm", 2 * a[1] * a[2] * 4, 0
     if name == "ud_bn_backward":
-        return "BN1d backward (2 kernels)", "hbm", 4 * a[3] * a[4] * 4, 0
+        return "BN1d backward (reduce + apply)", "hbm", 4 * a[3] * a[4] * 4, 0
     if name in ("ud_bn_finalize", "ud_bn_eval_coeffs"):
         return "BN1d coefficients", "latency", 0, 0
     if name in ("ud_scatter_to_bev", "ud_gather_from_bev"):

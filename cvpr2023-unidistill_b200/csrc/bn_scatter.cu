@@ -8,15 +8,18 @@
 // Scatter: reference layers/blocks_2d/det3d/map_to_bev/height_compression.py:11-22
 // (`sp_tensor.dense()` -> (B, C, D, H, W) -> view(B, C*D, H, W)); channel index = c*D + z.
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace {
 
 // ---- statistics: per-channel sum and sum of squares over the active rows ----------------------
 // block = 256 threads = (256/C) row lanes x C channels, C in {16,32,64,128}
 __global__ void __launch_bounds__(256)
-k_bn_stats(const float* __restrict__ x, int n, int C, double* __restrict__ sum, double* __restrict__ sqsum) {
+k_bn_stats(const float* __restrict__ x, int n, int C, double* __restrict__ sums, unsigned char* __restrict__ ws,
+           int group) {
     __shared__ float s_sum[256];
     __shared__ float s_sq[256];
+    __shared__ int flag_s;
     const int c = threadIdx.x % C;
     const int rl = threadIdx.x / C;
     const int RL = blockDim.x / C;
@@ -29,15 +32,14 @@ k_bn_stats(const float* __restrict__ x, int n, int C, double* __restrict__ sum, 
     s_sum[threadIdx.x] = a;
     s_sq[threadIdx.x] = b;
     __syncthreads();
-    if (rl == 0) {
-        double da = 0.0, db = 0.0;
-        for (int j = 0; j < RL; ++j) {
-            da += (double)s_sum[j * C + c];
-            db += (double)s_sq[j * C + c];
-        }
-        atomicAdd(sum + c, da);
-        atomicAdd(sqsum + c, db);
+    // this block's partial of column tid (tid < C: sum, tid in [C, 2C): sum of squares), then the fixed-order reduction
+    double v = 0.0;
+    if (threadIdx.x < 2 * C) {
+        const float* src = threadIdx.x < C ? s_sum : s_sq;
+        const int cc = threadIdx.x % C;
+        for (int j = 0; j < RL; ++j) v += (double)src[j * C + cc];
     }
+    ud_det_reduce(v, threadIdx.x, 2 * C, ws, group, sums, &flag_s);
 }
 
 // scale = gamma * invstd, shift = beta - mean * scale; optional running-stat update (training).
@@ -108,9 +110,10 @@ k_bn_apply(const float4* x, long long n4, int C4, const float4* __restrict__ sca
 __global__ void __launch_bounds__(256)
 k_bn_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, int n,
                 int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                double* __restrict__ sum_g, double* __restrict__ sum_gx) {
+                double* __restrict__ sums, unsigned char* __restrict__ ws, int group) {
     __shared__ float s_a[256];
     __shared__ float s_b[256];
+    __shared__ int flag_s;
     const int c = threadIdx.x % C;
     const int rl = threadIdx.x / C;
     const int RL = blockDim.x / C;
@@ -125,15 +128,13 @@ k_bn_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ y, const
     s_a[threadIdx.x] = a;
     s_b[threadIdx.x] = b;
     __syncthreads();
-    if (rl == 0) {
-        double da = 0.0, db = 0.0;
-        for (int j = 0; j < RL; ++j) {
-            da += (double)s_a[j * C + c];
-            db += (double)s_b[j * C + c];
-        }
-        atomicAdd(sum_g + c, da);
-        atomicAdd(sum_gx + c, db);
+    double v = 0.0;
+    if (threadIdx.x < 2 * C) {
+        const float* src = threadIdx.x < C ? s_a : s_b;
+        const int cc = threadIdx.x % C;
+        for (int j = 0; j < RL; ++j) v += (double)src[j * C + cc];
     }
+    ud_det_reduce(v, threadIdx.x, 2 * C, ws, group, sums, &flag_s);      // sums[0..C) = sum g, [C..2C) = sum g * xhat
 }
 
 // dx = gamma*invstd * (g - sum_g/n - xhat * sum_gx/n);  dres = g (optional)
@@ -224,17 +225,32 @@ k_gather_bev(const float* __restrict__ dense, const int4* __restrict__ coords, i
 
 extern "C" {
 
-// sum/sqsum: (C) f64 device scratch (zeroed here).  C must divide 256.
-int ud_bn_stats(const float* x, int n, int C, double* sum, double* sqsum, void* stream_) {
+static int ud_bn_reduce_grid(int n, int C) {
+    const int RL = 256 / C;
+    const long long want = ((long long)n + RL - 1) / RL;
+    return (int)(want < UD_NUM_SMS * 8 ? (want > 0 ? want : 1) : UD_NUM_SMS * 8);
+}
+
+// Scratch of the fixed-order reductions behind ud_bn_stats and ud_bn_backward for (n, C) inputs.
+int ud_bn_workspace_bytes(int n, int C, size_t* bytes) {
+    if (!bytes || n < 0 || C < 1 || C > 128 || 256 % C != 0) return UD_ERR_INVALID_ARG;
+    *bytes = ud_det_reduce_bytes(ud_bn_reduce_grid(n, C), 2 * C);
+    return UD_OK;
+}
+
+// sums: (2, C) f64 = per-channel sum | sum of squares, fully written (fixed summation order: bit-reproducible).
+// C must divide 256, C <= 128.
+int ud_bn_stats(const float* x, int n, int C, double* sums, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!x || !sum || !sqsum || n < 0 || C < 1 || C > 256 || 256 % C != 0) return UD_ERR_INVALID_ARG;
-    UD_CUDA_TRY(cudaMemsetAsync(sum, 0, sizeof(double) * C, stream));
-    UD_CUDA_TRY(cudaMemsetAsync(sqsum, 0, sizeof(double) * C, stream));
-    if (n == 0) return UD_OK;
-    int RL = 256 / C;
-    long long want = ((long long)n + RL - 1) / RL;
-    int grid = (int)(want < UD_NUM_SMS * 8 ? want : UD_NUM_SMS * 8);
-    k_bn_stats<<<grid, 256, 0, stream>>>(x, n, C, sum, sqsum);
+    if (!x || !sums || n < 0 || C < 1 || C > 128 || 256 % C != 0) return UD_ERR_INVALID_ARG;
+    if (n == 0) {
+        UD_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+        return UD_OK;
+    }
+    const int grid = ud_bn_reduce_grid(n, C);
+    if (!workspace || workspace_bytes < ud_det_reduce_bytes(grid, 2 * C)) return UD_ERR_WORKSPACE;
+    UD_CUDA_TRY(cudaMemsetAsync(workspace, 0, UD_DET_COUNTER_BYTES, stream));
+    k_bn_stats<<<grid, 256, 0, stream>>>(x, n, C, sums, (unsigned char*)workspace, ud_det_group(grid));
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -276,21 +292,26 @@ int ud_bn_apply(const float* x, int n, int C, const float* scale, const float* s
     return UD_OK;
 }
 
-// sum_g/sum_gx: (C) f64 scratch (zeroed here); dx: (n,C); dres nullable (n,C).
+// sums: (2, C) f64, fully written: [0..C) = sum_g (d beta), [C..2C) = sum_gx (d gamma), fixed summation order;
+// dx: (n,C); dres nullable (n,C); workspace: ud_bn_workspace_bytes(n, C).
 int ud_bn_backward(const float* dy, const float* y, const float* x, int n, int C, const float* mean,
-                   const float* invstd, const float* gamma, int relu, double* sum_g, double* sum_gx,
-                   float* dx, float* dres, void* stream_) {
+                   const float* invstd, const float* gamma, int relu, double* sums, float* dx, float* dres,
+                   void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!dy || !x || !mean || !invstd || !sum_g || !sum_gx || !dx || n < 0 || C < 1 || C > 256 || 256 % C != 0)
+    if (!dy || !x || !mean || !invstd || !sums || !dx || n < 0 || C < 1 || C > 128 || 256 % C != 0)
         return UD_ERR_INVALID_ARG;
     if (relu && !y) return UD_ERR_INVALID_ARG;
-    UD_CUDA_TRY(cudaMemsetAsync(sum_g, 0, sizeof(double) * C, stream));
-    UD_CUDA_TRY(cudaMemsetAsync(sum_gx, 0, sizeof(double) * C, stream));
-    if (n == 0) return UD_OK;
-    int RL = 256 / C;
-    long long want = ((long long)n + RL - 1) / RL;
-    int grid = (int)(want < UD_NUM_SMS * 8 ? want : UD_NUM_SMS * 8);
-    k_bn_bwd_reduce<<<grid, 256, 0, stream>>>(dy, y, x, n, C, mean, invstd, relu, sum_g, sum_gx);
+    if (n == 0) {
+        UD_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+        return UD_OK;
+    }
+    const int grid = ud_bn_reduce_grid(n, C);
+    if (!workspace || workspace_bytes < ud_det_reduce_bytes(grid, 2 * C)) return UD_ERR_WORKSPACE;
+    UD_CUDA_TRY(cudaMemsetAsync(workspace, 0, UD_DET_COUNTER_BYTES, stream));
+    double* sum_g = sums;
+    double* sum_gx = sums + C;
+    k_bn_bwd_reduce<<<grid, 256, 0, stream>>>(dy, y, x, n, C, mean, invstd, relu, sums, (unsigned char*)workspace,
+                                              ud_det_group(grid));
     UD_LAUNCH_CHECK();
     long long total = (long long)n * C;
     long long want2 = (total + 255) / 256;

@@ -248,7 +248,8 @@ class SparseSequential(SparseModule):
                     continue
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
                 if (type(module) is nn.BatchNorm1d and input.features.is_cuda
-                        and input.features.shape[1] % 4 == 0 and 256 % input.features.shape[1] == 0):
+                        and input.features.shape[1] % 4 == 0 and 256 % input.features.shape[1] == 0
+                        and input.features.shape[1] <= 128):
                     relu = type(nxt) is nn.ReLU
                     feats = _sp.batch_norm_act(input.features, module, relu=relu)
                     input = input.replace_feature(feats)

@@ -34,7 +34,7 @@ def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stri
 
 def _fusable(bn, feats):
     c = feats.shape[1]
-    return type(bn) is nn.BatchNorm1d and feats.is_cuda and c % 4 == 0 and 256 % c == 0
+    return type(bn) is nn.BatchNorm1d and feats.is_cuda and c % 4 == 0 and 256 % c == 0 and c <= 128
 
 
 class SparseBasicBlock(spconv.SparseModule):

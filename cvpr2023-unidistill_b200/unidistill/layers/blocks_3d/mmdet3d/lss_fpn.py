@@ -78,6 +78,8 @@ class LSSFPN(nn.Module):
         if bda_mat is not None:
             bda = bda_mat.unsqueeze(1).repeat(1, ncam, 1, 1).view(batch, ncam, 1, 1, 1, 4, 4)
             pts = (bda @ pts).squeeze(-1)
+        else:
+            pts = pts.squeeze(-1)
         return pts[..., :3]
 
     def get_cam_feats(self, imgs):

@@ -64,6 +64,9 @@ class SepHead(nn.Module):
 BATCH_TOWERS = os.environ.get("UD_BATCH_TOWERS", "1") != "0"
 
 
+_ROWS_CACHE = {}
+
+
 def batched_towers(tasks, x):
     """tasks: the ModuleList of SepHeads of one CenterHead; x (B, C, H, W).  Returns [ {head: (B, classes, H, W)} per task ]
     == [task(x) for task in tasks], or None when the towers do not have the regular conv-BN-ReLU-conv shape."""
@@ -108,7 +111,11 @@ def batched_towers(tasks, x):
     # ---- layer 2: one grouped convolution, every tower padded to the widest output (zero rows)
     outs = [tw[3].out_channels for tw in towers]
     cmax = max(outs)
-    rows = torch.tensor([i * cmax + c for i, c_ in enumerate(outs) for c in range(c_)], device=x.device)
+    key = (str(x.device), cmax, tuple(outs))
+    rows = _ROWS_CACHE.get(key)
+    if rows is None:      # built once per layout (the first call must be outside a CUDA-graph capture: warm-up runs are)
+        rows = torch.tensor([i * cmax + c for i, c_ in enumerate(outs) for c in range(c_)], device=x.device)
+        _ROWS_CACHE[key] = rows
     w2_all = torch.cat([tw[3].weight for tw in towers], dim=0)
     b2_all = torch.cat([tw[3].bias for tw in towers], dim=0)
     w2 = w2_all.new_zeros((n * cmax,) + tuple(w2_all.shape[1:])).index_copy(0, rows, w2_all)

@@ -95,7 +95,11 @@ class CenterHeadIouAware(CenterHead):
         def decode(t):
             x = (t[..., 0:1] * stride * voxel_size[0]).reshape(-1, 1)
             y = (t[..., 1:2] * stride * voxel_size[1]).reshape(-1, 1)
-            whl = torch.clamp(torch.exp(t[..., 3:6]).reshape(-1, 3), min=0.001, max=30)
+            # exp(clamp(x, max=10)) == exp(x) wherever the outer clamp (max=30 < e^10) does not cut it off, values and
+            # gradients alike; but it cannot overflow.  The reference only puts this branch into the graph when
+            # loc_loss < 1 (a Python `if` on .item(), :131-133); the sync-free torch.where below always builds it, and a
+            # zero gradient flowing into an exp() that overflowed to inf would be 0 * inf = NaN for the whole step.
+            whl = torch.clamp(torch.exp(t[..., 3:6].clamp(max=10.0)).reshape(-1, 3), min=0.001, max=30)
             rot = torch.atan2(t[..., 6], t[..., 7]).reshape(-1, 1)
             z = t[..., 2].reshape(-1, 1)
             return x, y, z, whl, rot

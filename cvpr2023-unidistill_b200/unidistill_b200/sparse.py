@@ -155,9 +155,6 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
 # tensor-core (tcgen05) sparse convolution for the channel pairs the library supports; UD_SPCONV_TC=0 keeps
 # every layer on the fp32 SIMT kernel (used by the tests to cross-check the two kernels)
 USE_TENSOR_CORES = os.environ.get("UD_SPCONV_TC", "1") != "0"
-# 4: bf16x3 operand split, gathered rows go global -> registers -> TMEM (default), 3: bf16x3 with the rows staged in
-# shared memory, 0: A through TMEM, tf32 + bf16 correction MMAs, 1: A through smem (3xTF32), 2: A through TMEM (3xTF32)
-TC_VARIANT = int(os.environ.get("UD_SPCONV_TC_VARIANT", "4"))
 # the tensor-core kernel's epilogue also accumulates the per-channel sum / sum of squares of its output, so the
 # BatchNorm1d that follows skips its statistics pass (attribute `_ud_bn_sums` on the conv output, see batch_norm_act)
 FUSE_BN_STATS = os.environ.get("UD_FUSE_BN_STATS", "1") != "0"
@@ -166,28 +163,36 @@ FUSE_BN_STATS = os.environ.get("UD_FUSE_BN_STATS", "1") != "0"
 USE_TC_WGRAD = os.environ.get("UD_SPCONV_TC_WGRAD", "1") != "0"
 
 
-# id(weight) -> (weakref to the weight, its _version, kernel variant, packed image): re-pack only when the parameter
-# object is new or was modified in place (optimizer steps and load_state_dict bump _version)
+# id(weight) -> (weakref to the weight, its _version, packed image): re-pack only when the parameter object is new or
+# was modified in place (optimizer steps, load_state_dict and every in-place op bump _version).  Writes THROUGH
+# `weight.data` (p.data.copy_(...), EMA / weight surgery code) do not bump it: call invalidate_packed_weights() after them.
 _PACK_CACHE = {}
+
+
+def invalidate_packed_weights(weight=None):
+    """Drops the cached packed image of `weight` (or all of them)."""
+    if weight is None:
+        _PACK_CACHE.clear()
+    else:
+        _PACK_CACHE.pop(id(weight), None)
 
 
 def _packed_weights(w_k, K, cin, cout, sp, weight=None):
     lib = native.load()
     if weight is not None:
         hit = _PACK_CACHE.get(id(weight))
-        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == TC_VARIANT \
-                and hit[3].device == weight.device:
-            return hit[3]
+        if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
+            return hit[2]
     w_k = w_k() if callable(w_k) else w_k
-    nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout, TC_VARIANT)
+    nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout)
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=w_k.device)
-    rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), TC_VARIANT, sp)
+    rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
     native.check(rc, "ud_sparse_conv_tc_pack_weights")
     if weight is not None:
         if len(_PACK_CACHE) > 256:
             for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
                 del _PACK_CACHE[k]
-        _PACK_CACHE[id(weight)] = (weakref.ref(weight), weight._version, TC_VARIANT, packed)
+        _PACK_CACHE[id(weight)] = (weakref.ref(weight), weight._version, packed)
     return packed
 
 
@@ -198,21 +203,22 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
     sp = native.stream_ptr(dev)
     meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
             "table": table} if native.TIMER.enabled else None
-    if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout, TC_VARIANT):
+    if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout):
         packed = _packed_weights(w_k, K, cin, cout, sp, weight)
         if meta is not None:
-            meta["kernel"] = {1: "k_spconv_umma", 4: "k_spconv_umma_dg"}.get(TC_VARIANT, "k_spconv_umma_ts")
+            meta["kernel"] = "k_spconv_umma_dg"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
-        sums = None
-        if want_stats and FUSE_BN_STATS and TC_VARIANT != 1:
-            sums = torch.zeros((2, cout), dtype=torch.float64, device=dev)
+        stats = None
+        if want_stats and FUSE_BN_STATS:
+            # scratch of the kernel's fixed-order statistics reduction; its first 2 * cout doubles are the result
+            stats = torch.empty((native.query_bytes("ud_sparse_conv_tc_stats_bytes", n_out, cout) // 8,),
+                                dtype=torch.float64, device=dev)
         native.TIMER.meta = meta
         rc = lib.ud_sparse_conv_tc_forward(native.ptr(feats), native.ptr(packed), native.ptr(bias), native.ptr(table_t),
-                                           native.ptr(masks), n_out, K, cin, cout, native.ptr(out), native.ptr(sums),
-                                           TC_VARIANT, sp)
+                                           native.ptr(masks), n_out, K, cin, cout, native.ptr(out), native.ptr(stats), sp)
         native.check(rc, "ud_sparse_conv_tc_forward")
-        if sums is not None:
-            out._ud_bn_sums = sums
+        if stats is not None:
+            out._ud_bn_sums = stats[: 2 * cout].view(2, cout)
         return out
     if meta is not None:
         meta["kernel"] = "k_spconv_gather_gemm"
@@ -332,7 +338,8 @@ class BatchNormActFunction(Function):
             sums = fused_sums
             if sums is None or tuple(sums.shape) != (2, C) or sums.device != dev:
                 sums = torch.empty((2, C), dtype=torch.float64, device=dev)
-                rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums[0]), native.ptr(sums[1]), sp)
+                ws = native.WORKSPACE.get(native.query_bytes("ud_bn_workspace_bytes", n, C), dev)
+                rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums), native.ptr(ws), ws.numel(), sp)
                 native.check(rc, "ud_bn_stats")
             rc = lib.ud_bn_finalize(native.ptr(sums[0]), native.ptr(sums[1]), n, C, native.ptr(gamma),
                                     native.ptr(beta), float(eps), float(momentum), native.ptr(running_mean),
@@ -367,9 +374,10 @@ class BatchNormActFunction(Function):
             sums = torch.empty((2, C), dtype=torch.float64, device=dev)
             dx = torch.empty_like(x)
             dres = torch.empty_like(x) if ctx.has_res else None
+            ws = native.WORKSPACE.get(native.query_bytes("ud_bn_workspace_bytes", n, C), dev)
             rc = lib.ud_bn_backward(native.ptr(dy), native.ptr(y), native.ptr(x), n, C, native.ptr(mean),
                                     native.ptr(invstd), native.ptr(gamma), 1 if ctx.relu else 0,
-                                    native.ptr(sums[0]), native.ptr(sums[1]), native.ptr(dx), native.ptr(dres),
+                                    native.ptr(sums), native.ptr(dx), native.ptr(dres), native.ptr(ws), ws.numel(),
                                     native.stream_ptr(dev))
             native.check(rc, "ud_bn_backward")
             dgamma = sums[1].float() if ctx.has_affine else None

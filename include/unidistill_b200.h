@@ -94,30 +94,24 @@ int ud_sparse_conv_forward(const float* in, const float* w, const float* bias, c
 int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int n_out, int K, int cin,
                          int cout, float* dw, void* stream);
 
-/* Tensor-core variant (tcgen05.mma kind::tf32 with a hi/lo operand split == fp32-accurate "3xTF32",
- * accumulators in TMEM; csrc/sparse_conv_umma.cu).  Same arithmetic contract as ud_sparse_conv_forward for
- * the (cin, cout) pairs ud_sparse_conv_tc_supported() accepts; the weights are first packed into the
- * swizzled hi/lo image the kernel's bulk copies read (packed_bytes from ud_sparse_conv_tc_weight_bytes). */
-int ud_sparse_conv_tc_supported(int K, int cin, int cout, int variant);
-int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, int variant, size_t* bytes);
-int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, int variant, void* stream);
-/* development aid: device buffer of 16 uint64 receiving role-level cycle counts of the tensor-core kernel; NULL = off */
-int ud_debug_umma_prof(void* buf);
-/* development aid: disables pipeline roles of the tensor-core kernel (results become wrong); 0 = normal operation */
-int ud_debug_umma_flags(int flags);
+/* Tensor-core kernel (tcgen05.mma kind::f16 on a bf16 hi/lo split of both operands == fp32-accurate to ~2e-5, fp32
+ * accumulators in TMEM, gathered rows global -> registers -> TMEM; csrc/sparse_conv_umma.cu).  Same arithmetic contract as
+ * ud_sparse_conv_forward for the (cin, cout) pairs ud_sparse_conv_tc_supported() accepts; the weights are first packed
+ * into the swizzled bf16 hi/lo image the kernel's bulk copies read (ud_sparse_conv_tc_weight_bytes). */
+int ud_sparse_conv_tc_supported(int K, int cin, int cout);
+int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
+int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
 /* nbr (n,K) row-major gather table -> nbr_t (K4,ld) tap-major with K4 = K rounded up to 4, ld = n rounded up to 128
- * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row tile: the two table forms the
- * tensor-core kernel reads */
+ * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row
+ * tile: the two table forms the tensor-core kernels read */
 int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream);
-/* variant 4 = default kernel (both operands split into bf16 hi + bf16 lo, three bf16 MMAs per 16 channels; the gathered
- * rows go global -> registers -> TMEM without shared-memory staging), 3 = the same arithmetic with the rows staged in shared
- * memory (cp.async ring + transform warps; weights packed identically), 0 = A through TMEM, hi*hi in TF32 + the two correction products as bf16 MMAs,
- * 1 = A through shared memory with 3xTF32, 2 = A through TMEM with 3xTF32; pack the weights for the same variant */
-/* bn_sums (nullable; not with variant 1): double[2*cout]; the kernel adds the per-channel sum and sum of squares of `out`
- * to it, i.e. the statistics pass of the BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113) */
+/* bn_stats (nullable): scratch of ud_sparse_conv_tc_stats_bytes(n_out, cout) bytes, 16-byte aligned, uninitialised.  On
+ * return its first 2*cout doubles are the per-channel sum and sum of squares of `out`, i.e. the statistics pass of the
+ * BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113), reduced in a fixed order (bit-reproducible) */
+int ud_sparse_conv_tc_stats_bytes(int n_out, int cout, size_t* bytes);
 int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
-                              double* bn_sums, int variant, void* stream);
+                              void* bn_stats, void* stream);
 
 /* Tensor-core weight gradient (csrc/sparse_conv_wgrad_umma.cu): dw[k] += in[nbr[o][k],:]^T dout[o,:] as tcgen05 MMAs
  * over the row dimension (both operands MN-major in shared memory, rounded to TF32 to-nearest on the way in, fp32
@@ -132,7 +126,11 @@ int ud_sparse_conv_tc_wgrad(const float* in, const float* dout, const int* nbr_t
  * BatchNorm1d over active rows (+residual, +ReLU).  Replaces the nn.BatchNorm1d / nn.ReLU /
  * replace_feature passes of spconv_backbone.py:50-56,97-113,255.
  * ------------------------------------------------------------------------------------------- */
-int ud_bn_stats(const float* x, int n, int C, double* sum, double* sqsum, void* stream);
+/* ud_bn_stats / ud_bn_backward reduce over the rows in a FIXED order (no floating-point atomics): bit-reproducible.
+ * sums (2,C) f64 is fully written: statistics pass [sum | sum of squares]; backward [sum g | sum g*xhat] = [d beta | d gamma].
+ * workspace: ud_bn_workspace_bytes(n, C).  C divides 256, C <= 128. */
+int ud_bn_workspace_bytes(int n, int C, size_t* bytes);
+int ud_bn_stats(const float* x, int n, int C, double* sums, void* workspace, size_t workspace_bytes, void* stream);
 int ud_bn_finalize(const double* sum, const double* sqsum, int n, int C, const float* gamma,
                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
@@ -141,8 +139,8 @@ int ud_bn_eval_coeffs(const float* running_mean, const float* running_var, const
 int ud_bn_apply(const float* x, int n, int C, const float* scale, const float* shift, const float* residual,
                 int relu, float* y, void* stream);
 int ud_bn_backward(const float* dy, const float* y, const float* x, int n, int C, const float* mean,
-                   const float* invstd, const float* gamma, int relu, double* sum_g, double* sum_gx,
-                   float* dx, float* dres, void* stream);
+                   const float* invstd, const float* gamma, int relu, double* sums, float* dx, float* dres,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Scatter to BEV.  Replaces SparseConvTensor.dense() + view of

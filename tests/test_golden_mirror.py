@@ -181,3 +181,32 @@ def test_default_centernet_focal_loss_matches_reference():
     f = FocalLoss(0.25, 2)(pred, (gt == 1).float())
     assert abs(float(f) - float(g["loss_focal_025_2"])) <= 1e-6 * abs(float(g["loss_focal_025_2"]))
     assert abs(float(f) - float(g["loss"])) > 1e-3            # the two criteria are not interchangeable
+
+
+def test_iou_branch_cannot_poison_the_gradient():
+    """Random-init heads can predict log-sizes whose exp() overflows.  The reference keeps the IoU loss out of the graph
+    unless loc_loss < 1 (Python `if loc_loss.item() < 1`, center_head_iou_aware.py:131-133); the sync-free torch.where of the
+    mirror always builds the branch, so its exp() must not overflow (0 * inf = NaN in ExpBackward): gradients stay finite
+    and equal those of the loss without the IoU term."""
+    g = _load("head_loss.npz")
+    head = _head(g).train()
+    with torch.no_grad():
+        for task in head.tasks:
+            task.dim[3].bias.fill_(120.0)                     # exp(120) = inf in fp32
+    x, gt = torch.from_numpy(g["x"]), torch.from_numpy(g["gt_boxes"])
+    ret = head(x, gt)
+    for _, enc in ret["box_encoding"].items():
+        enc[torch.isinf(enc)] = 0
+    loss, tb = head.get_loss(ret)
+    assert torch.isfinite(loss) and any(float(tb["task_%d/loc_loss" % t]) >= 1 for t in range(6))
+    loss.backward()
+    grads = [p.grad for p in head.parameters() if p.grad is not None]
+    assert grads and all(bool(torch.isfinite(gr).all()) for gr in grads)
+    # tasks whose localisation loss is >= 1 contribute `loss` WITHOUT the IoU term, the others with it (reference :131-133)
+    want = 0.0
+    for t in range(6):
+        part = head.auto_loss(tb["task_%d/hm_loss" % t], tb["task_%d/loc_loss" % t], tb["task_%d/iou_aware_loss" % t])
+        if float(tb["task_%d/loc_loss" % t]) < 1:
+            part = part + tb["task_%d/iou_loss" % t] * head.iou_weight
+        want = want + float(part)
+    assert abs(float(loss) - want) <= 1e-5 * abs(want)

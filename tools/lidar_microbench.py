@@ -80,28 +80,11 @@ def main():
         x = torch.randn((rb.n_in, cin), device=dev)
         ks3 = rb.ksize
         w = torch.randn((cout, ks3[0], ks3[1], ks3[2], cin), device=dev) * 0.05
-        if os.environ.get("UD_MB_DEBUG_FLAGS"):
-            native.load().ud_debug_umma_flags(int(os.environ["UD_MB_DEBUG_FLAGS"]))
-        if os.environ.get("UD_MB_PROF"):
-            prof = torch.zeros(16, dtype=torch.int64, device=dev)
-            native.load().ud_debug_umma_prof(native.ptr(prof))
-            with torch.no_grad():
-                sparse.sparse_conv(x, w, None, rb)
-            torch.cuda.synchronize()
-            native.load().ud_debug_umma_prof(None)
-            names = ["mma_wait_a", "mma_wait_b", "mma_total", "tr_wait_raw", "tr_wait_a", "tr_total", "ld_wait_raw",
-                     "ld_total", "prologue", "epilogue", "cta_total", "ctas", "stages", "ld_wait_idx"]
-            pv = prof.cpu().tolist()
-            ctas, stages = max(1, pv[11]), max(1, pv[12])
-            print("  role cycles for %d->%d: ctas=%d stages=%d (per CTA %.0f)" % (cin, cout, ctas, stages, stages / ctas))
-            for nm, v in list(zip(names[:11], pv[:11])) + [(names[13], pv[13])]:
-                div = 2 if nm.startswith(("tr_", "ld_")) else 1      # two transform sets / loader groups report
-                print("    %-12s %10.0f cycles/CTA   %8.1f cycles/stage" % (nm, v / div / ctas, v / div / stages))
         with torch.no_grad():
             ms, out = timed(lambda: sparse.sparse_conv(x, w, None, rb))
         byt = rb.n_in * cin * 4 + rb.n_out * cout * 4 + rb.n_out * rb.K * 4 + rb.K * cin * cout * 4
         rows.append(("conv %s %d->%d N=%d P=%d" % (kind, cin, cout, rb.n_out, P), ms, byt, 2.0 * P * cin * cout))
-        if sparse.USE_TENSOR_CORES and native.load().ud_sparse_conv_tc_supported(rb.K, cin, cout, sparse.TC_VARIANT):
+        if sparse.USE_TENSOR_CORES and native.load().ud_sparse_conv_tc_supported(rb.K, cin, cout):
             sparse.USE_TENSOR_CORES = False
             with torch.no_grad():
                 ms2, out2 = timed(lambda: sparse.sparse_conv(x, w, None, rb))
