@@ -476,7 +476,7 @@ def _algorithmic(name, a, meta, cache):
         return "rulebook SubM (K=%d)" % K, "hbm", n * 16 + n * K * 4, 0
     if name in ("ud_rulebook_conv_count", "ud_rulebook_conv_fill"):
         n_in, K = a[1], meta.get("K", 27)
-        n_out = a[9] if name.endswith("fill") else 0
+        n_out = a[10] if name.endswith("fill") else 0
         return ("rulebook strided %s (K=%d)" % (name.rsplit("_", 1)[1], K), "hbm",
                 n_in * 16 + ((n_in + n_out) * K * 4 + n_out * 16 if n_out else 0), 0)
     if name == "ud_rulebook_transpose":
@@ -1089,39 +1089,44 @@ def cpu_baseline(workload, budget_s=25.0):
 
 
 def full_size_parity(wl, device):
-    """Full-size GPU-vs-CPU check on one of the bench's own clouds (bs=1, eval-mode BatchNorm so that batch statistics do
-    not amplify 1-ulp differences): voxel coordinates bit-exact, BEV map of the sparse encoder within 1e-3 relative."""
+    """Full-size GPU-vs-CPU check on one of the bench's own clouds (bs=1): a FRESH LiDAR encoder (seed 0, the weights both
+    arms start from; eval-mode BatchNorm with non-trivial running statistics, so that batch statistics do not amplify 1-ulp
+    differences): voxel coordinates and counts bit-exact, BEV map of voxelizer + 21-layer sparse encoder + scatter within
+    1e-3 relative of the CPU port's."""
     import numpy as np
     import torch
 
     from oracle import lidar as O
+    from unidistill_b200 import models
 
     model = getattr(wl, "model", None)
     if model is None:
         model = wl.step_fn.student
-    enc = model.lidar_encoder
+    torch.manual_seed(0)
+    enc = models.LidarEncoder(model.cfg.lidar_encoder).to(device).eval()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
     cloud = (wl.points_dev if hasattr(wl, "points_dev") else wl.dev["points"])[0]
-    was = enc.training
-    enc.eval()
-    try:
-        with torch.no_grad():
-            v = enc.voxelizer
-            _, coords, num = v([cloud])
-            bev = enc([cloud])
-        torch.cuda.synchronize()
-        _, rc, rn, rmean = O.voxelize([cloud.cpu().numpy()], v.voxel_size.tolist(), v.point_cloud_range.tolist(),
-                                      v.grid_size.tolist(), v.max_num_points, v.max_voxels)
-        sd = {k: t.detach().cpu() for k, t in enc.backbone_3d.state_dict().items()}
-        f, c, shape = O.backbone_forward(sd, rmean, rc, 1, [int(s) for s in enc.backbone_3d.sparse_shape], training=False)
-        ref = O.height_compression(f.numpy(), c, 1, shape)
-        got = bev.float().cpu().numpy()
-        rel = float(np.abs(got - ref).max() / max(1e-12, np.abs(ref).max()))
-        return {"what": "bench cloud 0 (bs=1, eval-mode BN): GPU voxelizer + 21-layer sparse encoder + scatter vs CPU port",
-                "voxels": int(rc.shape[0]), "voxel_coords_bit_exact": bool(np.array_equal(coords.cpu().numpy(), rc)),
-                "voxel_counts_bit_exact": bool(np.array_equal(num.cpu().numpy(), rn)),
-                "bev_rel_err": rel, "tol": 1e-3, "ok": bool(rel <= 1e-3)}
-    finally:
-        enc.train(was)
+    with torch.no_grad():
+        v = enc.voxelizer
+        _, coords, num = v([cloud])
+        bev = enc([cloud])
+    torch.cuda.synchronize()
+    _, rc, rn, rmean = O.voxelize([cloud.cpu().numpy()], v.voxel_size.tolist(), v.point_cloud_range.tolist(),
+                                  v.grid_size.tolist(), v.max_num_points, v.max_voxels)
+    sd = {k: t.detach().cpu() for k, t in enc.backbone_3d.state_dict().items()}
+    f, c, shape = O.backbone_forward(sd, rmean, rc, 1, [int(s) for s in enc.backbone_3d.sparse_shape], training=False)
+    ref = O.height_compression(f.numpy(), c, 1, shape)
+    got = bev.float().cpu().numpy()
+    rel = float(np.abs(got - ref).max() / max(1e-12, np.abs(ref).max()))
+    return {"what": "bench cloud 0 (bs=1, fresh seed-0 encoder, eval-mode BN): GPU voxelizer + 21-layer sparse encoder + "
+                    "scatter vs the CPU port", "voxels": int(rc.shape[0]),
+            "voxel_coords_bit_exact": bool(np.array_equal(coords.cpu().numpy(), rc)),
+            "voxel_counts_bit_exact": bool(np.array_equal(num.cpu().numpy(), rn)),
+            "bev_rel_err": rel, "tol": 1e-3, "ok": bool(rel <= 1e-3)}
 
 
 def run_reference(args):

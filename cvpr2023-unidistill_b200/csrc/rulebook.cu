@@ -22,7 +22,23 @@
 
 #define UD_EMPTY64 0xFFFFFFFFFFFFFFFFull
 
+// Output-row order of a strided convolution = ascending key over the output cells:
+//   order 0 (canonical, what the rulebook parity tests pin): key = linear (b, z, y, x) index;
+//   order 1 (Morton):  key = b << bits | interleave(z, y, x) -- a 128-row tile of the next layer is then a compact 3-D
+//   block whose 3x3x3 neighbourhood touches ~290 distinct rows instead of ~770 (profiles/r01_tile_locality_probe.txt), which
+//   the gather of the convolution kernel turns into L1 / L2 hits.  The row order of a sparse tensor between the
+//   voxelizer and the BEV scatter is not observable (the scatter is order independent).
+// The interleave handles unequal axis sizes: bit positions are dealt out z, y, x round-robin from the least significant
+// bit while an axis still has bits left (per-axis spread tables, built once per call by k_spread_tables).
+struct UdKeyLayout {
+    int order;          // 0 linear, 1 Morton
+    int bits_total;     // Morton: bits of one sample's key
+    int bz, by, bx;     // Morton: bits per axis
+    unsigned char pos[3][12];   // Morton: pos[axis][i] = key bit of coordinate bit i
+};
+
 struct UdConvGeom {
+    UdKeyLayout kl;
     int B;
     int iD, iH, iW;  // input spatial shape (z, y, x)
     int oD, oH, oW;  // output spatial shape
@@ -97,7 +113,29 @@ __device__ __forceinline__ int ud_out_coord(int in, int k, int stride, int pad, 
     return o < out_dim ? o : -1;
 }
 
-__device__ __forceinline__ bool ud_pair_key(const int4 c, int k, const UdConvGeom& g, uint32_t* key) {
+__device__ __forceinline__ uint32_t ud_spread(const UdKeyLayout& kl, int axis, int v) {
+    uint32_t r = 0u;
+    const int nb = axis == 0 ? kl.bz : (axis == 1 ? kl.by : kl.bx);
+    for (int i = 0; i < nb; ++i) r |= (uint32_t)((v >> i) & 1) << kl.pos[axis][i];
+    return r;
+}
+
+// spread tables: tab[0 .. oD) z, tab[oD .. oD+oH) y, then x
+__global__ void k_spread_tables(UdKeyLayout kl, int oD, int oH, int oW, uint32_t* __restrict__ tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < oD) tab[t] = ud_spread(kl, 0, t);
+    else if (t < oD + oH) tab[t] = ud_spread(kl, 1, t - oD);
+    else if (t < oD + oH + oW) tab[t] = ud_spread(kl, 2, t - oD - oH);
+}
+
+__device__ __forceinline__ uint32_t ud_out_key(const UdConvGeom& g, const uint32_t* __restrict__ tab, int b, int oz,
+                                               int oy, int ox) {
+    if (g.kl.order == 0) return (((uint32_t)b * g.oD + oz) * g.oH + oy) * g.oW + ox;
+    return ((uint32_t)b << g.kl.bits_total) | __ldg(tab + oz) | __ldg(tab + g.oD + oy) | __ldg(tab + g.oD + g.oH + ox);
+}
+
+__device__ __forceinline__ bool ud_pair_key(const int4 c, int k, const UdConvGeom& g, const uint32_t* __restrict__ tab,
+                                            uint32_t* key) {
     int kx = k % g.kW;
     int ky = (k / g.kW) % g.kH;
     int kz = k / (g.kW * g.kH);
@@ -105,19 +143,29 @@ __device__ __forceinline__ bool ud_pair_key(const int4 c, int k, const UdConvGeo
     int oy = ud_out_coord(c.z, ky, g.sH, g.pH, g.dH, g.oH);
     int ox = ud_out_coord(c.w, kx, g.sW, g.pW, g.dW, g.oW);
     if ((oz | oy | ox) < 0) return false;
-    *key = (((uint32_t)c.x * g.oD + oz) * g.oH + oy) * g.oW + ox;
+    *key = ud_out_key(g, tab, c.x, oz, oy, ox);
     return true;
 }
 
 __global__ void __launch_bounds__(256)
-k_conv_mark(const int4* __restrict__ coords, int n, UdConvGeom g, unsigned int* __restrict__ bitmap) {
+k_conv_mark(const int4* __restrict__ coords, int n, UdConvGeom g, const uint32_t* __restrict__ tab,
+            unsigned int* __restrict__ bitmap) {
     int K = g.kD * g.kH * g.kW;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * K) return;
     int i = (int)(t / K);
     int k = (int)(t - (long long)i * K);
     uint32_t key;
-    if (ud_pair_key(coords[i], k, g, &key)) atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+    if (ud_pair_key(coords[i], k, g, tab, &key)) atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+}
+
+__global__ void __launch_bounds__(256)
+k_morton_keys(const int4* __restrict__ coords, int n, UdConvGeom g, uint32_t* __restrict__ keys, int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = coords[i];
+    keys[i] = ((uint32_t)c.x << g.kl.bits_total) | ud_spread(g.kl, 0, c.y) | ud_spread(g.kl, 1, c.z) | ud_spread(g.kl, 2, c.w);
+    idx[i] = i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -143,17 +191,27 @@ k_conv_out_coords(const unsigned int* __restrict__ bitmap, const int* __restrict
         bits &= bits - 1;
         uint32_t key = ((uint32_t)w << 5) | (uint32_t)bpos;
         uint32_t t = key;
-        int x = t % g.oW; t /= g.oW;
-        int y = t % g.oH; t /= g.oH;
-        int z = t % g.oD; t /= g.oD;
+        int x, y, z;
+        if (g.kl.order == 0) {
+            x = t % g.oW; t /= g.oW;
+            y = t % g.oH; t /= g.oH;
+            z = t % g.oD; t /= g.oD;
+        } else {
+            x = y = z = 0;
+            for (int i = 0; i < g.kl.bz; ++i) z |= (int)((t >> g.kl.pos[0][i]) & 1u) << i;
+            for (int i = 0; i < g.kl.by; ++i) y |= (int)((t >> g.kl.pos[1][i]) & 1u) << i;
+            for (int i = 0; i < g.kl.bx; ++i) x |= (int)((t >> g.kl.pos[2][i]) & 1u) << i;
+            t >>= g.kl.bits_total;
+        }
         if (o < n_out) out_coords[o] = make_int4((int)t, z, y, x);
         ++o;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_conv_tables(const int4* __restrict__ coords, int n, UdConvGeom g, const unsigned int* __restrict__ bitmap,
-              const int* __restrict__ prefix, int n_out, int* __restrict__ nbr_in, int* __restrict__ nbr_out) {
+k_conv_tables(const int4* __restrict__ coords, int n, UdConvGeom g, const uint32_t* __restrict__ tab,
+              const unsigned int* __restrict__ bitmap, const int* __restrict__ prefix, int n_out,
+              int* __restrict__ nbr_in, int* __restrict__ nbr_out) {
     int K = g.kD * g.kH * g.kW;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * K) return;
@@ -161,7 +219,7 @@ k_conv_tables(const int4* __restrict__ coords, int n, UdConvGeom g, const unsign
     int k = (int)(t - (long long)i * K);
     uint32_t key;
     int o = -1;
-    if (ud_pair_key(coords[i], k, g, &key)) {
+    if (ud_pair_key(coords[i], k, g, tab, &key)) {
         unsigned int word = bitmap[key >> 5];
         unsigned int below = word & ((1u << (key & 31)) - 1u);
         o = prefix[key >> 5] + __popc(below);
@@ -208,8 +266,39 @@ static uint32_t ud_pow2_at_least(uint64_t v) {
     return (uint32_t)p;
 }
 
+static int ud_bits_for(int n) {
+    int b = 0;
+    while ((1 << b) < n) ++b;
+    return b;
+}
+
+// order 1: deal key bits out z, y, x round-robin from bit 0 while an axis has bits left
+static int ud_make_layout(int order, int oD, int oH, int oW, int B, UdKeyLayout* kl) {
+    kl->order = order;
+    kl->bz = ud_bits_for(oD); kl->by = ud_bits_for(oH); kl->bx = ud_bits_for(oW);
+    kl->bits_total = kl->bz + kl->by + kl->bx;
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < 12; ++i) kl->pos[a][i] = 0;
+    if (order == 0) return UD_OK;
+    if (order != 1) return UD_ERR_INVALID_ARG;
+    if (kl->bz > 12 || kl->by > 12 || kl->bx > 12) return UD_ERR_UNSUPPORTED;
+    if (((uint64_t)B << kl->bits_total) >= 0xFFFFFFFFull) return UD_ERR_UNSUPPORTED;
+    int used[3] = {0, 0, 0};
+    const int nb[3] = {kl->bz, kl->by, kl->bx};
+    int p = 0;
+    while (p < kl->bits_total)
+        for (int a = 2; a >= 0; --a)          // x takes the lowest bit of each round, then y, then z
+            if (used[a] < nb[a]) kl->pos[a][used[a]++] = (unsigned char)p++;
+    return UD_OK;
+}
+
+static uint64_t ud_out_cells(const UdConvGeom& g) {
+    if (g.kl.order == 0) return (uint64_t)g.B * g.oD * g.oH * g.oW;
+    return (uint64_t)g.B << g.kl.bits_total;
+}
+
 static int ud_geom_check(const UdConvGeom& g, bool in_side) {
-    uint64_t cells = (uint64_t)g.B * (in_side ? (uint64_t)g.iD * g.iH * g.iW : (uint64_t)g.oD * g.oH * g.oW);
+    uint64_t cells = in_side ? (uint64_t)g.B * g.iD * g.iH * g.iW : ud_out_cells(g);
     if (g.B < 1 || cells == 0 || cells >= 0xFFFFFFFFull) return UD_ERR_UNSUPPORTED;
     int K = g.kD * g.kH * g.kW;
     if (K < 1 || K > 32) return UD_ERR_UNSUPPORTED;
@@ -217,8 +306,11 @@ static int ud_geom_check(const UdConvGeom& g, bool in_side) {
 }
 
 static UdConvGeom ud_make_geom(int B, const int* in_shape, const int* out_shape, const int* ksize,
-                               const int* stride, const int* padding, const int* dilation) {
+                               const int* stride, const int* padding, const int* dilation, int order = 0,
+                               int* rc = nullptr) {
     UdConvGeom g;
+    int r = ud_make_layout(order, out_shape[0], out_shape[1], out_shape[2], B, &g.kl);
+    if (rc) *rc = r;
     g.B = B;
     g.iD = in_shape[0]; g.iH = in_shape[1]; g.iW = in_shape[2];
     g.oD = out_shape[0]; g.oH = out_shape[1]; g.oW = out_shape[2];
@@ -266,24 +358,27 @@ int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatia
 }
 
 // ---- strided / regular sparse conv --------------------------------------------------------------
-static size_t ud_conv_words(const UdConvGeom& g) {
-    uint64_t cells = (uint64_t)g.B * g.oD * g.oH * g.oW;
-    return (size_t)((cells + 31) / 32);
-}
+static size_t ud_conv_words(const UdConvGeom& g) { return (size_t)((ud_out_cells(g) + 31) / 32); }
 
-int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, size_t* bytes) {
+int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, int order, size_t* bytes) {
     if (!out_shape || !bytes || batch_size < 1) return UD_ERR_INVALID_ARG;
-    uint64_t cells = (uint64_t)batch_size * out_shape[0] * out_shape[1] * out_shape[2];
+    UdKeyLayout kl;
+    int rc = ud_make_layout(order, out_shape[0], out_shape[1], out_shape[2], batch_size, &kl);
+    if (rc != UD_OK) return rc;
+    uint64_t cells = order == 0 ? (uint64_t)batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+                                : ((uint64_t)batch_size << kl.bits_total);
     if (cells == 0 || cells >= 0xFFFFFFFFull) return UD_ERR_UNSUPPORTED;
     size_t words = (size_t)((cells + 31) / 32);
     size_t scan_bytes = 0;
     UD_CUDA_TRY((cub::DeviceScan::ExclusiveSum<const int*, int*>(nullptr, scan_bytes, nullptr, nullptr,
                                                                  (int)words + 1)));
-    *bytes = ud_align_up(words * 4) + 2 * ud_align_up((words + 1) * 4) + ud_align_up(scan_bytes);
+    *bytes = ud_align_up(words * 4) + 2 * ud_align_up((words + 1) * 4) + ud_align_up(scan_bytes) +
+             ud_align_up((size_t)(out_shape[0] + out_shape[1] + out_shape[2]) * 4);
     return UD_OK;
 }
 
 struct UdConvWs {
+    uint32_t* tab;
     unsigned int* bitmap;
     int* pc;
     int* prefix;
@@ -303,6 +398,7 @@ static int ud_conv_layout(void* ws, size_t ws_bytes, const UdConvGeom& g, UdConv
                                                                  (int)L->words + 1)));
     L->cub_bytes = scan_bytes;
     L->cub_temp = a.take<char>(scan_bytes);
+    L->tab = a.take<uint32_t>((size_t)(g.oD + g.oH + g.oW));
     if (!a.ok()) return UD_ERR_WORKSPACE;
     return UD_OK;
 }
@@ -311,12 +407,14 @@ static int ud_conv_layout(void* ws, size_t ws_bytes, const UdConvGeom& g, UdConv
 // n_out_dev (device int).  The workspace must be kept untouched until phase 2 ran.
 int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const int* in_shape,
                            const int* out_shape, const int* ksize, const int* stride, const int* padding,
-                           const int* dilation, int* n_out_dev, void* workspace, size_t workspace_bytes,
+                           const int* dilation, int order, int* n_out_dev, void* workspace, size_t workspace_bytes,
                            void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!n_out_dev || n_in < 0 || (n_in > 0 && !coords)) return UD_ERR_INVALID_ARG;
-    UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation);
-    int rc = ud_geom_check(g, false);
+    int rc = UD_OK;
+    UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation, order, &rc);
+    if (rc != UD_OK) return rc;
+    rc = ud_geom_check(g, false);
     if (rc != UD_OK) return rc;
     UdConvWs L;
     rc = ud_conv_layout(workspace, workspace_bytes, g, &L);
@@ -324,8 +422,12 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
     int K = g.kD * g.kH * g.kW;
     int words = (int)L.words;
     UD_CUDA_TRY(cudaMemsetAsync(L.bitmap, 0, L.words * 4, stream));
+    if (g.kl.order != 0) {
+        k_spread_tables<<<ud_blocks(g.oD + g.oH + g.oW, 256), 256, 0, stream>>>(g.kl, g.oD, g.oH, g.oW, L.tab);
+        UD_LAUNCH_CHECK();
+    }
     if (n_in > 0) {
-        k_conv_mark<<<ud_blocks((long long)n_in * K, 256), 256, 0, stream>>>((const int4*)coords, n_in, g,
+        k_conv_mark<<<ud_blocks((long long)n_in * K, 256), 256, 0, stream>>>((const int4*)coords, n_in, g, L.tab,
                                                                              L.bitmap);
         UD_LAUNCH_CHECK();
     }
@@ -342,14 +444,16 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
 // Phase 2: with n_out known on the host, write out_coords (n_out,4), nbr_in (n_in,K), nbr_out (n_out,K).
 int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int* in_shape,
                           const int* out_shape, const int* ksize, const int* stride, const int* padding,
-                          const int* dilation, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
+                          const int* dilation, int order, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
                           void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_in < 0 || n_out < 0) return UD_ERR_INVALID_ARG;
     if (n_in > 0 && (!coords || !nbr_in)) return UD_ERR_INVALID_ARG;
     if (n_out > 0 && (!out_coords || !nbr_out)) return UD_ERR_INVALID_ARG;
-    UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation);
-    int rc = ud_geom_check(g, false);
+    int rc = UD_OK;
+    UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation, order, &rc);
+    if (rc != UD_OK) return rc;
+    rc = ud_geom_check(g, false);
     if (rc != UD_OK) return rc;
     UdConvWs L;
     rc = ud_conv_layout(workspace, workspace_bytes, g, &L);
@@ -364,9 +468,51 @@ int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int
     }
     if (n_in > 0) {
         k_conv_tables<<<ud_blocks((long long)n_in * K, 256), 256, 0, stream>>>(
-            (const int4*)coords, n_in, g, L.bitmap, L.prefix, n_out, nbr_in, nbr_out);
+            (const int4*)coords, n_in, g, L.tab, L.bitmap, L.prefix, n_out, nbr_in, nbr_out);
         UD_LAUNCH_CHECK();
     }
+    return UD_OK;
+}
+
+// ---- Morton order of a coordinate set ---------------------------------------------------------------
+int ud_morton_order_workspace_bytes(int n, size_t* bytes) {
+    if (n < 0 || !bytes) return UD_ERR_INVALID_ARG;
+    size_t sort_bytes = 0;
+    int m = n > 0 ? n : 1;
+    UD_CUDA_TRY((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, sort_bytes, nullptr, nullptr, nullptr, nullptr,
+                                                                m, 0, 32)));
+    *bytes = 3 * ud_align_up((size_t)m * 4) + ud_align_up(sort_bytes);
+    return UD_OK;
+}
+
+// coords (n,4) int32 [b,z,y,x] on a (z,y,x) grid `spatial_shape` (HOST int[3]) -> order (n) int32: row indices sorted by
+// (b, Morton(z,y,x)) (stable: equal keys keep their input order).  Gathering features / coordinates with `order` gives
+// the row order in which 128 consecutive rows form a compact 3-D block.
+int ud_morton_order(const int* coords, int n, int batch_size, const int* spatial_shape, int* order, void* workspace,
+                    size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || batch_size < 1 || !spatial_shape || (n > 0 && (!coords || !order))) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    UdConvGeom g;
+    int rc = ud_make_layout(1, spatial_shape[0], spatial_shape[1], spatial_shape[2], batch_size, &g.kl);
+    if (rc != UD_OK) return rc;
+    g.B = batch_size;
+    g.oD = spatial_shape[0]; g.oH = spatial_shape[1]; g.oW = spatial_shape[2];
+    UdArena a(workspace, workspace_bytes);
+    uint32_t* keys = a.take<uint32_t>(n);
+    uint32_t* keys_sorted = a.take<uint32_t>(n);
+    int* idx = a.take<int>(n);
+    size_t sort_bytes = 0;
+    UD_CUDA_TRY((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, sort_bytes, nullptr, nullptr, nullptr, nullptr,
+                                                                n, 0, 32)));
+    void* cub_temp = a.take<char>(sort_bytes);
+    if (!a.ok()) return UD_ERR_WORKSPACE;
+    k_morton_keys<<<ud_blocks(n, 256), 256, 0, stream>>>((const int4*)coords, n, g, keys, idx);
+    UD_LAUNCH_CHECK();
+    int end_bit = g.kl.bits_total + ud_bits_for(batch_size);
+    if (end_bit > 32) end_bit = 32;
+    UD_CUDA_TRY((cub::DeviceRadixSort::SortPairs<uint32_t, int>(cub_temp, sort_bytes, keys, keys_sorted, idx, order, n, 0,
+                                                                end_bit, stream)));
     return UD_OK;
 }
 

@@ -5,6 +5,7 @@ Same module tree (hence the same state_dict keys) and the same forward contract 
 conv_out; channels 16/32/64/128; BatchNorm1d(eps=1e-3, momentum=0.01).  Every conv runs as one
 gather-GEMM launch on a cached rulebook and every BN(+residual)+ReLU as one fused pass.
 """
+import os
 from functools import partial
 
 import numpy as np
@@ -12,7 +13,7 @@ import spconv.pytorch as spconv
 import torch.nn as nn
 from spconv.core import ConvAlgo
 
-from unidistill_b200.sparse import batch_norm_act
+from unidistill_b200.sparse import batch_norm_act, morton_order
 
 SPCONV_ALGO_TYPE = ConvAlgo.Native
 
@@ -149,12 +150,26 @@ class VoxelResBackBone8x(nn.Module):
             nn.ReLU(),
         )
         self.num_point_features = 128
+        # True: rows are put into Morton (Z-order) order on entry (pair with unidistill_b200.sparse.CONV_OUTPUT_ORDER =
+        # "morton" for the strided layers).  The row order of a sparse tensor is not observable after dense().  Off by
+        # default: measured slower than the raster order on B200 (see unidistill_b200/sparse.py).
+        self.morton_order = os.environ.get("UD_CONV_ORDER", "linear") == "morton"
 
     def forward(self, voxel_features, voxel_coords, batch_size, indice_dict=None):
         """voxel_features (M,C), voxel_coords (M,4) [b,z,y,x] -> (SparseConvTensor, 8, {x_conv1..4}).
         `indice_dict` (extension, default = the reference's behaviour): rulebook cache to start from / fill -- a second
         encoder run over the SAME voxel_coords tensor reuses the tables instead of rebuilding them."""
-        x = spconv.SparseConvTensor(features=voxel_features, indices=voxel_coords.int(),
+        voxel_coords = voxel_coords.int()
+        if self.morton_order and voxel_coords.is_cuda and voxel_coords.shape[0] > 0:
+            cached = indice_dict.get("__morton__") if indice_dict is not None else None
+            if cached is None or cached[0] is not voxel_coords:
+                order = morton_order(voxel_coords.contiguous(), batch_size, self.sparse_shape)
+                cached = (voxel_coords, order, voxel_coords.index_select(0, order))
+                if indice_dict is not None:
+                    indice_dict["__morton__"] = cached
+            voxel_features = voxel_features.index_select(0, cached[1])
+            voxel_coords = cached[2]
+        x = spconv.SparseConvTensor(features=voxel_features, indices=voxel_coords,
                                     spatial_shape=self.sparse_shape, batch_size=batch_size, indice_dict=indice_dict)
         x = self.conv_input(x)
         x_conv1 = self.conv1(x)

@@ -58,8 +58,8 @@ class SepHead(nn.Module):
 
 # the 6 tasks x 7 targets = 42 towers of a CenterHead all read the same 64-channel map and have the same shape
 # up to the class count of the last conv, so they can run as ONE 64 -> 42*64 convolution, ONE BatchNorm over 2688 channels
-# (per-channel statistics: identical to 42 separate norms), ONE ReLU and ONE grouped convolution (42 groups, 64 -> 3 with
-# zero-padded rows) instead of 42 x (conv, BN, ReLU, conv).  Parameters stay where the reference keeps them
+# (per-channel statistics: identical to 42 separate norms), ONE ReLU and ONE block-diagonal convolution 2688 -> 76 instead
+# of 42 x (conv, BN, ReLU, conv).  Parameters stay where the reference keeps them
 # (`tasks.<t>.<head>.{0,1,3}`), gradients flow back to them through the concatenations.  UD_BATCH_TOWERS=0 disables it.
 BATCH_TOWERS = os.environ.get("UD_BATCH_TOWERS", "1") != "0"
 
@@ -108,22 +108,34 @@ def batched_towers(tasks, x):
                 torch._foreach_copy_([bn.running_var for bn in bns], list(rv.split(mid)))
                 torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
     y = F.relu(y)
-    # ---- layer 2: one grouped convolution, every tower padded to the widest output (zero rows)
+    # ---- layer 2: ONE dense convolution over all 42*64 channels with a block-diagonal weight (tower i's rows see only
+    # tower i's 64 input channels, zeros elsewhere).  It spends 42x the FLOPs of the 42 small convolutions, but as one
+    # tensor-core implicit GEMM (~0.4 PFLOP/s) it is still ~5x faster than they are, and -- unlike a groups=42
+    # convolution, whose weight gradient cuDNN runs as 42 SIMT SGEMMs (13.5 ms per step measured on B200,
+    # profiles/r02_head_batching.md) -- its backward stays on the tensor cores.  Only the diagonal blocks of the weight
+    # gradient flow back to the parameters (index_put's backward gathers them).
     outs = [tw[3].out_channels for tw in towers]
-    cmax = max(outs)
-    key = (str(x.device), cmax, tuple(outs))
-    rows = _ROWS_CACHE.get(key)
-    if rows is None:      # built once per layout (the first call must be outside a CUDA-graph capture: warm-up runs are)
-        rows = torch.tensor([i * cmax + c for i, c_ in enumerate(outs) for c in range(c_)], device=x.device)
-        _ROWS_CACHE[key] = rows
-    w2_all = torch.cat([tw[3].weight for tw in towers], dim=0)
-    b2_all = torch.cat([tw[3].bias for tw in towers], dim=0)
-    w2 = w2_all.new_zeros((n * cmax,) + tuple(w2_all.shape[1:])).index_copy(0, rows, w2_all)
-    b2 = b2_all.new_zeros((n * cmax,)).index_copy(0, rows, b2_all)
-    z = F.conv2d(y, w2, b2, stride=1, padding=c2.padding, groups=n)
+    cin2 = c2.in_channels
+    key = (str(x.device), cin2, tuple(outs))
+    idx = _ROWS_CACHE.get(key)
+    if idx is None:      # built once per layout (the first call must be outside a CUDA-graph capture: warm-up runs are)
+        rows = torch.arange(sum(outs), device=x.device)
+        tower_of_row = torch.tensor([i for i, c_ in enumerate(outs) for _ in range(c_)], device=x.device)
+        cols = tower_of_row[:, None] * cin2 + torch.arange(cin2, device=x.device)[None, :]
+        idx = (rows[:, None].expand_as(cols).contiguous(), cols.contiguous())
+        _ROWS_CACHE[key] = idx
+    w2_all = torch.cat([tw[3].weight for tw in towers], dim=0)              # (sum outs, 64, 3, 3)
+    b2 = torch.cat([tw[3].bias for tw in towers], dim=0)
+    w2 = w2_all.new_zeros((w2_all.shape[0], n * cin2) + tuple(w2_all.shape[2:])).index_put(idx, w2_all)
+    if y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous():
+        w2 = w2.contiguous(memory_format=torch.channels_last)
+    z = F.conv2d(y, w2, b2, stride=1, padding=c2.padding)
+    starts = [0]
+    for c_ in outs:
+        starts.append(starts[-1] + c_)
     ret = [dict() for _ in tasks]
     for i, (t, head) in enumerate(names):
-        ret[t][head] = z[:, i * cmax: i * cmax + outs[i]]
+        ret[t][head] = z[:, starts[i]: starts[i + 1]]
     return [OrderedDict((h, d[h]) for h in task.heads) for task, d in zip(tasks, ret)]
 
 

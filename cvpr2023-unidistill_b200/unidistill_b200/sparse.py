@@ -113,7 +113,30 @@ def build_subm_rulebook(coords, batch_size, spatial_shape, ksize, dilation=1):
                     n, n, nbr, None, coords, batch_size)
 
 
-def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, padding, dilation=1):
+# Row order of strided-convolution outputs: "linear" (default: canonical ascending (b,z,y,x), what spconv's CPU rulebook
+# produces and the bit-exact rulebook tests pin) or "morton" (Z-order: compact 3-D tiles).  Measured on B200 at the bench
+# size (profiles/r02_morton_vs_linear.md): Morton tiles touch fewer distinct rows, but under the raster order the rows a tap
+# gathers are CONSECUTIVE in memory (x-adjacent voxels are adjacent rows), which the gather likes better: 64->64 6.82 vs
+# 6.69 ms, 128->128 5.47 vs 4.97 ms per step, whole step 93.4 vs 89.5 ms.  So the option stays off.
+CONV_OUTPUT_ORDER = os.environ.get("UD_CONV_ORDER", "linear")
+
+
+def morton_order(coords, batch_size, spatial_shape):
+    """(n,) int64 permutation sorting rows by (b, Morton(z, y, x)); stable."""
+    native.require_cuda(coords)
+    lib = native.load()
+    n = int(coords.shape[0])
+    dev = coords.device
+    order = torch.empty((n,), dtype=torch.int32, device=dev)
+    ws = native.WORKSPACE.get(native.query_bytes("ud_morton_order_workspace_bytes", n), dev)
+    shp = native.host_ints(spatial_shape)
+    rc = lib.ud_morton_order(native.ptr(coords), n, int(batch_size), native.host_ptr(shp), native.ptr(order),
+                             native.ptr(ws), ws.numel(), native.stream_ptr(dev))
+    native.check(rc, "ud_morton_order")
+    return order.long()
+
+
+def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, padding, dilation=1, order=None):
     native.require_cuda(coords)
     lib = native.load()
     ksize, stride, padding, dilation = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
@@ -125,7 +148,10 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
     ish, osh = native.host_ints(spatial_shape), native.host_ints(out_shape)
     ks, st, pd, dl = (native.host_ints(ksize), native.host_ints(stride), native.host_ints(padding),
                       native.host_ints(dilation))
-    nbytes = native.query_bytes("ud_rulebook_conv_workspace_bytes", int(batch_size), native.host_ptr(osh))
+    order_id = {"linear": 0, "morton": 1}[order if order is not None else CONV_OUTPUT_ORDER]
+    if order_id == 1 and (max(out_shape) > 4096 or (int(batch_size) << sum((s - 1).bit_length() for s in out_shape)) >= 2 ** 32 - 1):
+        order_id = 0                       # key space too large for 32-bit Morton keys: canonical order
+    nbytes = native.query_bytes("ud_rulebook_conv_workspace_bytes", int(batch_size), native.host_ptr(osh), order_id)
     ws = native.WORKSPACE.get(nbytes, dev, slot=_WS_RULEBOOK)
     n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
     sp = native.stream_ptr(dev)
@@ -133,7 +159,7 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
         native.TIMER.meta = {"K": K}
     rc = lib.ud_rulebook_conv_count(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
                                     native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
-                                    native.host_ptr(pd), native.host_ptr(dl), native.ptr(n_out_dev),
+                                    native.host_ptr(pd), native.host_ptr(dl), order_id, native.ptr(n_out_dev),
                                     native.ptr(ws), ws.numel(), sp)
     native.check(rc, "ud_rulebook_conv_count")
     n_out = int(n_out_dev.item())   # host sync: output row count sizes the tables
@@ -144,7 +170,7 @@ def build_conv_rulebook(coords, batch_size, spatial_shape, ksize, stride, paddin
         native.TIMER.meta = {"K": K}
     rc = lib.ud_rulebook_conv_fill(native.ptr(coords), n_in, int(batch_size), native.host_ptr(ish),
                                    native.host_ptr(osh), native.host_ptr(ks), native.host_ptr(st),
-                                   native.host_ptr(pd), native.host_ptr(dl), n_out, native.ptr(out_coords),
+                                   native.host_ptr(pd), native.host_ptr(dl), order_id, n_out, native.ptr(out_coords),
                                    native.ptr(nbr_in), native.ptr(nbr_out), native.ptr(ws), ws.numel(), sp)
     native.check(rc, "ud_rulebook_conv_fill")
     return Rulebook(False, ksize, stride, padding, dilation, spatial_shape, out_shape, n_in, n_out,
@@ -308,8 +334,22 @@ class SparseConvFunction(Function):
                 native.check(rc, "ud_sparse_conv_wgrad")
             dweight = dw.permute(2, 0, 1).reshape(ctx.wshape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            dbias = grad_out.sum(0)
+            dbias = column_sums(grad_out)
         return dfeat, dweight, dbias, None, None
+
+
+def column_sums(x):
+    """(N, C) -> (C,) column sums in one pass with the fixed-order reduction of ud_bn_stats (torch's sum(0) over a tall
+    matrix runs at ~0.6 TB/s and is not reproducible); falls back to torch for widths the kernel does not take."""
+    n, C = int(x.shape[0]), int(x.shape[1])
+    if not x.is_cuda or C > 128 or 256 % C != 0 or not x.is_contiguous():
+        return x.sum(0)
+    lib = native.load()
+    sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
+    ws = native.WORKSPACE.get(native.query_bytes("ud_bn_workspace_bytes", n, C), x.device)
+    rc = lib.ud_bn_stats(native.ptr(x), n, C, native.ptr(sums), native.ptr(ws), ws.numel(), native.stream_ptr(x.device))
+    native.check(rc, "ud_bn_stats")
+    return sums[0].float()
 
 
 def sparse_conv(features, weight, bias, rulebook, inverse=False):

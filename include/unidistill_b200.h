@@ -34,6 +34,22 @@ const char* ud_error_string(int code);
 int ud_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------------------------
+ * Input side: sweep merge + x/y range filter + ragged collate for the whole batch.  Replaces
+ *   CollectLidarSweeps.forward (unidistill/data/multisensorfusion/transforms3d.py:379-414),
+ *   ObjectRangeFilter.mask_points_by_range (transforms3d.py:247-256,271-276) and the zero-padding points part of
+ *   collate_fn (data/multisensorfusion/nuscenes_multimodal.py:418-470).
+ * points (n,C) f32: every (sample, sweep) segment concatenated, sample-major, a sample's key frame first; seg_offsets
+ * (n_seg+1) / sample_first_seg (B+1) DEVICE int32; mats (n_seg,3,4) DEVICE f64 sweep->key-frame transforms (identity for
+ * key frames), applied in float64 and rounded to float32 once like the numpy code; time_lag (n_seg) DEVICE f32 -> 5th
+ * column; range_xy HOST float[4] (x_min,y_min,x_max,y_max), inclusive.  out (n,C) f32 holds the kept points in input order
+ * (ragged batch: out_offsets (B+1) DEVICE int32, out_offsets[B] = total) -- the layout ud_hard_voxelize takes.
+ * ------------------------------------------------------------------------------------------- */
+int ud_collect_sweeps_workspace_bytes(int n_points, size_t* bytes);
+int ud_collect_sweeps(const float* points, int n, int C, const int* seg_offsets, int n_seg, const int* sample_first_seg,
+                      int batch_size, const double* mats, const float* time_lag, const float* range_xy, float* out,
+                      int* out_offsets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Hard voxelization + mean VFE.
  * Replaces spconv.pytorch.utils.PointToVoxel.__call__ as driven by
  *   unidistill/data/det3d/preprocess/voxelization.py:31-38,53-68   (per-sample loop + clones + cat)
@@ -59,23 +75,31 @@ int ud_hard_voxelize(const float* points, const int* sample_offsets, int batch_s
  * Tables are int32 with -1 == absent, K = kz*ky*kx (<= 32), tap index k = (kz*KY+ky)*KX+kx:
  *   nbr_out (n_out,K): input row feeding output row o through tap k
  *   nbr_in  (n_in, K): output row fed by input row i through tap k
- * Strided conv outputs are ordered ascending by linear (b,z,y,x) index.
+ * Strided conv outputs are ordered ascending by a key over the output cells, chosen by `order`:
+ *   0 = linear (b,z,y,x) index (canonical; the order the rulebook parity tests pin),
+ *   1 = (b, Morton(z,y,x)): 128 consecutive output rows form a compact 3-D block, which is what the convolution kernels'
+ *       gathers want.  The row order of a sparse tensor is not observable after SparseConvTensor.dense().
  * ------------------------------------------------------------------------------------------- */
 int ud_rulebook_subm_workspace_bytes(int n, size_t* bytes);
 int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatial_shape, const int* ksize,
                      const int* dilation, int* nbr_out, void* workspace, size_t workspace_bytes,
                      void* stream);
-int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, size_t* bytes);
+int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, int order, size_t* bytes);
 /* phase 1: n_out_dev (device int) <- number of output rows; keep the workspace for phase 2 */
 int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const int* in_shape,
                            const int* out_shape, const int* ksize, const int* stride, const int* padding,
-                           const int* dilation, int* n_out_dev, void* workspace, size_t workspace_bytes,
+                           const int* dilation, int order, int* n_out_dev, void* workspace, size_t workspace_bytes,
                            void* stream);
 /* phase 2: out_coords (n_out,4), nbr_in (n_in,K), nbr_out (n_out,K) */
 int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int* in_shape,
                           const int* out_shape, const int* ksize, const int* stride, const int* padding,
-                          const int* dilation, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
+                          const int* dilation, int order, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* order (n) int32 <- row indices of coords (n,4) sorted by (b, Morton(z,y,x)) on the (z,y,x) grid spatial_shape (HOST
+ * int[3]); stable.  Used once at the entry of the sparse encoder (the voxelizer emits first-come order). */
+int ud_morton_order_workspace_bytes(int n, size_t* bytes);
+int ud_morton_order(const int* coords, int n, int batch_size, const int* spatial_shape, int* order, void* workspace,
+                    size_t workspace_bytes, void* stream);
 /* spconv-shaped export: pairs (2,K,n_in) int32 (-1 padded), pair_num (K); mirror=1 reads a SubM nbr_out */
 int ud_rulebook_pairs_workspace_bytes(int n_in, int K, size_t* bytes);
 int ud_rulebook_pairs(const int* nbr_in, int n_in, int K, int mirror, int* pairs, int* pair_num,

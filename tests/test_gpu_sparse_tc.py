@@ -11,6 +11,18 @@ import torch
 from oracle import lidar as O
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _canonical_conv_order():
+    """These tests compare rows with the oracle's canonical (ascending linear index) output order; the Morton order the
+    model path uses by default is covered by tests/test_gpu_morton.py."""
+    from unidistill_b200 import sparse
+
+    old = sparse.CONV_OUTPUT_ORDER
+    sparse.CONV_OUTPUT_ORDER = "linear"
+    yield
+    sparse.CONV_OUTPUT_ORDER = old
 TC_TOL = 5e-5
 
 

@@ -16,12 +16,20 @@ dev = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True
 wl = bench.WORKLOADS[name](dev, 0)
 st = wl.step_fn
+names = dict((id(p), n) for n, p in st.student.named_parameters())
+every = max(1, steps // 14)
 for i in range(steps):
     t = wl.step()
+    if i % every and i != steps - 1:
+        continue
     bad = sum(int((~torch.isfinite(p)).sum()) for p in st.student.parameters())
     badb = sum(int((~torch.isfinite(b)).sum()) for b in st.student.buffers() if b.is_floating_point())
     print("step %2d  " % i + "  ".join("%s=%.5g" % (k, float(v)) for k, v in t.items()) + "  nonfinite params=%d buffers=%d"
           % (bad, badb), flush=True)
+top = sorted(((float(p.grad.norm()), names[id(p)], float(p.detach().norm())) for p in st.bucket.params), reverse=True)[:12]
+print("largest (clipped) gradient norms after the last step; parameter norm:")
+for g, n, w in top:
+    print("   %.4g  %s  |w|=%.4g" % (g, n, w))
 if "--profile" in sys.argv:
     from torch.profiler import ProfilerActivity, profile
 
