@@ -267,6 +267,56 @@ def golden_proposals():
           "train-mode", [out["train_pred_boxes_%d" % b].shape[0] for b in range(B)])
 
 
+def _input_side_samples(seed=31, B=3):
+    """Synthetic per-sample dicts in the layout the reference's dataset hands to its transforms."""
+    rng = np.random.default_rng(seed)
+
+    def pose(yaw, t):
+        m = np.eye(4)
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        m[:2, :2] = [[c, -s_], [s_, c]]
+        m[:3, 3] = t
+        return m
+
+    samples = []
+    for b in range(B):
+        n_sw = [3, 0, 2][b % 3]
+        key_e2g = pose(rng.uniform(-3, 3), rng.uniform(-200, 200, 3) * [1, 1, 0.01])
+        key_l2e = pose(rng.uniform(-0.05, 0.05), [0.94, 0.0, 1.84])
+        ts = 1.5e15 + 5e5 * b
+        pts = (rng.standard_normal((900 + 100 * b, 5)) * [30, 30, 1.5, 40, 1]).astype(np.float32)
+        sweeps, s_e2g, s_ts = [], [], []
+        for k in range(n_sw):
+            sweeps.append((rng.standard_normal((700 + 50 * k, 5)) * [30, 30, 1.5, 40, 1]).astype(np.float32))
+            s_e2g.append(key_e2g @ pose(rng.uniform(-0.02, 0.02), [0.4 * (k + 1), 0.05 * k, 0.0]))
+            s_ts.append(ts - 5e4 * (k + 1))
+        samples.append(dict(points=pts, sweep_points=sweeps, key_e2g=key_e2g, key_l2e=key_l2e, s_e2g=s_e2g, ts=ts, s_ts=s_ts))
+    return samples
+
+
+def golden_input_side():
+    """CollectLidarSweeps + ObjectRangeFilter (points part) of the REAL reference on synthetic sweeps."""
+    from unidistill.data.multisensorfusion.transforms3d import CollectLidarSweeps, ObjectRangeFilter
+
+    out = {}
+    rng_filter = ObjectRangeFilter(PC_RANGE).eval()
+    for b, s_ in enumerate(_input_side_samples()):
+        d = {"points": s_["points"].copy(), "sweep_points": [x.copy() for x in s_["sweep_points"]],
+             "info": {"ego_to_global": s_["key_e2g"], "lidar_to_ego": s_["key_l2e"], "timestamp": s_["ts"],
+                      "sweep_lidar_infos": [dict(sweep_lidar_to_ego=m, sweep_lidar_timestamp=t)
+                                            for m, t in zip(s_["s_e2g"], s_["s_ts"])]}}
+        d = CollectLidarSweeps()(d)
+        out["merged_%d" % b] = d["points"].astype(np.float32)
+        d = rng_filter(d)
+        out["filtered_%d" % b] = d["points"].astype(np.float32)
+        out["in_points_%d" % b] = s_["points"]
+        out["key_e2g_%d" % b], out["key_l2e_%d" % b], out["ts_%d" % b] = s_["key_e2g"], s_["key_l2e"], np.float64(s_["ts"])
+        out["n_sweeps_%d" % b] = np.int64(len(s_["sweep_points"]))
+        for k, (x, m, t) in enumerate(zip(s_["sweep_points"], s_["s_e2g"], s_["s_ts"])):
+            out["sweep_%d_%d" % (b, k)], out["s_e2g_%d_%d" % (b, k)], out["s_ts_%d_%d" % (b, k)] = x, m, np.float64(t)
+    np.savez_compressed(os.path.join(HERE, "input_side.npz"), **out)
+
+
 def golden_focal_default():
     """The head's DEFAULT heat-map criterion, CenterNetFocalLoss (reference layers/losses/det3d.py:325-360), on a
     Gaussian (non-binary) target: no alpha, negatives = gt < 1 weighted by (1 - gt)^4, no epsilon in log(1 - pred)."""
@@ -323,6 +373,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "iou3d":
         golden_iou3d()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "input_side":
+        golden_input_side()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "focal":
         golden_focal_default()
         sys.exit(0)
@@ -335,6 +388,7 @@ if __name__ == "__main__":
     golden_proposals()
     golden_iou3d()
     golden_focal_default()
+    golden_input_side()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
