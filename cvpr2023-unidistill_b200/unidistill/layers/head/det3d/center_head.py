@@ -92,7 +92,11 @@ def batched_towers(tasks, x):
     b1 = torch.cat([tw[0].bias for tw in towers], dim=0)
     if w1.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
         w1 = w1.contiguous(memory_format=torch.channels_last)
-    y = F.conv2d(x, w1, b1, stride=1, padding=c1.padding)
+    frozen = isinstance(towers[0][1], nn.Identity) and not torch.is_grad_enabled() and x.is_cuda
+    if frozen:          # folded BatchNorm, no gradients: bias + ReLU in the convolution's epilogue
+        y = torch.cudnn_convolution_relu(x, w1, b1, (1, 1), c1.padding, (1, 1), 1)
+    else:
+        y = F.conv2d(x, w1, b1, stride=1, padding=c1.padding)
     # ---- one BatchNorm over all 42*64 channels (identity when the norms were folded into the convolutions)
     bns = [tw[1] for tw in towers]
     if isinstance(bns[0], nn.BatchNorm2d):
@@ -107,7 +111,8 @@ def batched_towers(tasks, x):
                 torch._foreach_copy_([bn.running_mean for bn in bns], list(rm.split(mid)))
                 torch._foreach_copy_([bn.running_var for bn in bns], list(rv.split(mid)))
                 torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
-    y = F.relu(y)
+    if not frozen:
+        y = F.relu(y)
     # ---- layer 2: ONE dense convolution over all 42*64 channels with a block-diagonal weight (tower i's rows see only
     # tower i's 64 input channels, zeros elsewhere).  It spends 42x the FLOPs of the 42 small convolutions, but as one
     # tensor-core implicit GEMM (~0.4 PFLOP/s) it is still ~5x faster than they are, and -- unlike a groups=42

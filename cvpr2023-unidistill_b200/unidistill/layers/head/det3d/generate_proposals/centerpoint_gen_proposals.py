@@ -16,93 +16,72 @@ from .base_gen_proposals import BaseGenProposals
 
 
 class CenterPointGenProposals(BaseGenProposals):
+    # constructor arguments of the reference (:9-39), stored under the same attribute names
+    _ARGS = ("dataset_name", "class_names", "post_center_limit_range", "score_threshold", "pc_range", "out_size_factor",
+             "voxel_size", "no_log", "nms_iou_threshold_train", "nms_pre_max_size_train", "nms_post_max_size_train",
+             "nms_iou_threshold_test", "nms_pre_max_size_test", "nms_post_max_size_test")
+
     def __init__(self, dataset_name, class_names, post_center_limit_range, score_threshold, pc_range, out_size_factor,
                  voxel_size, no_log, nms_iou_threshold_train, nms_pre_max_size_train, nms_post_max_size_train,
                  nms_iou_threshold_test, nms_pre_max_size_test, nms_post_max_size_test):
         super().__init__()
-        self.dataset_name = dataset_name
-        self.class_names = class_names
-        self.post_center_limit_range = post_center_limit_range
-        self.score_threshold = score_threshold
-        self.pc_range = pc_range
-        self.out_size_factor = out_size_factor
-        self.voxel_size = voxel_size
-        self.no_log = no_log
-        self.nms_iou_threshold_train = nms_iou_threshold_train
-        self.nms_pre_max_size_train = nms_pre_max_size_train
-        self.nms_post_max_size_train = nms_post_max_size_train
-        self.nms_iou_threshold_test = nms_iou_threshold_test
-        self.nms_pre_max_size_test = nms_pre_max_size_test
-        self.nms_post_max_size_test = nms_post_max_size_test
+        given = locals()
+        for name in self._ARGS:
+            setattr(self, name, given[name])
         self.training = True
 
-    # ---- helpers, reference :41-83 ---------------------------------------------------------------
-    def _transpose_and_gather_feat(self, feat, ind):
-        feat = feat.permute(0, 2, 3, 1).contiguous()
-        feat = feat.view(feat.size(0), -1, feat.size(3))
-        return self._gather_feat(feat, ind)
-
+    # ---- map helpers (same names and results as the reference's, :41-83) ---------------------------
     def _gather_feat(self, feat, ind, mask=None):
-        dim = feat.size(2)
-        ind = ind.unsqueeze(2).expand(ind.size(0), ind.size(1), dim)
-        feat = feat.gather(1, ind)
-        if mask is not None:
-            mask = mask.unsqueeze(2).expand_as(feat)
-            feat = feat[mask].view(-1, dim)
-        return feat
+        """feat (B, N, C), ind (B, K) -> (B, K, C); with `mask` (B, K) the selected rows, flattened to (n, C)."""
+        picked = torch.take_along_dim(feat, ind.unsqueeze(-1), dim=1)
+        return picked if mask is None else picked[mask]
+
+    def _transpose_and_gather_feat(self, feat, ind):
+        """feat (B, C, H, W), ind (B, K) flat positions -> (B, K, C), without materialising the NHWC copy."""
+        flat = feat.flatten(2)                                                      # (B, C, H*W)
+        return torch.take_along_dim(flat, ind.unsqueeze(1), dim=2).transpose(1, 2).contiguous()
 
     def _nms(self, heat, kernel=3):
-        pad = (kernel - 1) // 2
-        hmax = nn.functional.max_pool2d(heat, (kernel, kernel), stride=1, padding=pad)
-        return heat * (hmax == heat).float()
+        """Keeps the local maxima of a heat-map (kernel x kernel neighbourhood), zeroes the rest."""
+        peak = nn.functional.max_pool2d(heat, kernel, stride=1, padding=(kernel - 1) // 2)
+        return torch.where(peak == heat, heat, torch.zeros_like(heat))
 
     def _topk(self, scores, K=40):
-        batch, cat, height, width = scores.size()
-        topk_scores, topk_inds = torch.topk(scores.reshape(batch, cat, -1), K)
-        topk_inds = topk_inds % (height * width)
-        topk_ys = (topk_inds / width).int().float()
-        topk_xs = (topk_inds % width).int().float()
-        topk_score, topk_ind = torch.topk(topk_scores.view(batch, -1), K)
-        topk_clses = (topk_ind / K).int()
-        topk_inds = self._gather_feat(topk_inds.view(batch, -1, 1), topk_ind).view(batch, K)
-        topk_ys = self._gather_feat(topk_ys.view(batch, -1, 1), topk_ind).view(batch, K)
-        topk_xs = self._gather_feat(topk_xs.view(batch, -1, 1), topk_ind).view(batch, K)
-        return topk_score, topk_inds, topk_clses, topk_ys, topk_xs
+        """Two-stage top-K as in the reference (per class, then across classes: tie order is part of the contract)
+        -> (score, flat index, class (int32), y, x), each (B, K)."""
+        B, n_cls, H, W = scores.shape
+        per_cls_score, per_cls_pos = scores.flatten(2).topk(K, dim=2)               # (B, n_cls, K)
+        score, pick = per_cls_score.flatten(1).topk(K, dim=1)                       # pick in [0, n_cls * K)
+        pos = torch.take_along_dim(per_cls_pos.flatten(1), pick, dim=1)             # flat position inside the map
+        cls = torch.div(pick, K, rounding_mode="floor").int()
+        ys = torch.div(pos, W, rounding_mode="floor").float()
+        xs = (pos - torch.div(pos, W, rounding_mode="floor") * W).float()
+        return score, pos, cls, ys, xs
 
-    # ---- NMS, reference :85-142 ------------------------------------------------------------------
+    # ---- per-sample NMS through the drop-in extension module (reference call site :97-100) ---------------------
     def _nms_gpu_3d(self, boxes, scores, thresh, pre_maxsize=None, post_max_size=None):
-        assert boxes.shape[1] == 7
-        order = scores.sort(0, descending=True)[1]
-        if pre_maxsize is not None:
-            order = order[:pre_maxsize]
-        boxes = boxes[order].contiguous()
-        keep = torch.LongTensor(boxes.size(0))
-        num_out = iou3d_nms_cuda.nms_gpu(boxes, keep, thresh)
-        selected = order[keep[:num_out].to(boxes.device)].contiguous()
-        if post_max_size is not None:
-            selected = selected[:post_max_size]
-        return selected
+        if boxes.shape[1] != 7:
+            raise ValueError("rotated NMS takes (N, 7) boxes [x, y, z, dx, dy, dz, heading]")
+        ranked = torch.argsort(scores, dim=0, descending=True)[:pre_maxsize]        # [:None] keeps everything
+        kept_slots = torch.empty(ranked.numel(), dtype=torch.long)                  # CPU buffer, as the extension expects
+        n_kept = iou3d_nms_cuda.nms_gpu(boxes[ranked].contiguous(), kept_slots, thresh)
+        return ranked[kept_slots[:n_kept].to(boxes.device)][:post_max_size].contiguous()
 
     def _boxes3d_to_bevboxes_lidar_torch(self, boxes3d):
-        boxes_bev = boxes3d.new_empty((boxes3d.shape[0], 5))
-        cu, cv = boxes3d[:, 0], boxes3d[:, 1]
-        half_w, half_l = boxes3d[:, 3] / 2, boxes3d[:, 4] / 2
-        boxes_bev[:, 0], boxes_bev[:, 1] = cu - half_w, cv - half_l
-        boxes_bev[:, 2], boxes_bev[:, 3] = cu + half_w, cv + half_l
-        boxes_bev[:, 4] = boxes3d[:, -1]
-        return boxes_bev
+        """(N, 7+) [x, y, z, dx, dy, dz, ..., heading] -> (N, 5) axis-aligned BEV extents + heading."""
+        centre, half = boxes3d[:, 0:2], boxes3d[:, 3:5] / 2
+        return torch.cat([centre - half, centre + half, boxes3d[:, -1:]], dim=1)
 
     def get_nms_scores(self, scores):
         return scores
 
     def nms_options(self, boxes3d, labels, scores, nms_scores):
-        if nms_scores.shape[0] != 0:
-            selected = self._nms_gpu_3d(boxes3d[:, :7], nms_scores, thresh=self.nms_iou_threshold_use,
-                                        pre_maxsize=self.nms_pre_max_size_use,
-                                        post_max_size=self.nms_post_max_size_use)
+        if nms_scores.shape[0] == 0:
+            keep = []
         else:
-            selected = []
-        return boxes3d[selected], labels[selected], scores[selected]
+            keep = self._nms_gpu_3d(boxes3d[:, :7], nms_scores, self.nms_iou_threshold_use,
+                                    pre_maxsize=self.nms_pre_max_size_use, post_max_size=self.nms_post_max_size_use)
+        return boxes3d[keep], labels[keep], scores[keep]
 
     # ---- decoding shared by the per-sample and the batched path ---------------------------------------
     def _nms_score(self, scores, inds, task_id, iouhm):

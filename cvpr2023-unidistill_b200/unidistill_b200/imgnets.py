@@ -29,7 +29,12 @@ class ResNet(nn.Module):
         return None
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        if isinstance(self.bn1, nn.Identity):      # frozen + folded: bias and ReLU in the convolution's epilogue
+            from .fused_dense import conv_bias_relu
+
+            x = self.maxpool(conv_bias_relu(self.conv1, x))
+        else:
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             x = layer(x)

@@ -220,7 +220,7 @@ class DistillStep:
     def __init__(self, student, teacher, geometry, lr=None, weight_decay=1e-7, clamp_min=None, optimizer=True,
                  fold_teacher_bn=True, teacher_cuda_graph=True, weights=None, preset="camera_exp_distill_lidar",
                  grad_clip=0.1, lr_milestones=(10, 15), lr_gamma=0.1, teacher_mode="eval", overlap_allreduce=True,
-                 bucket_bytes=16 << 20):
+                 bucket_bytes=16 << 20, fuse_teacher_epilogues=True):
         cfg = PRESETS[preset]
         self.weights = tuple(float(w) for w in (weights if weights is not None else cfg["weights"]))
         self.clamp_min = float(clamp_min if clamp_min is not None else cfg["clamp_min"])
@@ -239,10 +239,17 @@ class DistillStep:
             p.requires_grad = False
         teacher.det_head.dense_head.distill = True             # (:419)
         self.folded_bn = 0
+        self.fused_epilogues = 0
         if teacher_mode == "eval":
             teacher.eval()
             # the frozen eval-mode teacher: BatchNorm folded into the dense convolutions
             self.folded_bn = fold_frozen_batchnorm(teacher) if fold_teacher_bn else 0
+            if self.folded_bn and fuse_teacher_epilogues:
+                from .fused_dense import fuse_frozen_conv_relu
+
+                # bias (+ residual) + ReLU of the folded convolutions in cuDNN's epilogue (the towers of the head are
+                # batched by CenterHead.run_towers, which fuses its own first layer)
+                self.fused_epilogues = fuse_frozen_conv_relu(teacher, skip=("SepHead",))
         else:
             teacher.train()
         if teacher_cuda_graph and next(teacher.parameters()).is_cuda:

