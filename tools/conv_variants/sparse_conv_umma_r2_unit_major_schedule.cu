@@ -1,0 +1,670 @@
+// Sparse 3-D convolution on the 5th-generation tensor cores (tcgen05, TMEM accumulators), sm_100a only.
+//
+// Same contract as ud_sparse_conv_forward (sparse_conv.cu):
+//     out[o, :] = bias + sum_k in[nbr[o][k], :] @ W[k]            nbr[o][k] == -1 -> no contribution
+// replacing spconv's ConvAlgo.Native gather/GEMM/scatter-add triplets behind
+//   reference unidistill/layers/blocks_3d/det3d/spconv_backbone.py:21-48,70-92 (+ their dgrad, which is
+//   this same kernel run on the transposed table and weights).
+//
+// Formulation: implicit GEMM, output stationary.  A tile = 128 consecutive output rows (UMMA M = 128) x all COUT columns
+// (UMMA N = COUT) with its fp32 accumulator in TMEM; one CTA owns up to 256/COUT (<= 8) tiles so that a weight slice is
+// fetched once per CTA.  A pipeline stage = one kernel (super-)tap x 64 input channels x one tile (narrow layers put
+// 2 (CIN 32) / 4 (CIN 16) taps side by side); the per-tile tap masks of the rulebook decide which stages exist.
+// Precision: the reference is fp32 and BASELINE.json asks for 1e-3 through 21 layers.  Both operands are split into two
+// bf16 terms (x = hi + lo to 2^-17) and the product is accumulated as lo*W_hi + hi*W_lo + hi*W_hi, three
+// tcgen05.mma kind::f16 per 16 channels, fp32 accumulation: <= 2e-5 of the largest output against the C oracle.
+// The gathered operand never touches shared memory (global -> registers in the tcgen05.st.16x256b fragment layout ->
+// bf16 hi/lo -> TMEM); shared memory holds only the weight-slice ring and the row-index ring.  DESIGN.md section 3.1.
+// The kernel's predecessors (A through shared memory, 3xTF32, TF32 + bf16 corrections: "variants 0-3" of round 1) are kept
+// for reference under tools/conv_variants/ and are not part of the library.
+#include "common.cuh"
+#include "umma_common.cuh"
+#include "det_reduce.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+using namespace ud_umma;
+
+constexpr int TILE_M = 128;
+constexpr int MAX_TAPS = 32;
+constexpr int MAX_TILES = 8;           // output tiles (TMEM accumulators) per CTA
+constexpr int MAX_SCHED = MAX_TAPS * 4 * 8;   // >= taps * stages per tap * tiles for every instantiation
+constexpr int TS_GROUP = 128;          // threads of one gather set
+constexpr int TS_ACC_COLS = 256;       // TMEM columns holding accumulators; the other 256 hold the A-operand ring
+
+__host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
+// taps that share one 64-channel stage (narrow layers)
+__host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin : 1; }
+// bytes of one weight slice: [COUT x 64] bf16 W_hi + [COUT x 64] bf16 W_lo
+__host__ __device__ constexpr int dg_b_bytes(int cout) { return 4 * cout * 64; }
+
+// Packed weight image: per (super-tap, stage of 64 channels) one block of
+//   [COUT x 64 bf16 W_hi] [COUT x 64 bf16 W_lo],  W_hi = bf16(W), W_lo = bf16(W - W_hi), 128-byte swizzle.
+// Block size = 4 * COUT * 64 bytes.
+__global__ void __launch_bounds__(256)
+k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int tapg, unsigned char* __restrict__ packed) {
+    constexpr int ks = 64;
+    const int cin_eff = cin * tapg;
+    const int k_eff = (K + tapg - 1) / tapg;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)k_eff * cin_eff * cout;
+    if (t >= total) return;
+    const int n = (int)(t % cout);
+    const int cv = (int)((t / cout) % cin_eff);             // virtual channel = g * cin + c
+    const int kj = (int)(t / ((long long)cout * cin_eff));
+    const int tap = kj * tapg + cv / cin, c = cv % cin;
+    const float v = tap < K ? w[((size_t)tap * cin + c) * cout + n] : 0.f;      // w[k][c][n]
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int nstage = cin_eff / ks;
+    const int stage = cv / ks, e = cv % ks;
+    __nv_bfloat16* blk = reinterpret_cast<__nv_bfloat16*>(packed + (size_t)(kj * nstage + stage) * ((size_t)4 * cout * ks));
+    const int chunk = e >> 3, within = e & 7;               // 16-byte chunk = 8 bf16
+    const size_t off = (size_t)n * ks + (size_t)((chunk ^ (n & 7)) * 8 + within);
+    blk[off] = hi;
+    blk[(size_t)cout * ks + off] = lo;
+}
+
+// [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
+// tile_masks[row / 128] |= 1 << k for every tap k that occurs in the 128-row tile (zeroed by the launcher).
+__global__ void __launch_bounds__(256)
+k_transpose_table(const int* __restrict__ src, int n, int K, int ld, int* __restrict__ dst,
+                  unsigned int* __restrict__ tile_masks) {
+    __shared__ int tile[32][33];
+    const int r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i;
+        tile[i][tx] = (r < n && tx < K) ? src[(size_t)r * K + tx] : -1;
+    }
+    __syncthreads();
+    unsigned int m = 0u;
+    const int k_pad = (K + 3) / 4 * 4;                 // rows [K, k_pad) = -1: multi-tap stages read whole tap groups
+    for (int k = ty; k < k_pad; k += 8) {
+        const int r = r0 + tx;
+        const int v = k < K ? tile[tx][k] : -1;
+        if (r < ld) dst[(size_t)k * ld + r] = v;
+        const unsigned any = __ballot_sync(0xffffffffu, r < n && v >= 0);
+        if (any) m |= 1u << k;
+    }
+    if (tile_masks && tx == 0 && m) atomicOr(tile_masks + (r0 >> 7), m);
+}
+
+// Builds the stage schedule of a CTA from the tap masks of its tiles (warp 0).
+//
+// Order = "unit major": a unit is a group of up to three consecutive kernel (super-)taps -- for a 3x3x3 kernel with one
+// tap per stage the three kx neighbours of one (kz, ky) -- times one 64-channel chunk.  Inside a unit the stages run
+// tile by tile, and for each tile the unit's taps back to back:
+//     unit (g, c):  tile 0: tap 3g, 3g+1, 3g+2;  tile 1: tap 3g, 3g+1, 3g+2;  ...
+// The rows the three kx taps of a tile gather are the same memory rows shifted by one voxel (raster row order: x-adjacent
+// voxels are adjacent rows), so issuing them back to back turns two of the three gathers into L1 / L2 hits; the unit's (up to)
+// three weight slices stay resident in the weight ring while the tiles pass, so a slice is still fetched once per CTA.
+//   b_sched[ib] = tap | chunk << 5                       weight slices in load order
+//   a_sched[it] = tap | chunk << 5 | tile << 8 | release << 11      release: last stage that uses the stage's slice
+//   a_slice[it] = index into b_sched of the slice the stage multiplies with
+template <int NCHUNK>
+__device__ __forceinline__ void build_schedule(const unsigned int* tile_mask_s, int tiles, int K, int lane,
+                                               unsigned short* a_sched, unsigned short* a_slice,
+                                               unsigned short* b_sched, int* n_a_s, int* n_b_s) {
+    unsigned int tm = 0u;                                 // bit t: tile t has tap `lane`
+    if (lane < K)
+        for (int t = 0; t < tiles; ++t) tm |= ((tile_mask_s[t] >> lane) & 1u) << t;
+    // lane g < 11 owns group g = taps 3g .. 3g+2
+    const int g = lane;
+    const unsigned int m0 = __shfl_sync(0xffffffffu, tm, (3 * g) & 31);
+    const unsigned int m1 = __shfl_sync(0xffffffffu, tm, (3 * g + 1) & 31);
+    const unsigned int m2 = __shfl_sync(0xffffffffu, tm, (3 * g + 2) & 31);
+    unsigned int gm[3] = {0u, 0u, 0u};
+    if (3 * g < K) {
+        gm[0] = m0;
+        gm[1] = 3 * g + 1 < 32 ? m1 : 0u;
+        gm[2] = 3 * g + 2 < 32 ? m2 : 0u;
+    }
+    const int n_slices = (gm[0] != 0u) + (gm[1] != 0u) + (gm[2] != 0u);
+    const int n_stages = __popc(gm[0]) + __popc(gm[1]) + __popc(gm[2]);
+    int incl_a = n_stages, incl_b = n_slices;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int va = __shfl_up_sync(0xffffffffu, incl_a, o);
+        const int vb = __shfl_up_sync(0xffffffffu, incl_b, o);
+        if (lane >= o) { incl_a += va; incl_b += vb; }
+    }
+    int a_pos = (incl_a - n_stages) * NCHUNK;
+    int b_pos = (incl_b - n_slices) * NCHUNK;
+    if (n_slices > 0) {
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            int slice_of[3];
+            int j = 0;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                slice_of[x] = b_pos + j;
+                if (gm[x]) {
+                    b_sched[b_pos + j] = (unsigned short)((3 * g + x) | (ch << 5));
+                    ++j;
+                }
+            }
+            for (int t = 0; t < tiles; ++t) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    if ((gm[x] >> t) & 1u) {
+                        const unsigned int last = 31u - (unsigned int)__clz(gm[x]);      // highest tile with this tap
+                        a_sched[a_pos] = (unsigned short)((3 * g + x) | (ch << 5) | (t << 8) | ((last == (unsigned)t) << 11));
+                        a_slice[a_pos] = (unsigned short)slice_of[x];
+                        ++a_pos;
+                    }
+                }
+            }
+            b_pos += n_slices;
+        }
+    }
+    if (lane == 31) {
+        *n_a_s = incl_a * NCHUNK;
+        *n_b_s = incl_b * NCHUNK;
+    }
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {   // element 2j in the low half
+    const __nv_bfloat162 t = __floats2bfloat162_rn(even, odd);
+    return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+
+// memory.  ncu showed the L1/shared-memory data pipe (not the tensor pipe) as the busiest unit of the TS kernels: per
+// 64-channel stage 32 KB of gathered rows were written to shared memory by cp.async, read back by the transform warps and
+// 24 KB of weight slices re-read by the MMAs.  Here a gather warp loads its rows straight into registers in the fragment
+// layout of tcgen05.st.16x256b (measured with tools/tmem_layout_probe.cu: thread t holds TMEM lanes t/4 and t/4+8,
+// columns 2(t%4), 2(t%4)+1 of every 8-column unit), so 4 lanes read 64 contiguous bytes of a row (whole 32-byte sectors),
+// splits them into bf16 hi/lo in registers and stores them to the stage's TMEM columns.
+//   warps 0-15 : four gather sets (set = stage % 4 = TMEM A slot; warp & 3 = TMEM lane quadrant); epilogue afterwards
+//   warp 16    : MMA issuer          warp 17 : weight slices (bulk copies)          warp 18 : row-index segments (bulk copies)
+constexpr int DG_THREADS = 608;
+constexpr int DG_SETS = 4;
+constexpr int DG_IDX_STAGES = 16;
+// weight-slice ring: a schedule unit keeps up to three slices resident; six slots (COUT <= 64: 16 KB slices) let the next
+// unit's slices arrive while the current unit runs, four is what fits beside 32 KB slices
+__host__ __device__ constexpr int dg_b_stages(int cout) { return cout <= 64 ? 6 : 4; }
+// statistics buffer: [0, 4096) final sums (2 * COUT doubles), then the workspace of det_reduce.cuh
+constexpr int DG_STAT_FINAL_BYTES = 4096;
+__host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout) {
+    return (size_t)dg_b_stages(cout) * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 + 1024;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const float* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(DG_THREADS, 1)
+k_spconv_umma_dg(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
+                 const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
+                 int tiles, float* __restrict__ out, unsigned char* __restrict__ stats, int stat_group) {
+    constexpr int TAPG = ts_tapg(CIN);               // kernel taps per 64-channel stage
+    constexpr int KS = 64;
+    constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
+    constexpr int IDX_INTS = TAPG * TILE_M;
+    constexpr int A_COLS = KS;                       // TMEM columns of one A stage: 32 hi | 32 lo (bf16 pairs)
+    constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
+    constexpr int B_BYTES = dg_b_bytes(COUT);
+    constexpr int B_RING = dg_b_stages(COUT);
+    constexpr int BBF_BYTES = COUT * KS * 2;
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                  ((uint32_t)(TILE_M >> 4) << 24);
+    static_assert(A_STAGES == DG_SETS, "one gather set per TMEM A slot");
+    static_assert((CIN * TAPG) % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
+    static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
+    constexpr int NBAR = 2 * A_STAGES + 2 * B_RING + 2 * DG_IDX_STAGES + 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[NBAR];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int tile_mask_s[MAX_TILES];
+    __shared__ unsigned short a_sched[MAX_SCHED];          // tap | chunk << 5 | tile << 8 | release << 11
+    __shared__ unsigned short a_slice[MAX_SCHED];          // weight slice (index into b_sched) of every stage
+    __shared__ unsigned short b_sched[MAX_TAPS * 4];
+    __shared__ int n_a_s, n_b_s;
+    __shared__ float wpart_s[16 * 2 * COUT];               // fused BatchNorm statistics: per epilogue warp, sum | sum of squares
+    __shared__ int stat_last_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int row0 = blockIdx.x * tiles * TILE_M;
+    const int rows_cta = min(tiles * TILE_M, n_out - row0);
+    const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
+    if (stats != nullptr)
+        for (int i = tid; i < 16 * 2 * COUT; i += DG_THREADS) wpart_s[i] = 0.f;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t smem_b = smem_base;
+    const uint32_t smem_idx = smem_b + B_RING * B_BYTES;
+    const int* const idx_ring = reinterpret_cast<const int*>(smem_al + B_RING * B_BYTES);
+    const uint32_t bar_a_full = smem_u32(&bars[0]);
+    const uint32_t bar_a_empty = bar_a_full + 8 * A_STAGES;
+    const uint32_t bar_b_full = bar_a_empty + 8 * A_STAGES;
+    const uint32_t bar_b_empty = bar_b_full + 8 * B_RING;
+    const uint32_t bar_idx_full = bar_b_empty + 8 * B_RING;
+    const uint32_t bar_idx_empty = bar_idx_full + 8 * DG_IDX_STAGES;
+    const uint32_t bar_acc = bar_idx_empty + 8 * DG_IDX_STAGES;
+
+    if (tid == 0) {
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, TS_GROUP);         // every thread of the owning gather set
+            mbar_init(bar_a_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < B_RING; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < DG_IDX_STAGES; ++s) {
+            mbar_init(bar_idx_full + 8 * s, 1);
+            mbar_init(bar_idx_empty + 8 * s, TS_GROUP / 32);   // lane 0 of each warp of the consuming gather set
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    const int K_eff = (K + TAPG - 1) / TAPG;
+    if (tid < MAX_TILES) {
+        const int tile_g = blockIdx.x * tiles + tid;
+        unsigned int m = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+        if (TAPG > 1) {
+            unsigned int me = 0u;
+            for (int j = 0; j < K_eff; ++j)
+                if ((m >> (j * TAPG)) & ((1u << TAPG) - 1u)) me |= 1u << j;
+            m = me;
+        }
+        tile_mask_s[tid] = m;
+    }
+    if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K_eff, lane, a_sched, a_slice, b_sched, &n_a_s, &n_b_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int n_a = n_a_s;
+    const int n_b = n_b_s;
+    const uint32_t tmem_acc = tmem_base_s;
+    const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+
+    if (warp < 16) {
+        // ============ gather sets: global -> registers (st.16x256b fragment layout) -> bf16 hi/lo -> TMEM ============
+        const int set = warp >> 2;
+        const int q = warp & 3;
+        const int rsub = lane >> 2;                      // row within an 8-row group
+        const int csub = (lane & 3) * 4;                 // first of this thread's 4 channels within a 16-channel unit
+        for (int it = set; it < n_a; it += DG_SETS) {
+            const int islot = it % DG_IDX_STAGES;
+            mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / DG_IDX_STAGES)) & 1u);
+            // rows 32 q + 16 h + rsub + 8 rr of the tile, for every tap of the stage
+            int idx[2][2][TAPG];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int g = 0; g < TAPG; ++g)
+                        idx[h][rr][g] = idx_ring[islot * IDX_INTS + g * TILE_M + q * 32 + h * 16 + rr * 8 + rsub];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
+            const int c0 = TAPG == 1 ? ((a_sched[it] >> 5) & 7) * KS : 0;      // chunk field: bits 5-7
+            uint4 x[2][2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // unit j = channels [16 j, 16 j + 16) of the stage: TAPG 1: one tap; TAPG 2 (CIN 32): tap j / 2;
+                        // TAPG 4 (CIN 16): tap j
+                        const int g = TAPG == 1 ? 0 : (TAPG == 2 ? (j >> 1) : j);
+                        const int ch = TAPG == 1 ? c0 + 16 * j + csub : (TAPG == 2 ? (j & 1) * 16 + csub : csub);
+                        const int r = idx[h][rr][g];
+                        x[h][rr][j] = make_uint4(0u, 0u, 0u, 0u);
+                        if (r >= 0) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + ch);
+                    }
+            const int aslot = it % A_STAGES;             // == set
+            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const uint4 v = x[h][rr][j];
+                        const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
+                        const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
+                        hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
+                        lo[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                    }
+                const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
+                tmem_st_16x256b_x4(taddr, hi);
+                tmem_st_16x256b_x4(taddr + KS / 2, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * aslot);
+        }
+    } else if (warp == 16) {
+        // ============ MMA issuer ============
+        unsigned int started = 0u;
+        for (int it = 0; it < n_a; ++it) {
+            const unsigned e = a_sched[it];
+            const int ib = a_slice[it];
+            const int bslot = ib % B_RING;
+            // (re-)waiting on a phase that completed is immediate: the slot is not re-armed before its release below
+            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / B_RING)) & 1u);
+            const uint32_t b_base = smem_b + bslot * B_BYTES;
+            const uint64_t db_hi = umma_desc_sw128(b_base);
+            const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
+            const int aslot = it % A_STAGES;
+            const int tile = (e >> 8) & 7;
+            mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
+                const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
+                const uint32_t first = (started >> tile) & 1u;
+#pragma unroll
+                for (int k16 = 0; k16 < KS / 16; ++k16) {
+                    const uint32_t a_hi = a_stage + (uint32_t)(k16 * 8);
+                    const uint32_t a_lo = a_hi + KS / 2;
+                    const uint64_t adv = (uint64_t)(k16 * 2);
+                    umma_bf16_ts(d, a_lo, db_hi + adv, IDESC_BF, (first || k16 > 0) ? 1u : 0u);
+                    umma_bf16_ts(d, a_hi, db_lo + adv, IDESC_BF, 1u);
+                    umma_bf16_ts(d, a_hi, db_hi + adv, IDESC_BF, 1u);
+                }
+                umma_commit(bar_a_empty + 8 * aslot);
+                if ((e >> 11) & 1u) umma_commit(bar_b_empty + 8 * bslot);       // last stage that reads this weight slice
+            }
+            started |= 1u << tile;
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        // ============ warp 17: weight slices, warp 18: per-stage row-index segments (bulk async copies) ============
+        if (warp == 17 && lane == 0) {
+            for (int ib = 0; ib < n_b; ++ib) {
+                const int bslot = ib % B_RING;
+                mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / B_RING)) & 1u) ^ 1u);
+                const unsigned e = b_sched[ib];
+                const int tap = e & 31, ch = e >> 5;
+                const float* src = wpacked + (size_t)(tap * NCHUNK + ch) * (B_BYTES / 4);
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
+                bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
+            }
+        } else if (warp == 18 && lane == 0) {
+            for (int it = 0; it < n_a; ++it) {
+                const int islot = it % DG_IDX_STAGES;
+                mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / DG_IDX_STAGES)) & 1u) ^ 1u);
+                const unsigned e = a_sched[it];
+                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, IDX_INTS * 4);
+#pragma unroll
+                for (int g = 0; g < TAPG; ++g) {
+                    const int* seg = nbr_t + (size_t)((e & 31) * TAPG + g) * ld_t + row0 + ((e >> 8) & 7) * TILE_M;
+                    bulk_g2s(smem_idx + (islot * TAPG + g) * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
+    if (warp < 16) {
+        if (n_a > 0) {
+            mbar_wait(bar_acc, 0u);
+            tc_fence_after();
+        }
+        const int q = warp & 3;
+        constexpr int CW = COUT >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int t = warp >> 2; t < tiles; t += DG_SETS) {
+            if (t * TILE_M >= rows_cta) break;
+            const bool has_acc = tile_mask_s[t] != 0u;
+            const int r_local = t * TILE_M + q * 32 + lane;
+            const int row = row0 + r_local;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                uint32_t v[32];
+                if (has_acc) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = 0u;
+                }
+                const bool row_ok = r_local < rows_cta;
+                float* dst = out + (size_t)row * COUT + c0;
+#pragma unroll
+                for (int i = 0; i < CW; i += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[i + 0]);
+                    o.y = __uint_as_float(v[i + 1]);
+                    o.z = __uint_as_float(v[i + 2]);
+                    o.w = __uint_as_float(v[i + 3]);
+                    if (bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
+                    if (stats != nullptr) {
+                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
+                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
+                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
+                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
+                    }
+                }
+                if (stats != nullptr) {
+                    float a[32], sq[32];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        a[i] = __uint_as_float(v[i]);
+                        sq[i] = a[i] * a[i];
+                    }
+                    int col = 0;
+#pragma unroll
+                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float sa = up ? a[i] : a[i + sft];
+                            const float sb = up ? sq[i] : sq[i + sft];
+                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
+                            const float rq = __shfl_xor_sync(0xffffffffu, sb, sft);
+                            a[i] = (up ? a[i + sft] : a[i]) + ra;
+                            sq[i] = (up ? sq[i + sft] : sq[i]) + rq;
+                        }
+                        if (up) col += sft;
+                    }
+                    if (CW == 16) {
+                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+                        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 16);
+                    }
+                    if (CW == 32 || lane < 16) {          // the warp's own slot, tiles in ascending order: no atomics
+                        wpart_s[(warp * 2 + 0) * COUT + c0 + col] += a[0];
+                        wpart_s[(warp * 2 + 1) * COUT + c0 + col] += sq[0];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (stats != nullptr) {
+        // 16 warp slots -> this CTA's partial (fixed order), then the fixed-order cross-CTA reduction of det_reduce.cuh:
+        // final[2 * COUT] doubles = per-channel sum | sum of squares of `out`, bit-reproducible from run to run
+        float v = 0.f;
+        if (tid < 2 * COUT) {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) v += wpart_s[(w * 2 + tid / COUT) * COUT + tid % COUT];
+        }
+        ud_det_reduce((double)v, tid, 2 * COUT, stats + DG_STAT_FINAL_BYTES, stat_group,
+                      reinterpret_cast<double*>(stats), &stat_last_s);
+        __syncthreads();
+    }
+    if (warp == 16) tmem_dealloc(tmem_acc, 512);
+}
+
+// tiles per CTA and grid size for n_out rows (one wave-balanced choice shared by the launcher and the size queries)
+void dg_grid(int n_out, int cout, int* tiles_out, int* ctas_out) {
+    const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
+    const int tmax = ts_tiles_max(cout);
+    const int waves = (n_tiles + UD_NUM_SMS * tmax - 1) / (UD_NUM_SMS * tmax);
+    int tiles = (n_tiles + UD_NUM_SMS * waves - 1) / (UD_NUM_SMS * (waves > 0 ? waves : 1));
+    if (tiles < 1) tiles = 1;
+    if (tiles > tmax) tiles = tmax;
+    *tiles_out = tiles;
+    *ctas_out = (n_tiles + tiles - 1) / tiles;
+}
+
+size_t dg_stat_bytes(int n_out, int cout) {
+    int tiles, ctas;
+    dg_grid(n_out, cout, &tiles, &ctas);
+    return (size_t)DG_STAT_FINAL_BYTES + ud_det_reduce_bytes(ctas, 2 * cout);
+}
+
+template <int CIN, int COUT>
+int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                   const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
+                   cudaStream_t stream) {
+    const size_t smem = dg_smem_bytes(CIN, COUT);
+    auto kern = k_spconv_umma_dg<CIN, COUT>;
+    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tiles, ctas;
+    dg_grid(n_out, COUT, &tiles, &ctas);
+    if (stats != nullptr)       // arrival counters of the statistics reduction
+        UD_CUDA_TRY(cudaMemsetAsync(stats + DG_STAT_FINAL_BYTES, 0, UD_DET_COUNTER_BYTES, stream));
+    kern<<<ctas, DG_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
+                                             ud_det_group(ctas));
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// forward shapes of VoxelResBackBone8x and the dgrad (cin/cout swapped) of every layer but the first
+bool tc_shape_ok(int K, int cin, int cout) {
+    static const int shapes[][2] = {{16, 16}, {16, 32}, {32, 16}, {32, 32}, {32, 64}, {64, 32}, {64, 64}, {64, 128},
+                                    {128, 64}, {128, 128}};
+    if (K < 1 || K > MAX_TAPS) return false;
+    for (const auto& s : shapes)
+        if (s[0] == cin && s[1] == cout) return true;
+    return false;
+}
+
+}  // namespace
+
+#define UD_DISPATCH_DG(CI, CO) \
+    if (cin == CI && cout == CO) return launch_umma_dg<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+
+extern "C" {
+
+// 1 when (K, cin, cout) has a tensor-core instantiation, else 0.
+int ud_sparse_conv_tc_supported(int K, int cin, int cout) { return tc_shape_ok(K, cin, cout) ? 1 : 0; }
+
+int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes) {
+    if (!bytes) return UD_ERR_INVALID_ARG;
+    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    const int tapg = ts_tapg(cin);
+    *bytes = (size_t)((K + tapg - 1) / tapg) * (cin * tapg) * cout * 2 * sizeof(__nv_bfloat16);
+    return UD_OK;
+}
+
+// w: (K, cin, cout) f32 (the layout ud_sparse_conv_forward takes) -> packed bf16 hi/lo image, 128-byte swizzle applied
+// (16-byte aligned): one bulk copy per (super-tap, 64-channel stage) in the kernel.
+int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!w || !packed) return UD_ERR_INVALID_ARG;
+    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
+    const int tapg = ts_tapg(cin);
+    const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
+    k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, tapg, (unsigned char*)packed);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// nbr (n, K) int32 row-major gather table -> nbr_t (K4, ld) tap-major, K4 = K rounded up to 4 and ld = n rounded up to 128
+// (all padding = -1, base 16-byte aligned so every (tile, tap) index segment can be bulk-copied) + tile_masks
+// (ceil(n/128)) uint32 (bit k set when tap k occurs in the 128-row tile): the two inputs ud_sparse_conv_tc_forward reads.
+int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int* tile_masks, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || K < 1 || K > MAX_TAPS || (n > 0 && (!nbr || !nbr_t || !tile_masks))) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    UD_CUDA_TRY(cudaMemsetAsync(tile_masks, 0, sizeof(unsigned int) * (size_t)((n + TILE_M - 1) / TILE_M), stream));
+    const int ld = (n + TILE_M - 1) / TILE_M * TILE_M;
+    k_transpose_table<<<ud_blocks(ld, 32), 256, 0, stream>>>(nbr, n, K, ld, nbr_t, tile_masks);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// Size of the statistics buffer ud_sparse_conv_tc_forward needs for n_out rows (0 rows -> header only).
+int ud_sparse_conv_tc_stats_bytes(int n_out, int cout, size_t* bytes) {
+    if (!bytes || n_out < 0 || cout < 1 || cout > 256) return UD_ERR_INVALID_ARG;
+    *bytes = dg_stat_bytes(n_out > 0 ? n_out : 1, cout);
+    return UD_OK;
+}
+
+// in (n_in, cin) f32, 16-byte aligned rows; wpacked from ud_sparse_conv_tc_pack_weights; bias (cout)|NULL;
+// nbr_t (K, n_out) int32 tap-major gather table and tile_masks (ceil(n_out/128)) from ud_rulebook_transpose;
+// out (n_out, cout) f32.
+// bn_stats (nullable): buffer of ud_sparse_conv_tc_stats_bytes(n_out, cout) bytes, 16-byte aligned, no initialisation
+// needed.  On return its first 2 * cout doubles hold the per-channel sum and sum of squares of `out` -- the statistics
+// pass of the BatchNorm that follows (spconv_backbone.py:50-56,97-113), fused into the epilogue and reduced in a FIXED
+// order (bit-reproducible from run to run); the rest of the buffer is scratch of that reduction.
+int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
+                              const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
+                              void* bn_stats, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float* wpacked = (const float*)wpacked_;
+    unsigned char* stats = (unsigned char*)bn_stats;
+    if (!in || !wpacked || !nbr_t || !tile_masks || !out || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out | (uintptr_t)stats) & 15u) != 0) return UD_ERR_INVALID_ARG;
+    if (n_out == 0) {
+        if (stats) UD_CUDA_TRY(cudaMemsetAsync(stats, 0, 2 * cout * sizeof(double), stream));
+        return UD_OK;
+    }
+    UD_DISPATCH_DG(16, 16)
+    UD_DISPATCH_DG(16, 32)
+    UD_DISPATCH_DG(32, 16)
+    UD_DISPATCH_DG(32, 32)
+    UD_DISPATCH_DG(32, 64)
+    UD_DISPATCH_DG(64, 32)
+    UD_DISPATCH_DG(64, 64)
+    UD_DISPATCH_DG(64, 128)
+    UD_DISPATCH_DG(128, 64)
+    UD_DISPATCH_DG(128, 128)
+    return UD_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"
