@@ -39,6 +39,16 @@ __host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin 
 // bytes of one weight slice: [COUT x 64] bf16 W_hi + [COUT x 64] bf16 W_lo
 __host__ __device__ constexpr int dg_b_bytes(int cout) { return 4 * cout * 64; }
 
+// K order inside a 64-channel stage.  For CIN >= 32 the gather warps read 32 bytes (8 channels) per lane: lane l of a quad
+// holds physical channels 8 l .. 8 l + 7 of a 32-channel block and feeds them to K positions 4 l .. 4 l + 3 of the block's two
+// 16-channel MMA units, i.e. physical position pe = 32 b + 8 l + 4 u + i  <->  logical K = 16 (2 b + u) + 4 l + i.  A and B only
+// have to agree on the order, so the permutation lives in the weight image.  CIN 16 keeps the natural order.
+__host__ __device__ __forceinline__ int dg_logical_k(int pe, int cin) {
+    if (cin < 32) return pe;
+    const int b = pe >> 5, l = (pe >> 3) & 3, u = (pe >> 2) & 1, i = pe & 3;
+    return 16 * (2 * b + u) + 4 * l + i;
+}
+
 // Packed weight image: per (super-tap, stage of 64 channels) one block of
 //   [COUT x 64 bf16 W_hi] [COUT x 64 bf16 W_lo],  W_hi = bf16(W), W_lo = bf16(W - W_hi), 128-byte swizzle.
 // Block size = 4 * COUT * 64 bytes.
@@ -58,7 +68,8 @@ k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int ta
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const int nstage = cin_eff / ks;
-    const int stage = cv / ks, e = cv % ks;
+    const int stage = cv / ks;
+    const int e = dg_logical_k(cv % ks, cin);          // K position inside the 64-wide stage (permuted for cin >= 32)
     __nv_bfloat16* blk = reinterpret_cast<__nv_bfloat16*>(packed + (size_t)(kj * nstage + stage) * ((size_t)4 * cout * ks));
     const int chunk = e >> 3, within = e & 7;               // 16-byte chunk = 8 bf16
     const size_t off = (size_t)n * ks + (size_t)((chunk ^ (n & 7)) * 8 + within);
@@ -175,6 +186,12 @@ __device__ __forceinline__ uint4 ldg_stream(const float* p) {
     asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+// 256-bit variant: four lanes cover a whole 128-byte line of a row, so L1 / L2 see one full-line request per row instead of
+// two half-line ones (the gather is limited by the L2 -> SM request rate, profiles/r02_unit_major_schedule.md)
+__device__ __forceinline__ void ldg_stream256(const float* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::evict_last.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -299,20 +316,36 @@ k_spconv_umma_dg(const float* __restrict__ in, const float* __restrict__ wpacked
             if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
             const int c0 = TAPG == 1 ? ((a_sched[it] >> 5) & 7) * KS : 0;
             uint4 x[2][2][4];
+            if constexpr (TAPG <= 2) {
+                // CIN >= 32: one 32-byte load per lane and 32-channel block.  Lane l of a quad reads PHYSICAL channels
+                // [8 l, 8 l + 8) of the block and uses them as LOGICAL K positions 4 l .. 4 l + 3 of the block's two
+                // 16-channel units; the weight image is packed in the same permuted K order (dg_logical_k).
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
+                    for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // unit j = channels [16 j, 16 j + 16) of the stage: TAPG 1: one tap; TAPG 2 (CIN 32): tap j / 2;
-                        // TAPG 4 (CIN 16): tap j
-                        const int g = TAPG == 1 ? 0 : (TAPG == 2 ? (j >> 1) : j);
-                        const int ch = TAPG == 1 ? c0 + 16 * j + csub : (TAPG == 2 ? (j & 1) * 16 + csub : csub);
-                        const int r = idx[h][rr][g];
-                        x[h][rr][j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (r >= 0) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + ch);
-                    }
+                        for (int j2 = 0; j2 < 2; ++j2) {
+                            const int g = TAPG == 1 ? 0 : j2;                     // TAPG 2 (CIN 32): block j2 = tap j2
+                            const int ch = (TAPG == 1 ? c0 + 32 * j2 : 0) + 2 * csub;
+                            const int r = idx[h][rr][g];
+                            x[h][rr][2 * j2] = make_uint4(0u, 0u, 0u, 0u);
+                            x[h][rr][2 * j2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+                            if (r >= 0) ldg_stream256(in + (size_t)r * CIN + ch, x[h][rr][2 * j2], x[h][rr][2 * j2 + 1]);
+                        }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            // TAPG 4 (CIN 16): unit j = tap j, 64-byte rows: 16-byte loads, natural K order
+                            const int r = idx[h][rr][j];
+                            x[h][rr][j] = make_uint4(0u, 0u, 0u, 0u);
+                            if (r >= 0) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + csub);
+                        }
+            }
             const int aslot = it % A_STAGES;             // == set
             mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
             tc_fence_after();
