@@ -9,6 +9,8 @@
 // (`sp_tensor.dense()` -> (B, C, D, H, W) -> view(B, C*D, H, W)); channel index = c*D + z.
 #include "common.cuh"
 #include "det_reduce.cuh"
+#include "tma.cuh"
+#include "umma_common.cuh"
 
 namespace {
 
@@ -160,19 +162,23 @@ k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
 }
 
 // ---- scatter to BEV ---------------------------------------------------------------------------
-// CTA = 32 consecutive rows (rows of one conv output are sorted by (b,z,y,x), so they are mostly
-// x-adjacent) x all C channels, staged through smem so that both the row reads (C contiguous floats)
-// and the NCHW writes (x contiguous) coalesce.
+// CTA = 32 consecutive rows (rows of one conv output are sorted by (b,z,y,x), so they are mostly x-adjacent) x all C
+// channels.  The 32 x C voxel tile is staged in shared memory by TMA: C/32 tensor loads (cp.async.bulk.tensor.2d) of a
+// [32 rows x 32 channels] box each, 128-byte swizzle, rows past the end read as zero.  The NCHW writes then walk the tile
+// channel by channel with lanes = voxels, so x-adjacent voxels write adjacent floats; the swizzle (16-byte chunk index XOR
+// row & 7) spreads a column read over 8 bank groups (4-way conflict instead of 32-way for a dense 128-byte pitch).
 __global__ void __launch_bounds__(256)
-k_scatter_bev(const float* __restrict__ feat, const int4* __restrict__ coords, int n, int C, int D, int H,
+k_scatter_bev(const __grid_constant__ CUtensorMap feat_map, const int4* __restrict__ coords, int n, int C, int D, int H,
               int W, float* __restrict__ out) {
-    extern __shared__ float tile[];   // [32][C+1]
+    extern __shared__ __align__(1024) unsigned char tile_raw[];   // C/32 boxes of [32 rows][32 floats], swizzled
     __shared__ long long base_off[32];
+    __shared__ __align__(8) unsigned long long bar;
     const int row0 = blockIdx.x * 32;
     const int rows = min(32, n - row0);
-    for (int e = threadIdx.x; e < 32 * C; e += blockDim.x) {
-        int r = e / C, c = e - r * C;
-        tile[r * (C + 1) + c] = r < rows ? feat[(size_t)(row0 + r) * C + c] : 0.f;
+    const uint32_t bar_a = ud_umma::smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        ud_umma::mbar_init(bar_a, 1);
+        ud_umma::fence_barrier_init();
     }
     if (threadIdx.x < 32) {
         long long off = -1;
@@ -183,13 +189,23 @@ k_scatter_bev(const float* __restrict__ feat, const int4* __restrict__ coords, i
         base_off[threadIdx.x] = off;
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        ud_umma::mbar_arrive_expect_tx(bar_a, 32u * (uint32_t)C * 4u);
+        for (int b = 0; b < C / 32; ++b) tma_load_2d(ud_umma::smem_u32(tile_raw) + b * 4096, &feat_map, b * 32, row0, bar_a);
+    }
+    ud_umma::mbar_wait(bar_a, 0u);
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
     const long long off = base_off[lane];
     const long long cstride = (long long)D * H * W;
     if (off >= 0)
-        for (int c = wid; c < C; c += nw) out[off + c * cstride] = tile[lane * (C + 1) + c];
+        for (int c = wid; c < C; c += nw) {
+            const int j = c & 31;
+            const float v = *reinterpret_cast<const float*>(tile_raw + (c >> 5) * 4096 + lane * 128 +
+                                                            ((((j >> 2) ^ (lane & 7)) << 4) | ((j & 3) << 2)));
+            out[off + c * cstride] = v;
+        }
 }
 
 __global__ void __launch_bounds__(256)
@@ -330,8 +346,13 @@ int ud_scatter_to_bev(const float* feat, const int* coords, int n, int batch_siz
     if (zero_fill)
         UD_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)batch_size * C * D * H * W * sizeof(float), stream));
     if (n == 0) return UD_OK;
-    size_t smem = (size_t)32 * (C + 1) * sizeof(float);
-    k_scatter_bev<<<ud_blocks(n, 32), 256, smem, stream>>>(feat, (const int4*)coords, n, C, D, H, W, out);
+    if (C % 32 != 0 || C > 1024 || (((uintptr_t)feat) & 15u) != 0) return UD_ERR_UNSUPPORTED;   // [32 x 32] TMA boxes
+    CUtensorMap feat_map;
+    int rc = ud_make_tmap_2d_b32(&feat_map, feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)n, (uint64_t)C,
+                                 (uint64_t)C * sizeof(float), 32, 32, true);
+    if (rc != UD_OK) return rc;
+    size_t smem = (size_t)32 * C * sizeof(float) + 1024;
+    k_scatter_bev<<<ud_blocks(n, 32), 256, smem, stream>>>(feat_map, (const int4*)coords, n, C, D, H, W, out);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }

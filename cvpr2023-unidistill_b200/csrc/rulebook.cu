@@ -81,27 +81,53 @@ k_hash_build(const int4* __restrict__ coords, int n, int D, int H, int W, unsign
     ud_hash_insert(table, mask, key, i);
 }
 
+// One block = 32 consecutive rows x all K taps, staged in shared memory so that BOTH table forms are written coalesced:
+//   nbr   (n, K)   row-major  (API form: pair export, fp32 SIMT kernels)            -- optional
+//   nbr_t (K4, ld) tap-major  (what the tensor-core kernels read: the 128 indices of a (tile, tap) are one 512-byte
+//                  segment; K4 = K rounded up to 4, ld = n rounded up to 128, padding -1)  -- optional
+// plus tile_masks[row / 128] |= 1 << k for every tap that occurs in the 128-row tile (zeroed by the launcher).  This is the
+// round-1 builder and its separate transpose kernel (0.8 ms per step) in one pass.
 __global__ void __launch_bounds__(256)
 k_subm_table(const int4* __restrict__ coords, int n, UdConvGeom g, const unsigned long long* __restrict__ table,
-             uint32_t mask, int* __restrict__ nbr) {
-    int K = g.kD * g.kH * g.kW;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * K) return;
-    int o = (int)(t / K);
-    int k = (int)(t - (long long)o * K);
-    int kx = k % g.kW;
-    int ky = (k / g.kW) % g.kH;
-    int kz = k / (g.kW * g.kH);
-    int4 c = coords[o];
-    int z = c.y + (kz - g.kD / 2) * g.dD;
-    int y = c.z + (ky - g.kH / 2) * g.dH;
-    int x = c.w + (kx - g.kW / 2) * g.dW;
-    int r = -1;
-    if (z >= 0 && z < g.iD && y >= 0 && y < g.iH && x >= 0 && x < g.iW) {
-        uint32_t key = (((uint32_t)c.x * g.iD + z) * g.iH + y) * g.iW + x;
-        r = ud_hash_lookup(table, mask, key);
+             uint32_t mask, int ld, int* __restrict__ nbr, int* __restrict__ nbr_t, unsigned int* __restrict__ tile_masks) {
+    __shared__ int tile[32][33];
+    const int K = g.kD * g.kH * g.kW;
+    const int r0 = blockIdx.x * 32;
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+        const int rl = e >> 5, k = e & 31;            // a warp = one row, lanes = taps: the 27 probes of a row together
+        const int o = r0 + rl;
+        int r = -1;
+        if (o < n && k < K) {
+            const int kx = k % g.kW;
+            const int ky = (k / g.kW) % g.kH;
+            const int kz = k / (g.kW * g.kH);
+            const int4 c = coords[o];
+            const int z = c.y + (kz - g.kD / 2) * g.dD;
+            const int y = c.z + (ky - g.kH / 2) * g.dH;
+            const int x = c.w + (kx - g.kW / 2) * g.dW;
+            if (z >= 0 && z < g.iD && y >= 0 && y < g.iH && x >= 0 && x < g.iW) {
+                const uint32_t key = (((uint32_t)c.x * g.iD + z) * g.iH + y) * g.iW + x;
+                r = ud_hash_lookup(table, mask, key);
+            }
+        }
+        tile[rl][k] = r;
     }
-    nbr[t] = r;
+    __syncthreads();
+    if (nbr != nullptr) {                              // 32 rows x K ints are contiguous in the row-major table
+        const int rows = min(32, n - r0);
+        for (int e = threadIdx.x; e < rows * K; e += 256) nbr[(size_t)r0 * K + e] = tile[e / K][e % K];
+    }
+    if (nbr_t != nullptr) {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // lanes = rows, warps = taps
+        const int k_pad = (K + 3) / 4 * 4;
+        unsigned int m = 0u;
+        for (int k = ty; k < k_pad; k += 8) {
+            const int v = k < K ? tile[tx][k] : -1;
+            if (r0 + tx < ld) nbr_t[(size_t)k * ld + r0 + tx] = v;
+            if (__ballot_sync(0xffffffffu, r0 + tx < n && v >= 0)) m |= 1u << k;
+        }
+        if (tile_masks != nullptr && tx == 0 && m) atomicOr(tile_masks + (r0 >> 7), m);
+    }
 }
 
 // out coordinate along one axis for input coordinate `in` and kernel tap `k`; -1 if none.
@@ -208,24 +234,54 @@ k_conv_out_coords(const unsigned int* __restrict__ bitmap, const int* __restrict
     }
 }
 
+// Same 32-row block scheme for the input-major table of a strided convolution; the output-major table is scattered
+// (nbr_out[o][k] = i, both forms, pre-filled with -1 by the launcher) with its tile masks set by a test-then-atomicOr.
 __global__ void __launch_bounds__(256)
 k_conv_tables(const int4* __restrict__ coords, int n, UdConvGeom g, const uint32_t* __restrict__ tab,
-              const unsigned int* __restrict__ bitmap, const int* __restrict__ prefix, int n_out,
-              int* __restrict__ nbr_in, int* __restrict__ nbr_out) {
-    int K = g.kD * g.kH * g.kW;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * K) return;
-    int i = (int)(t / K);
-    int k = (int)(t - (long long)i * K);
-    uint32_t key;
-    int o = -1;
-    if (ud_pair_key(coords[i], k, g, tab, &key)) {
-        unsigned int word = bitmap[key >> 5];
-        unsigned int below = word & ((1u << (key & 31)) - 1u);
-        o = prefix[key >> 5] + __popc(below);
-        if (o < n_out) nbr_out[(size_t)o * K + k] = i; else o = -1;
+              const unsigned int* __restrict__ bitmap, const int* __restrict__ prefix, int n_out, int ld_in, int ld_out,
+              int* __restrict__ nbr_in, int* __restrict__ nbr_out, int* __restrict__ nbr_in_t,
+              unsigned int* __restrict__ masks_in, int* __restrict__ nbr_out_t, unsigned int* __restrict__ masks_out) {
+    __shared__ int tile[32][33];
+    const int K = g.kD * g.kH * g.kW;
+    const int r0 = blockIdx.x * 32;
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+        const int rl = e >> 5, k = e & 31;
+        const int i = r0 + rl;
+        int o = -1;
+        uint32_t key;
+        if (i < n && k < K && ud_pair_key(coords[i], k, g, tab, &key)) {
+            const unsigned int word = bitmap[key >> 5];
+            const unsigned int below = word & ((1u << (key & 31)) - 1u);
+            o = prefix[key >> 5] + __popc(below);
+            if (o < n_out) {
+                if (nbr_out) nbr_out[(size_t)o * K + k] = i;
+                if (nbr_out_t) {
+                    nbr_out_t[(size_t)k * ld_out + o] = i;
+                    unsigned int* mw = masks_out + (o >> 7);
+                    if (!((*reinterpret_cast<volatile unsigned int*>(mw) >> k) & 1u)) atomicOr(mw, 1u << k);
+                }
+            } else {
+                o = -1;
+            }
+        }
+        tile[rl][k] = o;
     }
-    nbr_in[t] = o;
+    __syncthreads();
+    if (nbr_in != nullptr) {
+        const int rows = min(32, n - r0);
+        for (int e = threadIdx.x; e < rows * K; e += 256) nbr_in[(size_t)r0 * K + e] = tile[e / K][e % K];
+    }
+    if (nbr_in_t != nullptr) {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const int k_pad = (K + 3) / 4 * 4;
+        unsigned int m = 0u;
+        for (int k = ty; k < k_pad; k += 8) {
+            const int v = k < K ? tile[tx][k] : -1;
+            if (r0 + tx < ld_in) nbr_in_t[(size_t)k * ld_in + r0 + tx] = v;
+            if (__ballot_sync(0xffffffffu, r0 + tx < n && v >= 0)) m |= 1u << k;
+        }
+        if (tx == 0 && m) atomicOr(masks_in + (r0 >> 7), m);
+    }
 }
 
 // ---- spconv-shaped pair list export ---------------------------------------------------------
@@ -333,10 +389,11 @@ int ud_rulebook_subm_workspace_bytes(int n, size_t* bytes) {
 // coords: (n,4) int32 [b,z,y,x] device; spatial_shape/ksize/dilation: HOST int[3] (z,y,x)
 // nbr_out: (n, K) int32 device, K = kz*ky*kx (odd sizes only).
 int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatial_shape, const int* ksize,
-                     const int* dilation, int* nbr_out, void* workspace, size_t workspace_bytes,
-                     void* stream_) {
+                     const int* dilation, int* nbr_out, int* nbr_out_t, unsigned int* tile_masks, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (n < 0 || (n > 0 && (!coords || !nbr_out))) return UD_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && (!coords || (!nbr_out && !nbr_out_t)))) return UD_ERR_INVALID_ARG;
+    if (nbr_out_t && !tile_masks) return UD_ERR_INVALID_ARG;
     int ones[3] = {1, 1, 1}, zeros[3] = {0, 0, 0};
     UdConvGeom g = ud_make_geom(batch_size, spatial_shape, spatial_shape, ksize, ones, zeros, dilation);
     if ((g.kD & 1) == 0 || (g.kH & 1) == 0 || (g.kW & 1) == 0) return UD_ERR_UNSUPPORTED;
@@ -350,9 +407,10 @@ int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatia
     k_hash_build<<<ud_blocks(n, 256), 256, 0, stream>>>((const int4*)coords, n, g.iD, g.iH, g.iW, table,
                                                         cap - 1);
     UD_LAUNCH_CHECK();
-    int K = g.kD * g.kH * g.kW;
-    k_subm_table<<<ud_blocks((long long)n * K, 256), 256, 0, stream>>>((const int4*)coords, n, g, table,
-                                                                       cap - 1, nbr_out);
+    const int ld = (n + 127) / 128 * 128;
+    if (tile_masks) UD_CUDA_TRY(cudaMemsetAsync(tile_masks, 0, sizeof(unsigned int) * (size_t)(ld / 128), stream));
+    k_subm_table<<<ud_blocks(nbr_out_t ? ld : n, 32), 256, 0, stream>>>((const int4*)coords, n, g, table, cap - 1, ld,
+                                                                        nbr_out, nbr_out_t, tile_masks);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -445,11 +503,13 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
 int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int* in_shape,
                           const int* out_shape, const int* ksize, const int* stride, const int* padding,
                           const int* dilation, int order, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
+                          int* nbr_in_t, unsigned int* masks_in, int* nbr_out_t, unsigned int* masks_out,
                           void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_in < 0 || n_out < 0) return UD_ERR_INVALID_ARG;
-    if (n_in > 0 && (!coords || !nbr_in)) return UD_ERR_INVALID_ARG;
-    if (n_out > 0 && (!out_coords || !nbr_out)) return UD_ERR_INVALID_ARG;
+    if (n_in > 0 && (!coords || (!nbr_in && !nbr_in_t))) return UD_ERR_INVALID_ARG;
+    if (n_out > 0 && (!out_coords || (!nbr_out && !nbr_out_t))) return UD_ERR_INVALID_ARG;
+    if ((nbr_in_t && !masks_in) || (nbr_out_t && !masks_out)) return UD_ERR_INVALID_ARG;
     int rc = UD_OK;
     UdConvGeom g = ud_make_geom(batch_size, in_shape, out_shape, ksize, stride, padding, dilation, order, &rc);
     if (rc != UD_OK) return rc;
@@ -460,15 +520,23 @@ int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int
     if (rc != UD_OK) return rc;
     int K = g.kD * g.kH * g.kW;
     int words = (int)L.words;
+    const int ld_in = (n_in + 127) / 128 * 128, ld_out = (n_out + 127) / 128 * 128;
+    const int k_pad = (K + 3) / 4 * 4;
     if (n_out > 0) {
-        UD_CUDA_TRY(cudaMemsetAsync(nbr_out, 0xFF, (size_t)n_out * K * sizeof(int), stream));
+        if (nbr_out) UD_CUDA_TRY(cudaMemsetAsync(nbr_out, 0xFF, (size_t)n_out * K * sizeof(int), stream));
+        if (nbr_out_t) {
+            UD_CUDA_TRY(cudaMemsetAsync(nbr_out_t, 0xFF, (size_t)k_pad * ld_out * sizeof(int), stream));
+            UD_CUDA_TRY(cudaMemsetAsync(masks_out, 0, sizeof(unsigned int) * (size_t)(ld_out / 128), stream));
+        }
         k_conv_out_coords<<<ud_blocks(words, 256), 256, 0, stream>>>(L.bitmap, L.prefix, words, g, n_out,
                                                                      (int4*)out_coords);
         UD_LAUNCH_CHECK();
     }
     if (n_in > 0) {
-        k_conv_tables<<<ud_blocks((long long)n_in * K, 256), 256, 0, stream>>>(
-            (const int4*)coords, n_in, g, L.tab, L.bitmap, L.prefix, n_out, nbr_in, nbr_out);
+        if (masks_in) UD_CUDA_TRY(cudaMemsetAsync(masks_in, 0, sizeof(unsigned int) * (size_t)(ld_in / 128), stream));
+        k_conv_tables<<<ud_blocks(nbr_in_t ? ld_in : n_in, 32), 256, 0, stream>>>(
+            (const int4*)coords, n_in, g, L.tab, L.bitmap, L.prefix, n_out, ld_in, ld_out, nbr_in, nbr_out, nbr_in_t,
+            masks_in, nbr_out_t, masks_out);
         UD_LAUNCH_CHECK();
     }
     return UD_OK;

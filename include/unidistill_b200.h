@@ -81,9 +81,13 @@ int ud_hard_voxelize(const float* points, const int* sample_offsets, int batch_s
  *       gathers want.  The row order of a sparse tensor is not observable after SparseConvTensor.dense().
  * ------------------------------------------------------------------------------------------- */
 int ud_rulebook_subm_workspace_bytes(int n, size_t* bytes);
+/* Every builder can emit, besides / instead of the row-major (n,K) table, the tap-major form the tensor-core kernels read:
+ * nbr_*_t (K4, ld) with K4 = K rounded up to 4 and ld = n rounded up to 128 (padding -1), plus tile masks (ld/128) uint32
+ * with bit k set when tap k occurs in the 128-row tile (same layout as ud_rulebook_transpose produces).  Any of the table
+ * outputs may be NULL (at least one per side); a tap-major table needs its mask array. */
 int ud_rulebook_subm(const int* coords, int n, int batch_size, const int* spatial_shape, const int* ksize,
-                     const int* dilation, int* nbr_out, void* workspace, size_t workspace_bytes,
-                     void* stream);
+                     const int* dilation, int* nbr_out, int* nbr_out_t, unsigned int* tile_masks, void* workspace,
+                     size_t workspace_bytes, void* stream);
 int ud_rulebook_conv_workspace_bytes(int batch_size, const int* out_shape, int order, size_t* bytes);
 /* phase 1: n_out_dev (device int) <- number of output rows; keep the workspace for phase 2 */
 int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const int* in_shape,
@@ -94,6 +98,7 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
 int ud_rulebook_conv_fill(const int* coords, int n_in, int batch_size, const int* in_shape,
                           const int* out_shape, const int* ksize, const int* stride, const int* padding,
                           const int* dilation, int order, int n_out, int* out_coords, int* nbr_in, int* nbr_out,
+                          int* nbr_in_t, unsigned int* masks_in, int* nbr_out_t, unsigned int* masks_out,
                           void* workspace, size_t workspace_bytes, void* stream);
 /* order (n) int32 <- row indices of coords (n,4) sorted by (b, Morton(z,y,x)) on the (z,y,x) grid spatial_shape (HOST
  * int[3]); stable.  Used once at the entry of the sparse encoder (the voxelizer emits first-come order). */

@@ -490,3 +490,26 @@ def test_backbone_gradients_through_the_whole_stack(cuda, native_lib):
     # the CPU in summation order only) worst 4.8e-2 / median 3.7e-3 / cosine 0.999995
     assert e_tc[worst_tc] <= max(3 * e_fp[worst_fp], 2e-2), "tensor-core gradients are off beyond the fp32 noise floor"
     assert float(np.median(list(e_tc.values()))) <= max(5 * float(np.median(list(e_fp.values()))), 5e-3)
+
+
+@pytest.mark.parametrize("kind", ["subm", "strided"])
+def test_builders_emit_the_tap_major_form(cuda, native_lib, kind):
+    """The rulebook builders write the tap-major table + tile masks themselves: identical to ud_rulebook_transpose of the
+    row-major table (the round-1 path), including the -1 padding of rows [n, ld) and taps [K, K4)."""
+    from unidistill_b200 import native, sparse
+
+    rng = np.random.default_rng(9)
+    B, shape, n = 2, [11, 30, 28], 4100            # 4100 rows: a ragged last tile
+    coords, _ = _clustered_sparse(rng, B, shape, n, 1)
+    ct = torch.from_numpy(coords).to(cuda)
+    rb = sparse.build_subm_rulebook(ct, B, shape, 3) if kind == "subm" else sparse.build_conv_rulebook(ct, B, shape, 3, 2, 1)
+    for table in ([rb.nbr_out] if kind == "subm" else [rb.nbr_out, rb.nbr_in]):
+        got_t, got_m = rb.tap_major(table)                       # seeded by the builder
+        rows, K = int(table.shape[0]), int(table.shape[1])
+        ld = (rows + 127) // 128 * 128
+        ref_t = torch.empty(((K + 3) // 4 * 4, ld), dtype=torch.int32, device=cuda)
+        ref_m = torch.empty((ld // 128,), dtype=torch.int32, device=cuda)
+        rc = native_lib.ud_rulebook_transpose(native.ptr(table), rows, K, native.ptr(ref_t), native.ptr(ref_m),
+                                              native.stream_ptr(cuda))
+        assert rc == 0
+        assert torch.equal(got_t, ref_t) and torch.equal(got_m, ref_m)
