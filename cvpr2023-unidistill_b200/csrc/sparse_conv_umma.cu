@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "umma_common.cuh"
 #include "det_reduce.cuh"
+#include "tma.cuh"
 #include <cuda_bf16.h>
 
 namespace {
@@ -204,7 +205,8 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(DG_THREADS, 1)
-k_spconv_umma_dg(const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
+k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __restrict__ in,
+                 const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
                  int tiles, float* __restrict__ out, unsigned char* __restrict__ stats, int stat_group) {
     constexpr int TAPG = ts_tapg(CIN);               // kernel taps per 64-channel stage
@@ -425,16 +427,16 @@ k_spconv_umma_dg(const float* __restrict__ in, const float* __restrict__ wpacked
                 bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
             }
         } else if (warp == 18 && lane == 0) {
+            // row-index segments of every stage: ONE TMA tensor load per stage -- a [TAPG taps x 128 rows] box of the tap-major
+            // table (2-D tensor map over nbr_t: K4 x ld int32), landing as TAPG consecutive 512-byte segments
+            tma_prefetch_desc(&idx_map);
             for (int it = 0; it < n_a; ++it) {
                 const int islot = it % DG_IDX_STAGES;
                 mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / DG_IDX_STAGES)) & 1u) ^ 1u);
                 const unsigned e = a_sched[it];
                 mbar_arrive_expect_tx(bar_idx_full + 8 * islot, IDX_INTS * 4);
-#pragma unroll
-                for (int g = 0; g < TAPG; ++g) {
-                    const int* seg = nbr_t + (size_t)((e & 31) * TAPG + g) * ld_t + row0 + (e >> 8) * TILE_M;
-                    bulk_g2s(smem_idx + (islot * TAPG + g) * TILE_M * 4, seg, TILE_M * 4, bar_idx_full + 8 * islot);
-                }
+                tma_load_2d(smem_idx + islot * IDX_INTS * 4, &idx_map, row0 + (int)(e >> 8) * TILE_M, (int)(e & 31) * TAPG,
+                            bar_idx_full + 8 * islot);
             }
         }
         __syncwarp();
@@ -566,7 +568,12 @@ int launch_umma_dg(const float* in, const float* wpacked, const float* bias, con
     dg_grid(n_out, COUT, &tiles, &ctas);
     if (stats != nullptr)       // arrival counters of the statistics reduction
         UD_CUDA_TRY(cudaMemsetAsync(stats + DG_STAT_FINAL_BYTES, 0, UD_DET_COUNTER_BYTES, stream));
-    kern<<<ctas, DG_THREADS, smem, stream>>>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
+    CUtensorMap idx_map;        // tap-major table as a 2-D tensor: (K rounded up to 4) rows x (n_out rounded up to 128) int32
+    const uint64_t ld = (uint64_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
+    int rc = ud_make_tmap_2d_b32(&idx_map, nbr_t, CU_TENSOR_MAP_DATA_TYPE_INT32, (uint64_t)((K + 3) / 4 * 4), ld, ld * 4,
+                                 (uint32_t)ts_tapg(CIN), TILE_M);
+    if (rc != UD_OK) return rc;
+    kern<<<ctas, DG_THREADS, smem, stream>>>(idx_map, in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
                                              ud_det_group(ctas));
     UD_LAUNCH_CHECK();
     return UD_OK;
