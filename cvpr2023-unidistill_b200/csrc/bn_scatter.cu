@@ -208,6 +208,37 @@ k_scatter_bev(const __grid_constant__ CUtensorMap feat_map, const int4* __restri
         }
 }
 
+// Channel counts that are not a multiple of 32 (e.g. the 5-channel pillar means of BASELINE configs[0]): the tile is staged
+// by the threads themselves with a padded pitch.
+__global__ void __launch_bounds__(256)
+k_scatter_bev_generic(const float* __restrict__ feat, const int4* __restrict__ coords, int n, int C, int D, int H,
+                      int W, float* __restrict__ out) {
+    extern __shared__ float tile_g[];   // [32][C+1]
+    __shared__ long long base_off[32];
+    const int row0 = blockIdx.x * 32;
+    const int rows = min(32, n - row0);
+    for (int e = threadIdx.x; e < 32 * C; e += blockDim.x) {
+        int r = e / C, c = e - r * C;
+        tile_g[r * (C + 1) + c] = r < rows ? feat[(size_t)(row0 + r) * C + c] : 0.f;
+    }
+    if (threadIdx.x < 32) {
+        long long off = -1;
+        if (threadIdx.x < rows) {
+            int4 q = coords[row0 + threadIdx.x];   // b, z, y, x
+            off = (((long long)q.x * C * D + q.y) * H + q.z) * W + q.w;
+        }
+        base_off[threadIdx.x] = off;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const long long off = base_off[lane];
+    const long long cstride = (long long)D * H * W;
+    if (off >= 0)
+        for (int c = wid; c < C; c += nw) out[off + c * cstride] = tile_g[lane * (C + 1) + c];
+}
+
 __global__ void __launch_bounds__(256)
 k_gather_bev(const float* __restrict__ dense, const int4* __restrict__ coords, int n, int C, int D, int H,
              int W, float* __restrict__ feat) {
@@ -346,7 +377,12 @@ int ud_scatter_to_bev(const float* feat, const int* coords, int n, int batch_siz
     if (zero_fill)
         UD_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)batch_size * C * D * H * W * sizeof(float), stream));
     if (n == 0) return UD_OK;
-    if (C % 32 != 0 || C > 1024 || (((uintptr_t)feat) & 15u) != 0) return UD_ERR_UNSUPPORTED;   // [32 x 32] TMA boxes
+    if (C % 32 != 0 || (((uintptr_t)feat) & 15u) != 0) {           // no [32 x 32] TMA boxes: thread-staged tile
+        size_t smem_g = (size_t)32 * (C + 1) * sizeof(float);
+        k_scatter_bev_generic<<<ud_blocks(n, 32), 256, smem_g, stream>>>(feat, (const int4*)coords, n, C, D, H, W, out);
+        UD_LAUNCH_CHECK();
+        return UD_OK;
+    }
     CUtensorMap feat_map;
     int rc = ud_make_tmap_2d_b32(&feat_map, feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)n, (uint64_t)C,
                                  (uint64_t)C * sizeof(float), 32, 32, true);
