@@ -482,11 +482,14 @@ def _algorithmic(name, a, meta, cache):
     if name == "ud_rulebook_transpose":
         n, K = a[1], a[2]
         return "rulebook tap-major transpose + tile masks", "hbm", 2 * n * K * 4 + (n + 127) // 128 * 4, 0
+    if name == "ud_rulebook_windows":
+        return "rulebook window starts (per tile and tap group)", "hbm", a[1] * a[2] * 4, 0
     if name == "ud_rulebook_pairs":
         return "rulebook spconv-pairs export", "hbm", 3 * a[1] * a[2] * 4, 0
-    if name in ("ud_sparse_conv_tc_forward", "ud_sparse_conv_forward"):
-        tc = name == "ud_sparse_conv_tc_forward"
-        n_out, K, cin, cout = (a[5], a[6], a[7], a[8]) if tc else (a[4], a[5], a[6], a[7])
+    if name in ("ud_sparse_conv_tc_forward", "ud_sparse_conv_forward", "ud_sparse_conv_tc_forward_window"):
+        tc = name != "ud_sparse_conv_forward"
+        n_out, K, cin, cout = ((a[7], a[8], a[9], a[10]) if name.endswith("window") else (a[6], a[7], a[8], a[9])) if tc \
+            else (a[4], a[5], a[6], a[7])
         n_in = meta.get("n_in", n_out)
         P = _lazy_int(cache, meta["table"], lambda t: (t >= 0).sum().item()) if "table" in meta else n_out * K
         kern = meta.get("kernel", "k_spconv_umma_dg" if tc else "k_spconv_gather_gemm")
@@ -500,6 +503,8 @@ def _algorithmic(name, a, meta, cache):
         return ("%s<%d,%d> K=%d" % ("k_spconv_wgrad_umma" if tc else "k_spconv_wgrad", cin, cout, K),
                 "tensor" if (tc and cin >= 32) else "hbm",
                 4 * (n_in * cin + n_rows * cout + n_rows * K + K * cin * cout), 2.0 * P * cin * cout)
+    if name == "ud_split_bf16":
+        return "bf16 hi/lo split of conv inputs", "hbm", 2 * a[1] * a[2] * 4, 0
     if name == "ud_sparse_conv_tc_pack_weights":
         return "conv weight pack (bf16 hi/lo, swizzled)", "hbm", 2 * a[1] * a[2] * a[3] * 4, 0
     if name == "ud_bn_stats":

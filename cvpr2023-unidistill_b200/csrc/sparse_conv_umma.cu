@@ -78,6 +78,28 @@ k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int ta
     blk[(size_t)cout * ks + off] = lo;
 }
 
+// fp32 rows -> "split" rows of the same size: every 4 consecutive channels c .. c+3 become one 16-byte group
+//   { bf16x2(hi c, hi c+1), bf16x2(hi c+2, hi c+3), bf16x2(lo c, lo c+1), bf16x2(lo c+2, lo c+3) },   hi = bf16_rn(x), lo = bf16_rn(x - hi)
+// i.e. exactly the registers a gather thread of k_spconv_umma_dg hands to tcgen05.st for its 4 channels.  The convolution
+// gathers every input row once per kernel tap that uses it (~16x on average), and splitting after the gather costs 64
+// conversion + 64 subtract / shift instructions per thread and stage -- the XU and ALU pipes, not the tensor or memory
+// pipes, bound the kernel (profiles/r02_ncu_full_dg.md).  Splitting ONCE per element moves that work out of the gather.
+__global__ void __launch_bounds__(256)
+k_split_bf16(const float4* __restrict__ x, long long n4, uint4* __restrict__ out) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x[t];
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h01);
+        o.y = *reinterpret_cast<const uint32_t*>(&h23);
+        o.z = *reinterpret_cast<const uint32_t*>(&l01);
+        o.w = *reinterpret_cast<const uint32_t*>(&l23);
+        out[t] = o;
+    }
+}
+
 // [rows][K] -> [K][rows] (tap-major), so that the 128 indices of one (tile, tap) are one 512-byte segment; also
 // tile_masks[row / 128] |= 1 << k for every tap k that occurs in the 128-row tile (zeroed by the launcher).
 __global__ void __launch_bounds__(256)
@@ -203,7 +225,114 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
         : "memory");
 }
 
-template <int CIN, int COUT>
+// Epilogue shared by the tensor-core forward kernels (called by ALL threads; warps 0-15 do the work: warp w -> TMEM lane
+// quadrant w & 3, tiles (w >> 2), (w >> 2) + 4, ...): tcgen05.ld -> + bias -> st.global.v4, plus the per-channel sum / sum of
+// squares of the output for the BatchNorm that follows, reduced in a fixed order (det_reduce.cuh).
+template <int COUT, int NTHREADS>
+__device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, int tiles, int rows_cta, int row0,
+                                            const unsigned int* tile_mask_s, uint32_t tmem_acc,
+                                            const float* __restrict__ bias, float* __restrict__ out,
+                                            unsigned char* __restrict__ stats, float* wpart_s, int stat_group,
+                                            int* stat_last_s) {
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
+    if (warp < 16) {
+        if (n_a > 0) {
+            mbar_wait(bar_acc, 0u);
+            tc_fence_after();
+        }
+        const int q = warp & 3;
+        constexpr int CW = COUT >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int t = warp >> 2; t < tiles; t += DG_SETS) {
+            if (t * TILE_M >= rows_cta) break;
+            const bool has_acc = tile_mask_s[t] != 0u;
+            const int r_local = t * TILE_M + q * 32 + lane;
+            const int row = row0 + r_local;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                uint32_t v[32];
+                if (has_acc) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = 0u;
+                }
+                const bool row_ok = r_local < rows_cta;
+                float* dst = out + (size_t)row * COUT + c0;
+#pragma unroll
+                for (int i = 0; i < CW; i += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[i + 0]);
+                    o.y = __uint_as_float(v[i + 1]);
+                    o.z = __uint_as_float(v[i + 2]);
+                    o.w = __uint_as_float(v[i + 3]);
+                    if (bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
+                    if (stats != nullptr) {
+                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
+                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
+                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
+                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
+                    }
+                }
+                if (stats != nullptr) {
+                    float a[32], sq[32];
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        a[i] = __uint_as_float(v[i]);
+                        sq[i] = a[i] * a[i];
+                    }
+                    int col = 0;
+#pragma unroll
+                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
+#pragma unroll
+                        for (int i = 0; i < sft; ++i) {
+                            const float sa = up ? a[i] : a[i + sft];
+                            const float sb = up ? sq[i] : sq[i + sft];
+                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
+                            const float rq = __shfl_xor_sync(0xffffffffu, sb, sft);
+                            a[i] = (up ? a[i + sft] : a[i]) + ra;
+                            sq[i] = (up ? sq[i + sft] : sq[i]) + rq;
+                        }
+                        if (up) col += sft;
+                    }
+                    if (CW == 16) {
+                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
+                        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 16);
+                    }
+                    if (CW == 32 || lane < 16) {          // the warp's own slot, tiles in ascending order: no atomics
+                        wpart_s[(warp * 2 + 0) * COUT + c0 + col] += a[0];
+                        wpart_s[(warp * 2 + 1) * COUT + c0 + col] += sq[0];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (stats != nullptr) {
+        // 16 warp slots -> this CTA's partial (fixed order), then the fixed-order cross-CTA reduction of det_reduce.cuh:
+        // final[2 * COUT] doubles = per-channel sum | sum of squares of `out`, bit-reproducible from run to run
+        float v = 0.f;
+        if (tid < 2 * COUT) {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) v += wpart_s[(w * 2 + tid / COUT) * COUT + tid % COUT];
+        }
+        ud_det_reduce((double)v, tid, 2 * COUT, stats + DG_STAT_FINAL_BYTES, stat_group,
+                      reinterpret_cast<double*>(stats), stat_last_s);
+        __syncthreads();
+    }
+}
+
+template <int CIN, int COUT, bool SPLIT>
 __global__ void __launch_bounds__(DG_THREADS, 1)
 k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __restrict__ in,
                  const float* __restrict__ wpacked, const float* __restrict__ bias,
@@ -359,13 +488,20 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         const uint4 v = x[h][rr][j];
-                        const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
-                        const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
-                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
-                        hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                        hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                        lo[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
-                        lo[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                        if constexpr (SPLIT) {           // `in` holds pre-split rows (k_split_bf16): nothing to convert
+                            hi[4 * j + 2 * rr + 0] = v.x;
+                            hi[4 * j + 2 * rr + 1] = v.y;
+                            lo[4 * j + 2 * rr + 0] = v.z;
+                            lo[4 * j + 2 * rr + 1] = v.w;
+                        } else {
+                            const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
+                            const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+                            const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
+                            hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                            hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            lo[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
+                            lo[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                        }
                     }
                 const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
                 tmem_st_16x256b_x4(taddr, hi);
@@ -442,101 +578,339 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
         __syncwarp();
     }
 
-    // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
-    if (warp < 16) {
-        if (n_a > 0) {
-            mbar_wait(bar_acc, 0u);
-            tc_fence_after();
-        }
-        const int q = warp & 3;
-        constexpr int CW = COUT >= 32 ? 32 : 16;
-#pragma unroll 1
-        for (int t = warp >> 2; t < tiles; t += DG_SETS) {
-            if (t * TILE_M >= rows_cta) break;
-            const bool has_acc = tile_mask_s[t] != 0u;
-            const int r_local = t * TILE_M + q * 32 + lane;
-            const int row = row0 + r_local;
-#pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += CW) {
-                uint32_t v[32];
-                if (has_acc) {
-                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * COUT + c0);
-                    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-                    tmem_ld_wait();
-                } else {
+    dg_epilogue<COUT, DG_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
+                                  stat_group, &stat_last_s);
+    if (warp == 16) tmem_dealloc(tmem_acc, 512);
+}
+
+// =====================================================================================================================
+// Window-staged variant for 3x3x3 kernels with 64 input channels (k_spconv_umma_win).
+//
+// Under the raster row order (rows sorted by (b, z, y, x)) the rows that the three kx taps of one (kz, ky) pair gather for
+// a 128-row tile are x-adjacent voxels of neighbouring lines, i.e. they lie in a narrow index window: measured on the
+// bench clouds, 97 % of them inside [lo, lo + 160) with lo = the smallest gathered row (tools/window_coverage_probe.py,
+// profiles/r02_window_probe.txt).  So instead of 3 x 128 per-thread gathers from global memory, TMA stages that window
+// ONCE per (tile, kz, ky) -- two tensor loads of a [160 rows x 32 channels] box, 128-byte swizzle -- and the gather warps
+// build the three taps' operands from shared memory (conflict-free LDS.128 thanks to the swizzle); rows outside the
+// window (3 %) still come from global memory.  Global gather traffic drops ~3x and, more to the point, stops depending on
+// how many loads an SM can keep in flight (the limit of k_spconv_umma_dg, profiles/r02_ncu_full_dg.md).
+// Schedule = unit major: unit = (kz, ky) group; inside a unit tile by tile, the tile's three kx stages back to back; the
+// unit's three weight slices stay resident in a 4-slot ring (a slice is released after its last tile).
+//   warps 0-15 gather sets | 16 MMA issuer | 17 weight slices | 18 row-index segments (TMA) | 19 windows (TMA)
+constexpr int WIN_ROWS = 160;
+constexpr int WIN_SLOTS = 3;
+constexpr int WIN_THREADS = 640;
+constexpr int WIN_B_RING = 4;
+constexpr int WIN_HALF_BYTES = WIN_ROWS * 128;          // one 32-channel half of a window, 128-byte rows
+constexpr int WIN_BYTES = 2 * WIN_HALF_BYTES;
+constexpr int WIN_GROUPS = 9;
+constexpr int WIN_CIN = 64;
+__host__ __device__ constexpr size_t win_smem_bytes(int cout) {
+    return (size_t)WIN_B_RING * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * TILE_M * 4 + (size_t)WIN_SLOTS * WIN_BYTES + 1024;
+}
+
+// lane g < 9 owns group g (taps 3g .. 3g+2).  A group that occurs in any tile gets all three weight slices, a tile that has
+// any tap of the group gets all three stages (an absent tap is an all -1 index segment = a zero operand), so every
+// (group, tile) window is read by exactly 3 stages x 4 warps.
+//   b_sched[ib] = tap;  w_sched[u] = group | tile << 4;  a_sched[it] = tap | tile << 8 | release << 11;  a_slice[it] = ib
+__device__ __forceinline__ void build_schedule_win(const unsigned int* tile_mask_s, int tiles, int lane,
+                                                   unsigned short* a_sched, unsigned short* a_slice,
+                                                   unsigned short* b_sched, unsigned short* w_sched, int* n_a_s,
+                                                   int* n_b_s) {
+    unsigned int gm = 0u;                                 // bit t: tile t has some tap of group `lane`
+    if (lane < WIN_GROUPS)
+        for (int t = 0; t < tiles; ++t) gm |= (((tile_mask_s[t] >> (3 * lane)) & 7u) != 0u ? 1u : 0u) << t;
+    const int n_ut = __popc(gm);
+    const int n_gr = gm != 0u;
+    int incl_u = n_ut, incl_g = n_gr;
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = 0u;
-                }
-                const bool row_ok = r_local < rows_cta;
-                float* dst = out + (size_t)row * COUT + c0;
-#pragma unroll
-                for (int i = 0; i < CW; i += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[i + 0]);
-                    o.y = __uint_as_float(v[i + 1]);
-                    o.z = __uint_as_float(v[i + 2]);
-                    o.w = __uint_as_float(v[i + 3]);
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
-                    if (stats != nullptr) {
-                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
-                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
-                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
-                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
-                    }
-                }
-                if (stats != nullptr) {
-                    float a[32], sq[32];
-#pragma unroll
-                    for (int i = 0; i < CW; ++i) {
-                        a[i] = __uint_as_float(v[i]);
-                        sq[i] = a[i] * a[i];
-                    }
-                    int col = 0;
-#pragma unroll
-                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
-                        const bool up = (lane & sft) != 0;
-#pragma unroll
-                        for (int i = 0; i < sft; ++i) {
-                            const float sa = up ? a[i] : a[i + sft];
-                            const float sb = up ? sq[i] : sq[i + sft];
-                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
-                            const float rq = __shfl_xor_sync(0xffffffffu, sb, sft);
-                            a[i] = (up ? a[i + sft] : a[i]) + ra;
-                            sq[i] = (up ? sq[i + sft] : sq[i]) + rq;
-                        }
-                        if (up) col += sft;
-                    }
-                    if (CW == 16) {
-                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
-                        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 16);
-                    }
-                    if (CW == 32 || lane < 16) {          // the warp's own slot, tiles in ascending order: no atomics
-                        wpart_s[(warp * 2 + 0) * COUT + c0 + col] += a[0];
-                        wpart_s[(warp * 2 + 1) * COUT + c0 + col] += sq[0];
-                    }
-                }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int vu = __shfl_up_sync(0xffffffffu, incl_u, o);
+        const int vg = __shfl_up_sync(0xffffffffu, incl_g, o);
+        if (lane >= o) { incl_u += vu; incl_g += vg; }
+    }
+    if (gm) {
+        const int b_base = 3 * (incl_g - 1);
+        int u = incl_u - n_ut;
+        const unsigned int last = 31u - (unsigned int)__clz(gm);
+        for (int x = 0; x < 3; ++x) b_sched[b_base + x] = (unsigned short)(3 * lane + x);
+        for (int t = 0; t < tiles; ++t) {
+            if (!((gm >> t) & 1u)) continue;
+            w_sched[u] = (unsigned short)(lane | (t << 4));
+            for (int x = 0; x < 3; ++x) {
+                a_sched[3 * u + x] = (unsigned short)((3 * lane + x) | (t << 8) | ((last == (unsigned)t) << 11));
+                a_slice[3 * u + x] = (unsigned short)(b_base + x);
             }
+            ++u;
         }
     }
+    if (lane == 31) {
+        *n_a_s = 3 * incl_u;
+        *n_b_s = 3 * incl_g;
+    }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(WIN_THREADS, 1)
+k_spconv_umma_win(const __grid_constant__ CUtensorMap idx_map, const __grid_constant__ CUtensorMap in_map,
+                  const float* __restrict__ in, const float* __restrict__ wpacked, const float* __restrict__ bias,
+                  const unsigned int* __restrict__ tile_masks, const int* __restrict__ win_lo, int n_out, int tiles,
+                  float* __restrict__ out, unsigned char* __restrict__ stats, int stat_group) {
+    constexpr int KS = 64;
+    constexpr int A_COLS = KS;
+    constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
+    constexpr int B_BYTES = dg_b_bytes(COUT);
+    constexpr int BBF_BYTES = COUT * KS * 2;
+    constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                  ((uint32_t)(TILE_M >> 4) << 24);
+    static_assert(A_STAGES == DG_SETS, "one gather set per TMEM A slot");
+    constexpr int NBAR = 2 * A_STAGES + 2 * WIN_B_RING + 2 * DG_IDX_STAGES + 2 * WIN_SLOTS + 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[NBAR];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int tile_mask_s[MAX_TILES];
+    __shared__ unsigned short a_sched[WIN_GROUPS * 3 * MAX_TILES];
+    __shared__ unsigned short a_slice[WIN_GROUPS * 3 * MAX_TILES];
+    __shared__ unsigned short b_sched[WIN_GROUPS * 3];
+    __shared__ unsigned short w_sched[WIN_GROUPS * MAX_TILES];
+    __shared__ int n_a_s, n_b_s;
+    __shared__ float wpart_s[16 * 2 * COUT];
+    __shared__ int stat_last_s;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int row0 = blockIdx.x * tiles * TILE_M;
+    const int rows_cta = min(tiles * TILE_M, n_out - row0);
+    if (stats != nullptr)
+        for (int i = tid; i < 16 * 2 * COUT; i += WIN_THREADS) wpart_s[i] = 0.f;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t smem_b = smem_base;
+    const uint32_t smem_idx = smem_b + WIN_B_RING * B_BYTES;
+    const int* const idx_ring = reinterpret_cast<const int*>(smem_al + WIN_B_RING * B_BYTES);
+    constexpr int W_OFF = WIN_B_RING * B_BYTES + DG_IDX_STAGES * TILE_M * 4;        // multiple of 1024
+    const uint32_t smem_w = smem_base + W_OFF;
+    const unsigned char* const win_ring = smem_al + W_OFF;
+    const uint32_t bar_a_full = smem_u32(&bars[0]);
+    const uint32_t bar_a_empty = bar_a_full + 8 * A_STAGES;
+    const uint32_t bar_b_full = bar_a_empty + 8 * A_STAGES;
+    const uint32_t bar_b_empty = bar_b_full + 8 * WIN_B_RING;
+    const uint32_t bar_idx_full = bar_b_empty + 8 * WIN_B_RING;
+    const uint32_t bar_idx_empty = bar_idx_full + 8 * DG_IDX_STAGES;
+    const uint32_t bar_w_full = bar_idx_empty + 8 * DG_IDX_STAGES;
+    const uint32_t bar_w_empty = bar_w_full + 8 * WIN_SLOTS;
+    const uint32_t bar_acc = bar_w_empty + 8 * WIN_SLOTS;
+
+    if (tid == 0) {
+        for (int s = 0; s < A_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, TS_GROUP);
+            mbar_init(bar_a_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < WIN_B_RING; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < DG_IDX_STAGES; ++s) {
+            mbar_init(bar_idx_full + 8 * s, 1);
+            mbar_init(bar_idx_empty + 8 * s, TS_GROUP / 32);
+        }
+        for (int s = 0; s < WIN_SLOTS; ++s) {
+            mbar_init(bar_w_full + 8 * s, 1);
+            mbar_init(bar_w_empty + 8 * s, 3 * (TS_GROUP / 32));      // 3 stages x 4 warps read every window
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (tid < MAX_TILES) {
+        const int tile_g = blockIdx.x * tiles + tid;
+        tile_mask_s[tid] = (tid < tiles && tile_g * TILE_M < n_out) ? __ldg(tile_masks + tile_g) : 0u;
+    }
+    if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    __syncthreads();
+    if (warp == 0) build_schedule_win(tile_mask_s, tiles, lane, a_sched, a_slice, b_sched, w_sched, &n_a_s, &n_b_s);
     tc_fence_before();
     __syncthreads();
-    if (stats != nullptr) {
-        // 16 warp slots -> this CTA's partial (fixed order), then the fixed-order cross-CTA reduction of det_reduce.cuh:
-        // final[2 * COUT] doubles = per-channel sum | sum of squares of `out`, bit-reproducible from run to run
-        float v = 0.f;
-        if (tid < 2 * COUT) {
+    tc_fence_after();
+    const int n_a = n_a_s;
+    const int n_b = n_b_s;
+    const uint32_t tmem_acc = tmem_base_s;
+    const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+
+    if (warp < 16) {
+        // ============ gather sets: window in shared memory (or global) -> registers -> bf16 hi/lo -> TMEM ============
+        const int set = warp >> 2;
+        const int q = warp & 3;
+        const int rsub = lane >> 2;
+        const int l4 = lane & 3;                         // this lane reads channels [8 l4, 8 l4 + 8) of each 32-channel half
+        for (int it = set; it < n_a; it += DG_SETS) {
+            const int islot = it % DG_IDX_STAGES;
+            mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / DG_IDX_STAGES)) & 1u);
+            int idx[2][2];
 #pragma unroll
-            for (int w = 0; w < 16; ++w) v += wpart_s[(w * 2 + tid / COUT) * COUT + tid % COUT];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) idx[h][rr] = idx_ring[islot * TILE_M + q * 32 + h * 16 + rr * 8 + rsub];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_idx_empty + 8 * islot);
+            const int u = it / 3;
+            const unsigned we = w_sched[u];
+            const int lo = __ldg(win_lo + (size_t)(blockIdx.x * tiles + (int)(we >> 4)) * WIN_GROUPS + (we & 15u));
+            const int wslot = u % WIN_SLOTS;
+            mbar_wait(bar_w_full + 8 * wslot, ((uint32_t)(u / WIN_SLOTS)) & 1u);
+            const unsigned char* const wbase = win_ring + wslot * WIN_BYTES;
+            uint4 x[2][2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = idx[h][rr];
+                    const unsigned local = (unsigned)(r - lo);
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        x[h][rr][2 * j2] = make_uint4(0u, 0u, 0u, 0u);
+                        x[h][rr][2 * j2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+                        if (r >= 0) {
+                            if (local < (unsigned)WIN_ROWS) {
+                                const unsigned char* rowp = wbase + j2 * WIN_HALF_BYTES + local * 128u;
+                                const unsigned sw = local & 7u;
+                                x[h][rr][2 * j2] = *reinterpret_cast<const uint4*>(rowp + (((2u * l4) ^ sw) << 4));
+                                x[h][rr][2 * j2 + 1] = *reinterpret_cast<const uint4*>(rowp + (((2u * l4 + 1u) ^ sw) << 4));
+                            } else {
+                                ldg_stream256(in + (size_t)r * WIN_CIN + 32 * j2 + 8 * l4, x[h][rr][2 * j2],
+                                              x[h][rr][2 * j2 + 1]);
+                            }
+                        }
+                    }
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_w_empty + 8 * wslot);
+            const int aslot = it % A_STAGES;
+            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo_[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const uint4 v = x[h][rr][j];
+                        const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
+                        const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
+                        hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+                        hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        lo_[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
+                        lo_[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                    }
+                const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
+                tmem_st_16x256b_x4(taddr, hi);
+                tmem_st_16x256b_x4(taddr + KS / 2, lo_);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a_full + 8 * aslot);
         }
-        ud_det_reduce((double)v, tid, 2 * COUT, stats + DG_STAT_FINAL_BYTES, stat_group,
-                      reinterpret_cast<double*>(stats), &stat_last_s);
-        __syncthreads();
+    } else if (warp == 16) {
+        // ============ MMA issuer ============
+        unsigned int started = 0u;
+        for (int it = 0; it < n_a; ++it) {
+            const unsigned e = a_sched[it];
+            const int ib = a_slice[it];
+            const int bslot = ib % WIN_B_RING;
+            // (re-)waiting on a completed phase is immediate: the slot is not re-armed before its release below
+            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / WIN_B_RING)) & 1u);
+            const uint32_t b_base = smem_b + bslot * B_BYTES;
+            const uint64_t db_hi = umma_desc_sw128(b_base);
+            const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
+            const int aslot = it % A_STAGES;
+            const int tile = (e >> 8) & 7;
+            mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
+                const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
+                const uint32_t first = (started >> tile) & 1u;
+#pragma unroll
+                for (int k16 = 0; k16 < KS / 16; ++k16) {
+                    const uint32_t a_hi = a_stage + (uint32_t)(k16 * 8);
+                    const uint32_t a_lo = a_hi + KS / 2;
+                    const uint64_t adv = (uint64_t)(k16 * 2);
+                    umma_bf16_ts(d, a_lo, db_hi + adv, IDESC_BF, (first || k16 > 0) ? 1u : 0u);
+                    umma_bf16_ts(d, a_hi, db_lo + adv, IDESC_BF, 1u);
+                    umma_bf16_ts(d, a_hi, db_hi + adv, IDESC_BF, 1u);
+                }
+                umma_commit(bar_a_empty + 8 * aslot);
+                if ((e >> 11) & 1u) umma_commit(bar_b_empty + 8 * bslot);
+            }
+            started |= 1u << tile;
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(bar_acc);
+        __syncwarp();
+    } else {
+        if (warp == 17 && lane == 0) {
+            // ---- weight slices (bulk copies of the pre-swizzled image) ----
+            for (int ib = 0; ib < n_b; ++ib) {
+                const int bslot = ib % WIN_B_RING;
+                mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / WIN_B_RING)) & 1u) ^ 1u);
+                const float* src = wpacked + (size_t)b_sched[ib] * (B_BYTES / 4);
+                mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
+                bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
+            }
+        } else if (warp == 18 && lane == 0) {
+            // ---- row-index segments: one [1 tap x 128 rows] TMA box per stage ----
+            tma_prefetch_desc(&idx_map);
+            for (int it = 0; it < n_a; ++it) {
+                const int islot = it % DG_IDX_STAGES;
+                mbar_wait(bar_idx_empty + 8 * islot, (((uint32_t)(it / DG_IDX_STAGES)) & 1u) ^ 1u);
+                const unsigned e = a_sched[it];
+                mbar_arrive_expect_tx(bar_idx_full + 8 * islot, TILE_M * 4);
+                tma_load_2d(smem_idx + islot * TILE_M * 4, &idx_map, row0 + (int)((e >> 8) & 7u) * TILE_M, (int)(e & 31u),
+                            bar_idx_full + 8 * islot);
+            }
+        } else if (warp == 19 && lane == 0) {
+            // ---- windows: rows [lo, lo + WIN_ROWS) of the feature matrix, two 32-channel halves, 128-byte swizzle ----
+            tma_prefetch_desc(&in_map);
+            const int n_u = n_a / 3;
+            for (int u = 0; u < n_u; ++u) {
+                const int wslot = u % WIN_SLOTS;
+                mbar_wait(bar_w_empty + 8 * wslot, (((uint32_t)(u / WIN_SLOTS)) & 1u) ^ 1u);
+                const unsigned we = w_sched[u];
+                int lo = __ldg(win_lo + (size_t)(blockIdx.x * tiles + (int)(we >> 4)) * WIN_GROUPS + (we & 15u));
+                if (lo == 0x7fffffff) lo = 0;                 // no valid row in this (tile, group): nothing will be read
+                mbar_arrive_expect_tx(bar_w_full + 8 * wslot, WIN_BYTES);
+                tma_load_2d(smem_w + wslot * WIN_BYTES, &in_map, 0, lo, bar_w_full + 8 * wslot);
+                tma_load_2d(smem_w + wslot * WIN_BYTES + WIN_HALF_BYTES, &in_map, 32, lo, bar_w_full + 8 * wslot);
+            }
+        }
+        __syncwarp();
     }
+
+    dg_epilogue<COUT, WIN_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
+                                   stat_group, &stat_last_s);
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
+}
+
+// win_lo[tile * 9 + g] = smallest valid row index among the three taps 3g .. 3g+2 of the tile's 128 rows (INT_MAX: none)
+__global__ void __launch_bounds__(288)
+k_window_lo(const int* __restrict__ nbr_t, int ld, int* __restrict__ win_lo) {
+    const int tile = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int m = 0x7fffffff;
+    for (int x = 0; x < 3; ++x) {
+        const int* seg = nbr_t + (size_t)(3 * g + x) * ld + (size_t)tile * TILE_M;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = __ldg(seg + lane + 32 * j);
+            if (v >= 0) m = min(m, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) win_lo[(size_t)tile * WIN_GROUPS + g] = m;
 }
 
 // tiles per CTA and grid size for n_out rows (one wave-balanced choice shared by the launcher and the size queries)
@@ -557,12 +931,12 @@ size_t dg_stat_bytes(int n_out, int cout) {
     return (size_t)DG_STAT_FINAL_BYTES + ud_det_reduce_bytes(ctas, 2 * cout);
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool SPLIT>
 int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
                    const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
                    cudaStream_t stream) {
     const size_t smem = dg_smem_bytes(CIN, COUT);
-    auto kern = k_spconv_umma_dg<CIN, COUT>;
+    auto kern = k_spconv_umma_dg<CIN, COUT, SPLIT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int tiles, ctas;
     dg_grid(n_out, COUT, &tiles, &ctas);
@@ -579,6 +953,30 @@ int launch_umma_dg(const float* in, const float* wpacked, const float* bias, con
     return UD_OK;
 }
 
+template <int COUT>
+int launch_umma_win(const float* in, int n_in, const float* wpacked, const float* bias, const int* nbr_t,
+                    const unsigned int* tile_masks, const int* win_lo, int n_out, float* out, unsigned char* stats,
+                    cudaStream_t stream) {
+    const size_t smem = win_smem_bytes(COUT);
+    auto kern = k_spconv_umma_win<COUT>;
+    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tiles, ctas;
+    dg_grid(n_out, COUT, &tiles, &ctas);
+    if (stats != nullptr)
+        UD_CUDA_TRY(cudaMemsetAsync(stats + DG_STAT_FINAL_BYTES, 0, UD_DET_COUNTER_BYTES, stream));
+    CUtensorMap idx_map, in_map;
+    const uint64_t ld = (uint64_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
+    int rc = ud_make_tmap_2d_b32(&idx_map, nbr_t, CU_TENSOR_MAP_DATA_TYPE_INT32, 28, ld, ld * 4, 1, TILE_M);
+    if (rc != UD_OK) return rc;
+    rc = ud_make_tmap_2d_b32(&in_map, in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)n_in, WIN_CIN, WIN_CIN * 4, WIN_ROWS, 32,
+                             true);
+    if (rc != UD_OK) return rc;
+    kern<<<ctas, WIN_THREADS, smem, stream>>>(idx_map, in_map, in, wpacked, bias, tile_masks, win_lo, n_out, tiles, out,
+                                              stats, ud_det_group(ctas));
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
 // forward shapes of VoxelResBackBone8x and the dgrad (cin/cout swapped) of every layer but the first
 bool tc_shape_ok(int K, int cin, int cout) {
     static const int shapes[][2] = {{16, 16}, {16, 32}, {32, 16}, {32, 32}, {32, 64}, {64, 32}, {64, 64}, {64, 128},
@@ -591,8 +989,10 @@ bool tc_shape_ok(int K, int cin, int cout) {
 
 }  // namespace
 
-#define UD_DISPATCH_DG(CI, CO) \
-    if (cin == CI && cout == CO) return launch_umma_dg<CI, CO>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+#define UD_DISPATCH_DG(CI, CO)                                                                                               \
+    if (cin == CI && cout == CO)                                                                                            \
+        return in_is_split ? launch_umma_dg<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
+                           : launch_umma_dg<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
 
 extern "C" {
 
@@ -635,6 +1035,55 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
     return UD_OK;
 }
 
+// Window-staged kernel (k_spconv_umma_win): 1 when a (K, cin, cout) has an instantiation.
+int ud_sparse_conv_tc_window_supported(int K, int cin, int cout) { return (K == 27 && cin == WIN_CIN && cout == 64) ? 1 : 0; }
+
+// win_lo (ceil(n/128), 9) int32 <- per 128-row tile and (kz, ky) tap group, the smallest valid row index of the tap-major
+// table nbr_t (28, ld) of a 3x3x3 kernel (INT_MAX when the group is absent): where the window of the group starts.
+int ud_rulebook_windows(const int* nbr_t, int n, int K, int* win_lo, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || K != 27 || (n > 0 && (!nbr_t || !win_lo))) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    const int n_tiles = (n + TILE_M - 1) / TILE_M;
+    k_window_lo<<<n_tiles, 288, 0, stream>>>(nbr_t, n_tiles * TILE_M, win_lo);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// Same contract as ud_sparse_conv_tc_forward for the shapes ud_sparse_conv_tc_window_supported() accepts, plus n_in (rows
+// of `in`: bounds of the TMA tensor map) and win_lo from ud_rulebook_windows.  Meant for tables whose rows are in raster
+// order (any order is correct: rows outside a window are gathered from global memory).
+int ud_sparse_conv_tc_forward_window(const float* in, int n_in, const void* wpacked_, const float* bias, const int* nbr_t,
+                                     const unsigned int* tile_masks, const int* win_lo, int n_out, int K, int cin,
+                                     int cout, float* out, void* bn_stats, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float* wpacked = (const float*)wpacked_;
+    unsigned char* stats = (unsigned char*)bn_stats;
+    if (!in || !wpacked || !nbr_t || !tile_masks || !win_lo || !out || n_out < 0 || n_in < 1) return UD_ERR_INVALID_ARG;
+    if (!ud_sparse_conv_tc_window_supported(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out | (uintptr_t)stats) & 15u) != 0) return UD_ERR_INVALID_ARG;
+    if (n_out == 0) {
+        if (stats) UD_CUDA_TRY(cudaMemsetAsync(stats, 0, 2 * cout * sizeof(double), stream));
+        return UD_OK;
+    }
+    return launch_umma_win<64>(in, n_in, wpacked, bias, nbr_t, tile_masks, win_lo, n_out, out, stats, stream);
+}
+
+// x (n, C) f32 -> out (n, C) 4-byte words in the split layout (see k_split_bf16): the form of `in` that
+// ud_sparse_conv_tc_forward takes with in_is_split = 1.  C % 4 == 0; 16-byte aligned.
+int ud_split_bf16(const float* x, int n, int C, void* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || C < 4 || C % 4 != 0 || (n > 0 && (!x || !out))) return UD_ERR_INVALID_ARG;
+    if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return UD_ERR_INVALID_ARG;
+    if (n == 0) return UD_OK;
+    const long long n4 = (long long)n * C / 4;
+    const long long want = (n4 + 255) / 256;
+    const int grid = (int)(want < UD_NUM_SMS * 16 ? want : UD_NUM_SMS * 16);
+    k_split_bf16<<<grid, 256, 0, stream>>>((const float4*)x, n4, (uint4*)out);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
 // Size of the statistics buffer ud_sparse_conv_tc_forward needs for n_out rows (0 rows -> header only).
 int ud_sparse_conv_tc_stats_bytes(int n_out, int cout, size_t* bytes) {
     if (!bytes || n_out < 0 || cout < 1 || cout > 256) return UD_ERR_INVALID_ARG;
@@ -649,7 +1098,7 @@ int ud_sparse_conv_tc_stats_bytes(int n_out, int cout, size_t* bytes) {
 // needed.  On return its first 2 * cout doubles hold the per-channel sum and sum of squares of `out` -- the statistics
 // pass of the BatchNorm that follows (spconv_backbone.py:50-56,97-113), fused into the epilogue and reduced in a FIXED
 // order (bit-reproducible from run to run); the rest of the buffer is scratch of that reduction.
-int ud_sparse_conv_tc_forward(const float* in, const void* wpacked_, const float* bias, const int* nbr_t,
+int ud_sparse_conv_tc_forward(const float* in, int in_is_split, const void* wpacked_, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               void* bn_stats, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

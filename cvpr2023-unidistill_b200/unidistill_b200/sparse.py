@@ -35,6 +35,7 @@ class Rulebook:
         self.K = ksize[0] * ksize[1] * ksize[2]
         self._pairs = None
         self._tap_major = {}
+        self._windows = {}
         self.in_coords_for_inverse = None
 
     def tap_major(self, table):
@@ -55,11 +56,26 @@ class Rulebook:
             self._tap_major[key] = t
         return t
 
+    def windows(self, table):
+        """(ceil(n/128), 9) int32: first row of the window of every (128-row tile, (kz, ky) tap group) of a 3x3x3 table
+        (what the window-staged convolution kernel stages by TMA); built once per table and cached."""
+        key = table.data_ptr()
+        w = self._windows.get(key)
+        if w is None:
+            n, K = int(table.shape[0]), int(table.shape[1])
+            table_t, _ = self.tap_major(table)
+            w = torch.empty(((n + 127) // 128, 9), dtype=torch.int32, device=table.device)
+            rc = native.load().ud_rulebook_windows(native.ptr(table_t), n, K, native.ptr(w), native.stream_ptr(table.device))
+            native.check(rc, "ud_rulebook_windows")
+            self._windows[key] = w
+        return w
+
     @classmethod
     def for_table(cls, table):
         """Minimal holder for a bare (n, K) gather table (functional API without a Rulebook)."""
         rb = cls.__new__(cls)
         rb._tap_major = {}
+        rb._windows = {}
         return rb
 
     def num_pairs(self):
@@ -258,10 +274,32 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
             # scratch of the kernel's fixed-order statistics reduction; its first 2 * cout doubles are the result
             stats = torch.empty((native.query_bytes("ud_sparse_conv_tc_stats_bytes", n_out, cout) // 8,),
                                 dtype=torch.float64, device=dev)
-        native.TIMER.meta = meta
-        rc = lib.ud_sparse_conv_tc_forward(native.ptr(feats), native.ptr(packed), native.ptr(bias), native.ptr(table_t),
-                                           native.ptr(masks), n_out, K, cin, cout, native.ptr(out), native.ptr(stats), sp)
-        native.check(rc, "ud_sparse_conv_tc_forward")
+        if USE_WINDOW_KERNEL and lib.ud_sparse_conv_tc_window_supported(K, cin, cout):
+            holder = rb if rb is not None else Rulebook.for_table(table)
+            if holder is not rb:
+                holder._tap_major[table.data_ptr()] = (table_t, masks)
+            win_lo = holder.windows(table)
+            if meta is not None:
+                meta["kernel"] = "k_spconv_umma_win"
+            native.TIMER.meta = meta
+            rc = lib.ud_sparse_conv_tc_forward_window(native.ptr(feats), int(feats.shape[0]), native.ptr(packed),
+                                                      native.ptr(bias), native.ptr(table_t), native.ptr(masks),
+                                                      native.ptr(win_lo), n_out, K, cin, cout, native.ptr(out),
+                                                      native.ptr(stats), sp)
+            native.check(rc, "ud_sparse_conv_tc_forward_window")
+        else:
+            src, is_split = feats, 0
+            if PRE_SPLIT_INPUT and feats.shape[0] > 0:
+                # split the rows into bf16 hi/lo ONCE here instead of once per (row, tap) inside the gather loop
+                src = torch.empty_like(feats)
+                rc = lib.ud_split_bf16(native.ptr(feats), int(feats.shape[0]), cin, native.ptr(src), sp)
+                native.check(rc, "ud_split_bf16")
+                is_split = 1
+            native.TIMER.meta = meta
+            rc = lib.ud_sparse_conv_tc_forward(native.ptr(src), is_split, native.ptr(packed), native.ptr(bias),
+                                               native.ptr(table_t), native.ptr(masks), n_out, K, cin, cout, native.ptr(out),
+                                               native.ptr(stats), sp)
+            native.check(rc, "ud_sparse_conv_tc_forward")
         if stats is not None:
             out._ud_bn_sums = stats[: 2 * cout].view(2, cout)
         return out
@@ -370,6 +408,16 @@ def column_sums(x):
     native.check(rc, "ud_bn_stats")
     return sums[0].float()
 
+
+# Two measured-and-shelved variants of the tensor-core forward kernel, both bit-identical to the default one
+# (tests/test_gpu_sparse_tc.py) and both OFF by default because they lost on B200 (profiles/r02_conv_experiments.md):
+#  * UD_SPCONV_WINDOW=1: 3x3x3 layers with 64 input channels go through k_spconv_umma_win -- TMA stages, once per
+#    (tile, kz, ky), the 160-row window holding 97 % of the rows the three kx taps gather; operands built from shared
+#    memory.  12 calls: 7.45 ms vs 6.44 ms.
+#  * UD_SPCONV_PRESPLIT=1: rows are split into bf16 hi/lo once (ud_split_bf16) instead of once per gathered copy.  The
+#    convolutions get 7-15 % faster (64->64 6.44 -> 6.01 ms), the 62 split passes cost 2.4 ms: net +2.7 ms per step.
+USE_WINDOW_KERNEL = os.environ.get("UD_SPCONV_WINDOW", "0") != "0"
+PRE_SPLIT_INPUT = os.environ.get("UD_SPCONV_PRESPLIT", "0") != "0"
 
 # conv_input of VoxelResBackBone8x has 5 input channels: 20-byte rows that the tensor-core kernels cannot gather (16-byte
 # vector loads, 16 channels per MMA).  Zero-padding rows and weights to 16 channels makes it a <16,Cout> instance of the

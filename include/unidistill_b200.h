@@ -138,9 +138,22 @@ int ud_rulebook_transpose(const int* nbr, int n, int K, int* nbr_t, unsigned int
  * return its first 2*cout doubles are the per-channel sum and sum of squares of `out`, i.e. the statistics pass of the
  * BatchNorm1d that follows the convolution (spconv_backbone.py:50-56,97-113), reduced in a fixed order (bit-reproducible) */
 int ud_sparse_conv_tc_stats_bytes(int n_out, int cout, size_t* bytes);
-int ud_sparse_conv_tc_forward(const float* in, const void* packed, const float* bias, const int* nbr_t,
+/* in_is_split: 0 = `in` is the fp32 feature matrix; 1 = `in` is its split image from ud_split_bf16 (same size: every 4
+ * channels stored as {bf16x2 hi01, hi23, lo01, lo23}), which takes the fp32 -> bf16 hi/lo conversion out of the gather loop:
+ * a row is gathered ~16 times (once per tap that uses it) but has to be split only once. */
+int ud_split_bf16(const float* x, int n, int C, void* out, void* stream);
+int ud_sparse_conv_tc_forward(const float* in, int in_is_split, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               void* bn_stats, void* stream);
+/* Window-staged variant for 3x3x3 kernels with 64 input channels (raster row order): TMA stages, once per (tile, kz, ky),
+ * the 160-row window of the feature matrix that holds the rows the three kx taps gather (97 % of them on the bench
+ * clouds) and the operands are built from shared memory; rows outside the window come from global memory, so any table is
+ * handled correctly.  win_lo (ceil(n/128), 9) int32 from ud_rulebook_windows (first row of every window); n_in = rows of `in`. */
+int ud_sparse_conv_tc_window_supported(int K, int cin, int cout);
+int ud_rulebook_windows(const int* nbr_t, int n, int K, int* win_lo, void* stream);
+int ud_sparse_conv_tc_forward_window(const float* in, int n_in, const void* packed, const float* bias, const int* nbr_t,
+                                     const unsigned int* tile_masks, const int* win_lo, int n_out, int K, int cin,
+                                     int cout, float* out, void* bn_stats, void* stream);
 
 /* Tensor-core weight gradient (csrc/sparse_conv_wgrad_umma.cu): dw[k] += in[nbr[o][k],:]^T dout[o,:] as tcgen05 MMAs
  * over the row dimension (both operands MN-major in shared memory, rounded to TF32 to-nearest on the way in, fp32

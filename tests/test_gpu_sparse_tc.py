@@ -266,3 +266,90 @@ def test_tc_wgrad_linearity_full_size(cuda, native_lib):
     lin = 2.0 * d1 + d2
     assert float((d12 - lin).abs().max() / lin.abs().max()) < WGRAD_TOL
     assert float((d1 - ref1).abs().max() / ref1.abs().max()) < WGRAD_TOL
+
+
+def _window_vs_direct(cuda, coords, feat, B, shape, cout, bias=True):
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(5)
+    cin = feat.shape[1]
+    w = torch.from_numpy((rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal((cout,)).astype(np.float32)).to(cuda) if bias else None
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    f = torch.from_numpy(feat).to(cuda)
+    old = sparse.USE_WINDOW_KERNEL, sparse.PRE_SPLIT_INPUT
+    try:
+        sparse.USE_WINDOW_KERNEL, sparse.PRE_SPLIT_INPUT = True, False
+        out_w = sparse.sparse_conv(f, w, b, rb)
+        sparse.USE_WINDOW_KERNEL = False
+        out_d = sparse.sparse_conv(f, w, b, rb)
+        sparse.PRE_SPLIT_INPUT = True                # rows split once by ud_split_bf16: same hi/lo values, same products
+        out_s = sparse.sparse_conv(f, w, b, rb)
+        assert torch.equal(out_s, out_d), "pre-split input path differs from the in-kernel split"
+        assert torch.equal(out_s._ud_bn_sums, out_d._ud_bn_sums)
+    finally:
+        sparse.USE_WINDOW_KERNEL, sparse.PRE_SPLIT_INPUT = old
+    return out_w, out_d, rb, w, b
+
+
+def test_window_kernel_equals_direct_gather_kernel(cuda, native_lib):
+    """k_spconv_umma_win (TMA-staged windows, unit-major schedule) == k_spconv_umma_dg bit for bit: the same bf16 hi/lo
+    products are accumulated per row in the same tap order; also the fused BatchNorm statistics and the C oracle."""
+    assert native_lib.ud_sparse_conv_tc_window_supported(27, 64, 64) == 1
+    rng = np.random.default_rng(12)
+    for (B, shape, n, order) in [(2, [9, 40, 44], 9000, "raster"), (2, [9, 40, 44], 9000, "shuffled"), (1, [5, 20, 20], 130, "raster"),
+                                 (3, [7, 30, 30], 4097, "raster")]:
+        lin = rng.choice(B * shape[0] * shape[1] * shape[2], size=n, replace=False)
+        if order == "raster":
+            lin.sort()                                          # the layout the windows are meant for
+        b_, r = np.divmod(lin, shape[0] * shape[1] * shape[2])
+        z, r = np.divmod(r, shape[1] * shape[2])
+        y, x = np.divmod(r, shape[2])
+        coords = np.stack([b_, z, y, x], 1).astype(np.int32)
+        feat = rng.standard_normal((n, 64)).astype(np.float32)
+        out_w, out_d, rb, w, b = _window_vs_direct(cuda, coords, feat, B, shape, 64)
+        assert torch.equal(out_w, out_d), (order, float((out_w - out_d).abs().max()))
+        assert torch.equal(out_w._ud_bn_sums, out_d._ud_bn_sums)
+        rp, rpn = O.rulebook_subm(coords, shape, 3)
+        ref = O.sparse_conv_c(feat, w.cpu().numpy(), b.cpu().numpy(), rp, rpn, n)
+        assert _rel(out_w.cpu().numpy(), ref) < TC_TOL
+
+
+def test_window_kernel_full_size_sheet(cuda, native_lib):
+    """A LiDAR-like sheet at the size of the bench's 64-channel stage (many tiles per CTA, several waves)."""
+    rng = np.random.default_rng(13)
+    B, shape = 2, [11, 256, 256]
+    yy, xx = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    pts = []
+    for b_ in range(B):
+        z = (4 + 2 * np.sin(xx / 37.0 + b_) + 2 * np.cos(yy / 29.0)).astype(np.int32)
+        for dz in (0, 1):
+            keep = rng.random(z.shape) < 0.8
+            pts.append(np.stack([np.full_like(z, b_), z + dz, yy, xx], -1)[keep])
+    coords = np.unique(np.concatenate(pts, 0), axis=0).astype(np.int32)       # sorted = raster order
+    feat = rng.standard_normal((coords.shape[0], 64)).astype(np.float32)
+    out_w, out_d, *_ = _window_vs_direct(cuda, coords, feat, B, shape, 64, bias=False)
+    assert torch.equal(out_w, out_d)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)])
+def test_pre_split_input_is_bit_identical(cuda, native_lib, cin, cout):
+    """ud_split_bf16 + the SPLIT instantiation of the kernel == the in-kernel bf16 hi/lo split (same rounding, same products)."""
+    from unidistill_b200 import sparse
+
+    rng = np.random.default_rng(cin + 3 * cout)
+    B, shape, n = 2, [7, 22, 22], 2300
+    coords, feat = _cloud(rng, B, shape, n, cin)
+    feat *= np.exp(rng.uniform(-8, 8, size=(n, 1))).astype(np.float32)
+    w = torch.from_numpy((rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)).to(cuda)
+    rb = sparse.build_subm_rulebook(torch.from_numpy(coords).to(cuda), B, shape, 3)
+    f = torch.from_numpy(feat).to(cuda)
+    old = sparse.PRE_SPLIT_INPUT
+    try:
+        sparse.PRE_SPLIT_INPUT = True
+        a = sparse.sparse_conv(f, w, None, rb)
+        sparse.PRE_SPLIT_INPUT = False
+        b = sparse.sparse_conv(f, w, None, rb)
+    finally:
+        sparse.PRE_SPLIT_INPUT = old
+    assert torch.equal(a, b)
