@@ -263,6 +263,28 @@ def _geometry(bev):
     return (S.PC_RANGE_128, 128) if bev == 128 else (S.PC_RANGE_180, 180)
 
 
+class RawLidarInput:
+    """The LiDAR input of a batch as a dataset hands it over: raw sweeps + sweep -> key-frame matrices, packed into five host
+    tensors (unidistill_b200.input_side.pack_sweeps).  `clouds(dev_tensors)` runs the input-side kernel (sweep merge + x/y
+    range filter + ragged collate, ud_collect_sweeps) and returns the per-sample clouds the model takes: no zero padding is
+    ever created, copied or voxelized."""
+
+    KEYS = ("points", "seg_offsets", "sample_first_seg", "mats", "time_lag")
+
+    def __init__(self, device, raw_batch, pc_range):
+        from unidistill_b200 import input_side as IS
+
+        self.IS, self.pc_range = IS, pc_range
+        packed = IS.pack_sweeps(raw_batch["samples"], pin=True)
+        self.host = [packed[k] for k in self.KEYS]
+        self.bytes = sum(t.numel() * t.element_size() for t in self.host)
+        self.resident = self.clouds([t.to(device) for t in self.host])
+
+    def clouds(self, dev_tensors):
+        flat, offsets = self.IS.collect_sweeps(dict(zip(self.KEYS, dev_tensors)), self.pc_range)
+        return self.IS.split_ragged(flat, offsets)
+
+
 class LidarForward:
     """configs[1]: BEVFusion-LiDAR SparseEncoder + CenterHead fwd, synthetic 40k pts x 10 sweeps, bs=4."""
 
@@ -281,24 +303,24 @@ class LidarForward:
         self.model = models.BEVFusionCenterHead(cfg).to(device).train()   # BN on batch statistics (student and
         self.model.use_channels_last(os.environ.get("UD_CHANNELS_LAST", "1") != "0")  # teacher both run so, quirk 9)
         self.model.use_cuda_graph(os.environ.get("UD_DENSE_GRAPH", "1") != "0")
-        batch = S.lidar_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=points_per_sweep,
-                              pc_range=_geometry(bev)[0])
-        self.points_host = batch["points"].pin_memory()                   # (B, Nmax, 5) zero padded (collate_fn)
+        batch = S.lidar_raw_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=points_per_sweep,
+                                  pc_range=_geometry(bev)[0])
+        self.raw = RawLidarInput(device, batch, _geometry(bev)[0])          # raw sweeps; merged + filtered on the GPU
         self.gt_host = _gt_with_labels(batch).pin_memory()
-        self.points_dev = self.points_host.to(device)
+        self.points_dev = self.raw.resident                                 # ragged list of per-sample clouds
         self.gt_dev = self.gt_host.to(device)
-        self.h2d = self.points_host.numel() * 4 + self.gt_host.numel() * 4
+        self.h2d = self.raw.bytes + self.gt_host.numel() * 4
         self.d2h = BS_PER_GPU * 10 * bev * bev * 4                          # class heat-maps (B, 10, H, W) f32
         self.samples = BS_PER_GPU
         self.bn_note = "train-mode batch statistics, torch.no_grad"
-        self.pipe = PipelinedE2E(device, [self.points_host, self.gt_host], self._forward,
+        self.pipe = PipelinedE2E(device, self.raw.host + [self.gt_host],
+                                 lambda *t: self._forward(self.raw.clouds(t[:-1]), t[-1]),
                                  lambda r: torch.cat([h["hm"] for h in r[2]], dim=1))
 
-    def _forward(self, points, gt):
+    def _forward(self, pts, gt):
         import torch
 
         with torch.no_grad():
-            pts = [points[b] for b in range(points.shape[0])]     # training_step splits the padded batch
             bev, feat, heads = self.model(pts, None, None, gt, return_feature=True)
         return bev, feat, heads
 
@@ -383,21 +405,25 @@ class DistillTrainStep:
             "eval mode, BatchNorm2d folded into its convolutions, dense trunk replayed from a CUDA graph"
             if teacher_mode == "eval" else "BatchNorm on batch statistics (pytorch-lightning train mode, quirk 9), "
             "buffers restored every step, dense trunk replayed from a CUDA graph"))
-        lid = S.lidar_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=points_per_sweep, pc_range=_geometry(bev)[0])
+        lid = S.lidar_raw_batch(BS_PER_GPU, seed=seed + rank, points_per_sweep=points_per_sweep, pc_range=_geometry(bev)[0])
         cam = S.camera_batch(BS_PER_GPU, seed=seed + rank)
+        self.raw = RawLidarInput(device, lid, _geometry(bev)[0])            # raw sweeps; merged + filtered on the GPU
         self._mat_keys = sorted(cam["mats_dict"])
-        self.host = [lid["points"].pin_memory(), cam["imgs"].pin_memory(), lid["gt_boxes"].pin_memory(),
-                     lid["gt_labels"].pin_memory()] + [cam["mats_dict"][k].pin_memory() for k in self._mat_keys]
-        self.dev = self._batch(*[t.to(device) for t in self.host])
+        rest = [cam["imgs"].pin_memory(), lid["gt_boxes"].pin_memory(), lid["gt_labels"].pin_memory()] + \
+               [cam["mats_dict"][k].pin_memory() for k in self._mat_keys]
+        self.host = self.raw.host + rest
+        self.dev = self._batch(self.raw.resident, *[t.to(device) for t in rest])
         self.h2d = sum(t.numel() * t.element_size() for t in self.host)
         self.d2h = 4
         self.samples = BS_PER_GPU
-        self.pipe = PipelinedE2E(device, self.host, lambda *t: self.step_fn(self._batch(*t)),
+        n_raw = len(self.raw.host)
+        self.pipe = PipelinedE2E(device, self.host,
+                                 lambda *t: self.step_fn(self._batch(self.raw.clouds(t[:n_raw]), *t[n_raw:])),
                                  lambda terms: terms["loss"].reshape(1))
 
-    def _batch(self, points, imgs, gt_boxes, gt_labels, *mats):
-        return {"points": [points[b] for b in range(points.shape[0])], "imgs": imgs, "gt_boxes": gt_boxes,
-                "gt_labels": gt_labels, "mats_dict": dict(zip(self._mat_keys, mats))}
+    def _batch(self, clouds, imgs, gt_boxes, gt_labels, *mats):
+        return {"points": clouds, "imgs": imgs, "gt_boxes": gt_boxes, "gt_labels": gt_labels,
+                "mats_dict": dict(zip(self._mat_keys, mats))}
 
     def step(self):
         return self.step_fn(self.dev)
@@ -467,6 +493,8 @@ def _lazy_int(cache, t, fn):
 def _algorithmic(name, a, meta, cache):
     """-> (label, bound, bytes, flops) for one recorded call; `a` = its arguments with pointers replaced by None."""
     meta = meta or {}
+    if name == "ud_collect_sweeps":
+        return "input side: sweep merge + range filter + ragged collate", "hbm", 2 * a[1] * a[2] * 4, 0
     if name == "ud_hard_voxelize":
         n, C, maxp = meta.get("n_points", 0), a[3], a[7]
         m = _lazy_int(cache, meta["counts"], lambda t: t[0].item()) if "counts" in meta else 0
@@ -593,7 +621,7 @@ def _dominant(roof_all):
         tpath = os.path.join(ROOT, "profiles", fn)                      # dram bytes/launch from an ncu --set full capture
         if os.path.exists(tpath):
             with open(tpath) as f:
-                t = json.load(f)
+                t = {k.replace(" ", ""): v for k, v in json.load(f).items()}
             if kname in t:
                 traffic = t[kname].get("dram_bytes_per_launch")
                 e["traffic_source"] = "profiles/" + fn
@@ -1114,7 +1142,7 @@ def full_size_parity(wl, device):
         if isinstance(m, torch.nn.BatchNorm1d):
             m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
             m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
-    cloud = (wl.points_dev if hasattr(wl, "points_dev") else wl.dev["points"])[0]
+    cloud = (wl.points_dev if hasattr(wl, "points_dev") else wl.dev["points"])[0].contiguous()
     with torch.no_grad():
         v = enc.voxelizer
         _, coords, num = v([cloud])

@@ -90,15 +90,31 @@ def gt_boxes_sample(rng, n_valid=30, max_objs=40, pc_range=PC_RANGE_128):
     return boxes, labels
 
 
-def lidar_sample(seed, points_per_sweep=40000, sweeps=10, pc_range=PC_RANGE_128, boxes=None):
-    """Key frame + (sweeps-1) ego-motion-shifted sweeps, range filtered in x,y: (N, 5) float32."""
+def lidar_sweeps_raw(seed, points_per_sweep=40000, sweeps=10, boxes=None):
+    """The raw material of one sample, as a dataset would hand it to the input transforms: `sweeps` clouds (N, 5)
+    [x, y, z, intensity, 0] each in its own sweep frame (sweep 0 = key frame), the 4x4 float64 sweep -> key-frame matrices
+    (ego motion v * 0.05 s per sweep: a translation) and the time lags in seconds."""
     rng = np.random.default_rng(seed)
     speed = rng.random() * 10.0
     heading = rng.random() * 2 * np.pi
     vel = np.array([np.cos(heading), np.sin(heading)]) * speed
-    clouds = []
+    clouds, mats, lags = [], [], []
     for s in range(sweeps):
         p = lidar_sweep(rng, points_per_sweep, boxes)
+        clouds.append(np.concatenate([p, np.zeros((p.shape[0], 1), np.float32)], 1))
+        m = np.eye(4)
+        m[0, 3], m[1, 3] = -vel[0] * 0.05 * s, -vel[1] * 0.05 * s
+        mats.append(m)
+        lags.append(0.05 * s)
+    return clouds, mats, lags, vel
+
+
+def lidar_sample(seed, points_per_sweep=40000, sweeps=10, pc_range=PC_RANGE_128, boxes=None):
+    """Key frame + (sweeps-1) ego-motion-shifted sweeps, range filtered in x,y: (N, 5) float32."""
+    raw, _, _, vel = lidar_sweeps_raw(seed, points_per_sweep, sweeps, boxes)
+    clouds = []
+    for s, c in enumerate(raw):
+        p = c[:, :4].copy()
         p[:, 0] -= vel[0] * 0.05 * s
         p[:, 1] -= vel[1] * 0.05 * s
         dt = np.full((p.shape[0], 1), 0.05 * s, np.float32)
@@ -107,6 +123,22 @@ def lidar_sample(seed, points_per_sweep=40000, sweeps=10, pc_range=PC_RANGE_128,
     keep = (pts[:, 0] > pc_range[0]) & (pts[:, 0] < pc_range[3]) & (pts[:, 1] > pc_range[1]) & \
            (pts[:, 1] < pc_range[4])
     return np.ascontiguousarray(pts[keep], dtype=np.float32)
+
+
+def lidar_raw_batch(batch_size, seed=0, points_per_sweep=40000, sweeps=10, pc_range=PC_RANGE_128, n_boxes=30,
+                    max_objs=40):
+    """The same samples as lidar_batch(), before the input transforms: a list of per-sample dicts for
+    unidistill_b200.input_side.pack_sweeps (key-frame points, sweep clouds, sweep -> key matrices, time lags) + GT."""
+    samples, boxes, labels = [], [], []
+    for b in range(batch_size):
+        rng = np.random.default_rng(1000 + seed * 97 + b)
+        bx, lb = gt_boxes_sample(rng, n_boxes, max_objs, pc_range)
+        boxes.append(bx)
+        labels.append(lb)
+        raw, mats, lags, _ = lidar_sweeps_raw(seed * 97 + b, points_per_sweep, sweeps, bx[:n_boxes])
+        samples.append(dict(points=raw[0], sweep_points=raw[1:], sweep_mats=mats[1:], sweep_time_lags=lags[1:]))
+    return {"samples": samples, "gt_boxes": torch.from_numpy(np.stack(boxes)),
+            "gt_labels": torch.from_numpy(np.stack(labels))}
 
 
 def lidar_batch(batch_size, seed=0, points_per_sweep=40000, sweeps=10, pc_range=PC_RANGE_128, pad=True,
