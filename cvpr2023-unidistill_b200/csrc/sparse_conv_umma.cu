@@ -185,6 +185,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {   // el
     return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// (f0, f1) -> hi = {bf16_rn(f1) : bf16_rn(f0)}, lo = {bf16_rn(f1 - hi1) : bf16_rn(f0 - hi0)} in six instructions (cvt pack, shift,
+// and, two subtractions, cvt pack: three on the ALU pipe, three on the FMA pipe); the bfloat16 intrinsics round-trip through
+// PRMT pairs and cost eight.  (sub.f32x2 for the two subtractions was measured too: the register-pair moves eat the gain.)
+__device__ __forceinline__ void split_bf16_pair(float f0, float f1, uint32_t& hi, uint32_t& lo) {
+    uint32_t h, l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f1), "f"(f0));
+    const float r0 = f0 - __uint_as_float(h << 16);
+    const float r1 = f1 - __uint_as_float(h & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+    hi = h;
+    lo = l;
+}
+
 
 // memory.  ncu showed the L1/shared-memory data pipe (not the tensor pipe) as the busiest unit of the TS kernels: per
 // 64-channel stage 32 KB of gathered rows were written to shared memory by cp.async, read back by the transform warps and
@@ -478,34 +491,34 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                         }
             }
             const int aslot = it % A_STAGES;             // == set
-            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
-            tc_fence_after();
+            uint32_t hi[2][16], lo[2][16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t hi[16], lo[16];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         const uint4 v = x[h][rr][j];
                         if constexpr (SPLIT) {           // `in` holds pre-split rows (k_split_bf16): nothing to convert
-                            hi[4 * j + 2 * rr + 0] = v.x;
-                            hi[4 * j + 2 * rr + 1] = v.y;
-                            lo[4 * j + 2 * rr + 0] = v.z;
-                            lo[4 * j + 2 * rr + 1] = v.w;
+                            hi[h][4 * j + 2 * rr + 0] = v.x;
+                            hi[h][4 * j + 2 * rr + 1] = v.y;
+                            lo[h][4 * j + 2 * rr + 0] = v.z;
+                            lo[h][4 * j + 2 * rr + 1] = v.w;
                         } else {
-                            const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y);
-                            const float f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
-                            const __nv_bfloat162 h01 = __floats2bfloat162_rn(f0, f1), h23 = __floats2bfloat162_rn(f2, f3);
-                            hi[4 * j + 2 * rr + 0] = *reinterpret_cast<const uint32_t*>(&h01);
-                            hi[4 * j + 2 * rr + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                            lo[4 * j + 2 * rr + 0] = pack_bf16x2(f0 - __low2float(h01), f1 - __high2float(h01));
-                            lo[4 * j + 2 * rr + 1] = pack_bf16x2(f2 - __low2float(h23), f3 - __high2float(h23));
+                            split_bf16_pair(__uint_as_float(v.x), __uint_as_float(v.y), hi[h][4 * j + 2 * rr + 0],
+                                            lo[h][4 * j + 2 * rr + 0]);
+                            split_bf16_pair(__uint_as_float(v.z), __uint_as_float(v.w), hi[h][4 * j + 2 * rr + 1],
+                                            lo[h][4 * j + 2 * rr + 1]);
                         }
                     }
+            // the conversions do not need the TMEM slot: only the stores wait for the MMAs that read it last
+            mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
                 const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
-                tmem_st_16x256b_x4(taddr, hi);
-                tmem_st_16x256b_x4(taddr + KS / 2, lo);
+                tmem_st_16x256b_x4(taddr, hi[h]);
+                tmem_st_16x256b_x4(taddr + KS / 2, lo[h]);
             }
             tmem_st_wait();
             tc_fence_before();

@@ -226,6 +226,15 @@ class CenterHead(nn.Module):
         self.add_module("crit", loss_utils.CenterNetFocalLoss())
         self.add_module("crit_reg", loss_utils.CenterNetRegLoss())
 
+    def _code_weights_on(self, like):
+        """code_weights as a tensor next to `like`, built once per device (a host->device copy per call would also make
+        get_loss impossible to capture into a CUDA graph)."""
+        cache = self.__dict__.setdefault("_code_w_cache", {})
+        key = (like.device, like.dtype)
+        if key not in cache:
+            cache[key] = like.new_tensor(self.code_weights)
+        return cache[key]
+
     def _sigmoid(self, x):
         return torch.clamp(x.sigmoid(), min=1e-4, max=1 - 1e-4)
 
@@ -251,7 +260,7 @@ class CenterHead(nn.Module):
             box_loss = self.crit_reg(pred, forward_ret_dict["mask"][task_id], forward_ret_dict["ind"][task_id],
                                      target)
             if code_w is None:
-                code_w = box_loss.new_tensor(self.code_weights)
+                code_w = self._code_weights_on(box_loss)
             loc_loss = (box_loss * code_w).sum()
             loss = hm_loss + self.weight * loc_loss
             key = "task_%d/" % task_id

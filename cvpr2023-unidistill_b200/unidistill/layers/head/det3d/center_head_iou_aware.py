@@ -62,7 +62,7 @@ class CenterHeadIouAware(CenterHead):
                                                           stride, voxel_size, num_pos)
             box_loss = self.crit_reg(pred[:, :n_code], mask, ind, target[:, :, :n_code], num_pos)
             if code_w is None:
-                code_w = box_loss.new_tensor(self.code_weights)
+                code_w = self._code_weights_on(box_loss)
             loc_loss = (box_loss * code_w).sum()
             loss = self.auto_loss(hm_loss, loc_loss, iou_aware_loss)
             # the IoU loss only joins once localisation is good enough (reference :131-133)

@@ -34,7 +34,8 @@ def boxes_iou_normal_paired(boxes_a, boxes_b):
 def boxes3d_lidar_to_aligned_bev_boxes(boxes3d):
     """(N,7+) [x,y,z,dx,dy,dz,heading] -> (N,4) nearest axis-aligned BEV box."""
     rot = common_utils.limit_period(boxes3d[:, 6], offset=0.5, period=np.pi).abs()
-    dims = torch.where(rot[:, None] < np.pi / 4, boxes3d[:, [3, 4]], boxes3d[:, [4, 3]])
+    dxy = boxes3d[:, 3:5]        # slices, not list indices: no host-built index tensor (CUDA-graph capturable)
+    dims = torch.where(rot[:, None] < np.pi / 4, dxy, dxy.flip(1))
     return torch.cat((boxes3d[:, 0:2] - dims / 2, boxes3d[:, 0:2] + dims / 2), dim=1)
 
 

@@ -308,6 +308,64 @@ class GraphedDenseTrunk:
         return self.static_out
 
 
+class _DenseTrainTrunk(nn.Module):
+    """BaseBEVBackbone -> CenterHead towers -> get_loss as ONE module: the unit torch.cuda.make_graphed_callables captures
+    (its parameters are the trunk's; the sub-modules stay owned by the model, this wrapper is never registered on it)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.bev_encoder = model.bev_encoder
+        self.det_head = model.det_head
+
+    def forward(self, bev, targets, num_pos, num_hm):
+        x = self.bev_encoder(bev)
+        ret = dict(self.det_head(x[0], None, targets=targets))
+        ret["num_pos_reduced"], ret["num_hm_reduced"] = num_pos, num_hm
+        loss, tb_dict = self.det_head.dense_head.get_loss(ret)
+        return loss, tb_dict, x[0], ret["multi_head_features"]
+
+
+class GraphedTrainTrunk:
+    """CUDA-graph replay of the student's dense 2-D part INCLUDING its loss and its backward.
+
+    BEV backbone + 42 towers + the per-task losses are ~1500 forward and ~2500 backward launches of a few microseconds
+    each with static shapes (the target assignment and the loss are sync-free tensor programs): issued eagerly the GPU
+    idles for more than half of that stretch.  torch.cuda.make_graphed_callables captures the forward and the backward
+    as two graphs behind one autograd node; the sparse encoder before it and the distillation losses after it stay
+    eager and exchange gradients with it through the node (BEV map in, head maps / features out).  BatchNorm running
+    statistics are snapshotted around the capture's warm-up runs so they leave no trace."""
+
+    def __init__(self, model):
+        self.model = model
+        self.key = None
+        self.fn = None
+
+    def __call__(self, bev, targets, num_pos, num_hm):
+        from torch.utils import _pytree as pytree
+
+        leaves = pytree.tree_leaves((targets, num_pos, num_hm))
+        key = (tuple(bev.shape), tuple(bev.stride()), bev.dtype, bev.device,
+               tuple((tuple(t.shape), t.dtype) for t in leaves))
+        if self.fn is None or key != self.key:
+            trunk = _DenseTrainTrunk(self.model)
+            # make_graphed_callables warms up and captures on side streams; the parameters' gradient accumulators would
+            # be created there and kept alive by the captured graph, and every later backward (on the current stream)
+            # would have to synchronise with that stream.  Created here and held, they belong to the current stream.
+            self._accumulators = [p.expand_as(p).grad_fn.next_functions[0][0] for p in trunk.parameters()
+                                  if p.requires_grad]
+            buffers = list(trunk.buffers())
+            snap = [b.detach().clone() for b in buffers]
+            sample = (bev.detach().clone(memory_format=torch.preserve_format).requires_grad_(True),
+                      pytree.tree_map(lambda t: t.detach().clone(), targets),
+                      num_pos.detach().clone(), num_hm.detach().clone())
+            self.fn = torch.cuda.make_graphed_callables(trunk, sample, allow_unused_input=True)
+            with torch.no_grad():
+                for b, v in zip(buffers, snap):
+                    b.copy_(v)
+            self.key = key
+        return self.fn(bev, targets, num_pos, num_hm)
+
+
 class BEVFusionCenterHead(BaseMultiSensorFusion):
     """forward(lidar_points, cameras_imgs, metas, gt_boxes, return_feature=False) with the reference's return
     conventions (..._centerhead_fusion_exp.py:134-171)."""
@@ -325,6 +383,13 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self.det_head = DetHead(model_cfg.det_head)
         self._channels_last = False
         self._dense_graph = None
+        self._train_graph = None
+
+    def use_cuda_graph_training(self, enable=True):
+        """Training steps that hand in pre-assigned `targets` and `normalisers` run the dense 2-D part, its loss and its
+        backward from CUDA graphs (see GraphedTrainTrunk)."""
+        self._train_graph = GraphedTrainTrunk(self) if enable else None
+        return self
 
     def use_cuda_graph(self, enable=True):
         """Gradient-free forwards replay the dense 2-D part from a CUDA graph (see GraphedDenseTrunk)."""
@@ -364,6 +429,14 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         model_output = self.extract_bev(lidar_points, cameras_imgs, metas, geometry=geometry)
         if self._channels_last:
             model_output = model_output.contiguous(memory_format=torch.channels_last)
+        if (self._train_graph is not None and self.training and torch.is_grad_enabled() and targets is not None
+                and normalisers is not None and not return_feature and model_output.is_cuda):
+            pre = {}
+            normalisers(pre)
+            loss_rpn, tb_dict, feats, heads = self._train_graph(model_output, targets, pre["num_pos_reduced"],
+                                                                pre["num_hm_reduced"])
+            tb_dict = dict(tb_dict, loss_rpn=loss_rpn.detach())
+            return {"loss": loss_rpn}, tb_dict, model_output, feats, heads, {}
         if self._dense_graph is not None and not torch.is_grad_enabled() and model_output.is_cuda:
             feats, pyramid, ret = self._dense_graph(model_output, None if targets is not None else gt_boxes)
             x = (feats, pyramid)

@@ -11,7 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG_ROOT, "libunidistill_b200.so")
+# UD_B200_LIB: an alternative build of the same library (kernel experiments: tools/build_dg_variants.sh)
+LIB_PATH = os.environ.get("UD_B200_LIB") or os.path.join(_PKG_ROOT, "libunidistill_b200.so")
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int

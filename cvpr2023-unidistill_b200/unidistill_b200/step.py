@@ -220,7 +220,8 @@ class DistillStep:
     def __init__(self, student, teacher, geometry, lr=None, weight_decay=1e-7, clamp_min=None, optimizer=True,
                  fold_teacher_bn=True, teacher_cuda_graph=True, weights=None, preset="camera_exp_distill_lidar",
                  grad_clip=0.1, lr_milestones=(10, 15), lr_gamma=0.1, teacher_mode="eval", overlap_allreduce=True,
-                 bucket_bytes=16 << 20, fuse_teacher_epilogues=True):
+                 bucket_bytes=16 << 20, fuse_teacher_epilogues=True,
+                 student_cuda_graph=True):
         cfg = PRESETS[preset]
         self.weights = tuple(float(w) for w in (weights if weights is not None else cfg["weights"]))
         self.clamp_min = float(clamp_min if clamp_min is not None else cfg["clamp_min"])
@@ -256,6 +257,8 @@ class DistillStep:
             teacher.use_cuda_graph(True)                       # dense trunk replayed from a CUDA graph
         self._teacher_buffers = [(b, b.detach().clone()) for b in teacher.buffers()]
         student.train()
+        if student_cuda_graph and next(student.parameters()).is_cuda:
+            student.use_cuda_graph_training(True)              # dense trunk + loss, forward AND backward, from CUDA graphs
         self.bucket = FlatGradBucket(student.parameters(), bucket_bytes=bucket_bytes, overlap=overlap_allreduce)
         self.opt = self.sched = None
         if optimizer:

@@ -125,3 +125,48 @@ def test_folded_graphed_teacher_equals_plain_teacher(cuda, native_lib):
                 assert torch.allclose(hg[k], he[k], rtol=2e-3, atol=2e-4), k
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_graphed_student_trunk_matches_eager(cuda, native_lib):
+    """The student's dense trunk + loss + backward replayed from CUDA graphs (GraphedTrainTrunk) against the same
+    student run eagerly: loss terms, every gradient and the BatchNorm running statistics after two steps' worth of
+    forward/backward (the first call captures, the second replays)."""
+    import copy
+
+    from unidistill_b200 import models
+    from unidistill_b200.step import DistillStep
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+        teacher = models.BEVFusionCenterHead(cfg).to(cuda)
+        student_g = models.BEVFusionCenterHead(cfg).to(cuda)
+        student_e = copy.deepcopy(student_g)
+        step_g = DistillStep(student_g, teacher, cfg["geometry"], optimizer=False, preset="lidar_exp_distill_fusion")
+        step_e = DistillStep(student_e, copy.deepcopy(teacher), cfg["geometry"], optimizer=False,
+                             preset="lidar_exp_distill_fusion", student_cuda_graph=False)
+        assert student_g._train_graph is not None and student_e._train_graph is None
+        batch = _batch(cuda, bs=2)
+        for it in range(2):
+            out = []
+            for st in (step_g, step_e):
+                st.bucket.zero()
+                terms = st.losses(batch)
+                terms["loss"].backward()
+                st.bucket.finish()
+                out.append(({k: float(v) for k, v in terms.items()}, st.bucket.flat.clone()))
+            (tg, gg), (te, ge) = out
+            for k in te:
+                assert abs(tg[k] - te[k]) <= 1e-4 * abs(te[k]) + 1e-6, (it, k, tg[k], te[k])
+            assert float(ge.abs().max()) > 0
+            cos = float((gg * ge).sum() / (gg.norm() * ge.norm()))
+            assert cos > 0.9999, (it, cos)
+            assert float((gg - ge).abs().max()) <= 2e-3 * float(ge.abs().max()), it
+        assert student_g._train_graph.fn is not None
+        bg = dict(student_g.named_buffers())
+        for name, b in student_e.named_buffers():
+            assert torch.allclose(bg[name].float(), b.float(), rtol=1e-4, atol=1e-5), name
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
