@@ -9,12 +9,21 @@ Differences from the reference are purely operational (same numbers):
   * the per-call scalar `reduce_mean`s can be replaced by one fused all-reduce: pass
     forward_ret_dict["num_pos_reduced"] = tensor(n_tasks) (see unidistill_b200.step).
 """
+import os
+
 import torch
 
 from unidistill.layers.head.det3d.center_head import CenterHead
-from unidistill.layers.losses.det3d import AutomaticWeightedLoss, _transpose_and_gather_feat
+from unidistill.layers.losses.det3d import (AutomaticWeightedLoss, CenterNetFocalLoss, CenterNetRegLoss, FocalLoss,
+                                            _transpose_and_gather_feat)
 from unidistill.utils.det3d_utils import box_utils
 from unidistill.utils.torch_dist import reduce_mean
+
+
+# The per-task loop of get_loss issues ~250 small kernels per task and as many again in its backward; with pre-reduced
+# normalisers (unidistill_b200.step) the six tasks have identical shapes except for the class count of the heat-map, so
+# the same arithmetic runs ONCE on tensors with a task dimension (`_get_loss_batched`).  UD_BATCH_LOSS=0 disables it.
+BATCH_LOSS = os.environ.get("UD_BATCH_LOSS", "1") != "0"
 
 
 class CenterHeadIouAware(CenterHead):
@@ -30,7 +39,109 @@ class CenterHeadIouAware(CenterHead):
         self.iou_weight = iou_weight
         self.out_size_factor = out_size_factor
 
+    def _box_heads(self):
+        return ["reg", "height", "dim", "rot"] + (["vel"] if self.dataset == "nuscenes" else []) + ["iou"]
+
+    def _can_batch_loss(self, ret):
+        if not (BATCH_LOSS and "num_pos_reduced" in ret and "num_hm_reduced" in ret):
+            return False
+        if type(self.crit) not in (FocalLoss, CenterNetFocalLoss) or type(self.crit_reg) is not CenterNetRegLoss \
+                or type(self.crit_iou_aware) is not CenterNetRegLoss:
+            return False
+        preds = ret["multi_head_features"]
+        n_code = 10 if self.dataset == "nuscenes" else 8
+        try:
+            widths = [[p[h].shape[1] for h in self._box_heads()] for p in preds]
+        except KeyError:
+            return False
+        if any(w != widths[0] for w in widths) or sum(widths[0]) != n_code + 1:
+            return False
+        k = ret["ind"][0].shape
+        return all(ret["ind"][t].shape == k and ret["box_encoding"][t].shape[-1] >= n_code for t in range(len(preds)))
+
+    def _task_onehot(self, like, classes):
+        """(sum classes, T) 0/1 matrix adding heat-map channels up per task; built once per device."""
+        cache = self.__dict__.setdefault("_onehot_cache", {})
+        key = (like.device, like.dtype, tuple(classes))
+        if key not in cache:
+            m = torch.zeros(sum(classes), len(classes))
+            c0 = 0
+            for t, c in enumerate(classes):
+                m[c0: c0 + c, t] = 1
+                c0 += c
+            cache[key] = m.to(device=like.device, dtype=like.dtype)
+        return cache[key]
+
+    def _get_loss_batched(self, ret):
+        """get_loss with a task dimension: same terms, same tb_dict, same side effects on the dict (quirk 6:
+        pred_dict["hm"] becomes the clamped sigmoid; "pred_box_encoding" is filled) as the per-task loop below."""
+        preds = ret["multi_head_features"]
+        T = len(preds)
+        n_code = 10 if self.dataset == "nuscenes" else 8
+        stride, voxel_size = self.out_size_factor, self.proposal_layer.voxel_size
+        num_pos, num_hm = ret["num_pos_reduced"], ret["num_hm_reduced"]                # (T,), (T,)
+        # ---- heat-maps: all tasks' classes side by side
+        classes = [p["hm"].shape[1] for p in preds]
+        hm_all = self._sigmoid(torch.cat([p["hm"] for p in preds], dim=1))             # (B, sum classes, H, W)
+        heat_all = torch.cat([ret["heatmap"][t] for t in range(T)], dim=1)
+        c0 = 0
+        for p, c in zip(preds, classes):
+            p["hm"] = hm_all[:, c0: c0 + c]                                            # quirk 6
+            c0 += c
+        per_task = self.crit.channel_sums(hm_all, heat_all) @ self._task_onehot(hm_all, classes)
+        hm_loss = -per_task / torch.where(num_hm == 0, torch.ones_like(num_hm), num_hm)
+        # ---- box codes at the assigned cells: (B, T, K, n_code + 1)
+        heads = self._box_heads()
+        B, _, H, W = preds[0][heads[0]].shape
+        codes = torch.cat([p[h] for p in preds for h in heads], dim=1).view(B, T, n_code + 1, H * W)
+        ret["pred_box_encoding"] = {t: codes[:, t].view(B, n_code + 1, H, W) for t in range(T)}
+        ind = torch.stack([ret["ind"][t] for t in range(T)], dim=1)                    # (B, T, K)
+        mask = torch.stack([ret["mask"][t] for t in range(T)], dim=1)                  # (B, T, K)
+        target = torch.stack([ret["box_encoding"][t][:, :, :n_code] for t in range(T)], dim=1)
+        K = ind.shape[-1]
+        pred = codes.gather(3, ind.unsqueeze(2).expand(B, T, n_code + 1, K)).permute(0, 1, 3, 2).contiguous()
+        maskf = mask.float()
+
+        def decode(t):
+            x = (t[..., 0:1] * stride * voxel_size[0]).reshape(-1, 1)
+            y = (t[..., 1:2] * stride * voxel_size[1]).reshape(-1, 1)
+            whl = torch.clamp(torch.exp(t[..., 3:6].clamp(max=10.0)).reshape(-1, 3), min=0.001, max=30)   # see _get_iou_loss
+            rot = torch.atan2(t[..., 6], t[..., 7]).reshape(-1, 1)
+            z = t[..., 2].reshape(-1, 1)
+            return x, y, z, whl, rot
+
+        tx, ty, tz, t_whl, t_rot = decode(target)
+        px, py, pz, p_whl, p_rot = decode(pred)
+        iou = self._get_3d_iou(tx, ty, t_whl, tz, px, py, p_whl, pz)
+        iou_pos = torch.clamp(iou[:, 0], 0, 1).view(B, T, K)
+        iou_loss = ((1 - iou_pos) * maskf).sum(dim=(0, 2)) / torch.clamp(num_pos, min=1)
+        target_box = torch.cat([tx, ty, tz, t_whl, t_rot], dim=-1)
+        pred_box = torch.cat([px, py, pz, p_whl, p_rot], dim=-1).detach()
+        bev_iou = box_utils.boxes3d_nearest_bev_iou_paired(target_box, pred_box)
+        tar_iou_pred = 2 * (bev_iou.view(B, T, K, 1) - 0.5)
+
+        def reg_loss(regr, gt_regr):          # CenterNetRegLoss._reg_loss with a task dimension -> (T, C)
+            m = maskf.unsqueeze(3).expand_as(gt_regr) * (~torch.isnan(gt_regr)).float()
+            return torch.abs(regr * m - gt_regr * m).sum(dim=(0, 2)) / (num_pos + 1e-4).unsqueeze(1)
+
+        iou_aware_loss = reg_loss(pred[..., n_code:], tar_iou_pred).sum(dim=1)
+        box_loss = reg_loss(pred[..., :n_code], target)                                # (T, n_code)
+        loc_loss = (box_loss * self._code_weights_on(box_loss)).sum(dim=1)
+        loss = self.auto_loss(hm_loss, loc_loss, iou_aware_loss)
+        loss = torch.where(loc_loss.detach() < 1, loss + iou_loss * self.iou_weight, loss)
+        n_positive = maskf.sum(dim=(0, 2))
+        tb_dict = {}
+        for t in range(T):
+            key = "task_%d/" % t
+            tb_dict.update({
+                key + "loss": loss[t].detach(), key + "hm_loss": hm_loss[t].detach(), key + "loc_loss": loc_loss[t].detach(),
+                key + "box_loss": box_loss[t].detach(), key + "iou_aware_loss": iou_aware_loss[t].detach(),
+                key + "iou_loss": iou_loss[t].detach(), key + "num_positive": n_positive[t]})
+        return loss.sum(), tb_dict
+
     def get_loss(self, forward_ret_dict):
+        if self._can_batch_loss(forward_ret_dict):
+            return self._get_loss_batched(forward_ret_dict)
         tb_dict = {}
         losses = []
         forward_ret_dict["pred_box_encoding"] = {}

@@ -45,6 +45,15 @@ class FocalLoss(nn.Module):
         safe = torch.where(num_pos == 0, torch.ones_like(num_pos), num_pos)
         return -(pos_loss + neg_loss) / safe
 
+    def channel_sums(self, pred, gt):
+        """(B,C,H,W) -> (C,): pos_loss + neg_loss of `_neg_loss` summed per channel (the batched head loss adds the
+        channels of each task and divides by its own normaliser)."""
+        pos = gt.eq(1).to(pred.dtype)
+        neg = gt.eq(0).to(pred.dtype)
+        both = torch.log(pred) * torch.pow(1 - pred, self.gamma) * pos * self.alpha \
+            + torch.log(1 - pred + 1e-4) * torch.pow(pred, self.gamma) * neg * (1 - self.alpha)
+        return both.sum(dim=(0, 2, 3))
+
     def forward(self, out, target, num_pos=None):
         return self._neg_loss(out, target, num_pos)
 
@@ -64,6 +73,14 @@ class CenterNetFocalLoss(nn.Module):
         # sync-free form of the reference's `if num_pos == 0` (no positives => pos_loss == 0)
         safe = torch.where(num_pos == 0, torch.ones_like(num_pos), num_pos)
         return -(pos_loss + neg_loss) / safe
+
+    def channel_sums(self, pred, gt):
+        """(B,C,H,W) -> (C,): pos_loss + neg_loss of `_neg_loss` summed per channel."""
+        pos = gt.eq(1).to(pred.dtype)
+        neg = gt.lt(1).to(pred.dtype)
+        both = torch.log(pred) * torch.pow(1 - pred, 2) * pos \
+            + torch.log(1 - pred) * torch.pow(pred, 2) * torch.pow(1 - gt, 4) * neg
+        return both.sum(dim=(0, 2, 3))
 
     def forward(self, out, target, num_pos=None):
         return self._neg_loss(out, target, num_pos)

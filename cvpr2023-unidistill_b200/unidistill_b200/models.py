@@ -340,23 +340,27 @@ class GraphedTrainTrunk:
         self.key = None
         self.fn = None
 
-    def __call__(self, bev, targets, num_pos, num_hm):
+    def __call__(self, bev, targets, num_pos, num_hm, persistent_targets=False):
+        """`persistent_targets`: the target tensors are static buffers that keep their addresses from step to step
+        (unidistill_b200.step.GraphedTargets): they become the graph's own input placeholders, nothing is copied."""
         from torch.utils import _pytree as pytree
 
         leaves = pytree.tree_leaves((targets, num_pos, num_hm))
         key = (tuple(bev.shape), tuple(bev.stride()), bev.dtype, bev.device,
-               tuple((tuple(t.shape), t.dtype) for t in leaves))
+               tuple((tuple(t.shape), t.dtype) for t in leaves),
+               tuple(t.data_ptr() for t in pytree.tree_leaves(targets)) if persistent_targets else None)
         if self.fn is None or key != self.key:
             trunk = _DenseTrainTrunk(self.model)
-            # make_graphed_callables warms up and captures on side streams; the parameters' gradient accumulators would
-            # be created there and kept alive by the captured graph, and every later backward (on the current stream)
-            # would have to synchronise with that stream.  Created here and held, they belong to the current stream.
-            self._accumulators = [p.expand_as(p).grad_fn.next_functions[0][0] for p in trunk.parameters()
-                                  if p.requires_grad]
+            # make_graphed_callables warms up and captures on side streams and the captured autograd graph keeps the
+            # parameters' gradient accumulators created there alive: later backwards accumulate the trunk's gradients on
+            # that stream (the engine orders it after the producer and joins it at the end of the backward).  Correct,
+            # but torch warns about it once; accumulators created on the legacy stream instead make the capture fail.
+            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
             buffers = list(trunk.buffers())
             snap = [b.detach().clone() for b in buffers]
             sample = (bev.detach().clone(memory_format=torch.preserve_format).requires_grad_(True),
-                      pytree.tree_map(lambda t: t.detach().clone(), targets),
+                      targets if persistent_targets else pytree.tree_map(lambda t: t.detach().clone(), targets),
                       num_pos.detach().clone(), num_hm.detach().clone())
             self.fn = torch.cuda.make_graphed_callables(trunk, sample, allow_unused_input=True)
             with torch.no_grad():
@@ -434,7 +438,8 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
             pre = {}
             normalisers(pre)
             loss_rpn, tb_dict, feats, heads = self._train_graph(model_output, targets, pre["num_pos_reduced"],
-                                                                pre["num_hm_reduced"])
+                                                                pre["num_hm_reduced"],
+                                                                persistent_targets=kwargs.get("persistent_targets", False))
             tb_dict = dict(tb_dict, loss_rpn=loss_rpn.detach())
             return {"loss": loss_rpn}, tb_dict, model_output, feats, heads, {}
         if self._dense_graph is not None and not torch.is_grad_enabled() and model_output.is_cuda:

@@ -177,17 +177,70 @@ def gt_with_labels(gt_boxes, gt_labels):
     return torch.cat([gt_boxes, (gt_labels.to(gt_boxes.dtype) + 1).unsqueeze(2)], dim=2)
 
 
+def normaliser_vector(targets, valid, mask_sum):
+    """[num_pos (T), num_hm (T), #valid boxes, Gaussian-mask sum] of this rank as one (2T + 2,) vector."""
+    tasks = sorted(targets["mask"].keys()) if isinstance(targets["mask"], dict) else list(range(len(targets["mask"])))
+    parts = [targets["mask"][t].float().sum() for t in tasks]
+    parts += [targets["heatmap"][t].eq(1).float().sum() for t in tasks]
+    parts += [valid.float().sum(), mask_sum]
+    return torch.stack([p.reshape(()) for p in parts]), len(tasks)
+
+
+class GraphedTargets:
+    """Everything of a step that depends on the ground truth only -- label column, valid-box prefix, BEV corners, the
+    head's target assignment, the Gaussian response mask and this rank's normaliser vector -- is ~150 launches of a few
+    microseconds with static shapes: captured once per ground-truth shape and replayed.  Outputs are static buffers,
+    valid until the next call."""
+
+    def __init__(self, step):
+        self.step = step
+        self.key = None
+        self.graph = None
+
+    def _run(self, gt_boxes, gt_labels):
+        st = self.step
+        gt = gt_with_labels(gt_boxes, gt_labels)
+        valid = D.valid_box_prefix(gt_boxes)
+        corners = D.box_corners_bev(gt, st.pc_range, st.voxel_size, st.osf)
+        head = st.student.det_head.dense_head
+        targets = head.assign_targets(gt)
+        for _, enc in targets["box_encoding"].items():
+            enc.masked_fill_(torch.isinf(enc), 0)
+        h, w = targets["heatmap"][0].shape[-2:]
+        mask = D.response_mask(gt, (h, w), st.pc_range, st.voxel_size, st.osf)
+        vec, n_tasks = normaliser_vector(targets, valid, mask.sum())
+        return gt, valid, corners, targets, vec, n_tasks
+
+    def __call__(self, gt_boxes, gt_labels):
+        key = (tuple(gt_boxes.shape), gt_boxes.dtype, tuple(gt_labels.shape), gt_labels.dtype, gt_boxes.device)
+        if self.graph is None or key != self.key:
+            self.static_in = (gt_boxes.detach().clone(), gt_labels.detach().clone())
+            side = torch.cuda.Stream(device=gt_boxes.device)
+            side.wait_stream(torch.cuda.current_stream(gt_boxes.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(3):
+                    self._run(*self.static_in)
+            torch.cuda.current_stream(gt_boxes.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.static_out = self._run(*self.static_in)
+            self.key = key
+        self.static_in[0].copy_(gt_boxes)
+        self.static_in[1].copy_(gt_labels)
+        self.graph.replay()
+        return self.static_out
+
+
 class AsyncNormalisers:
     """mean over ranks of [num_pos (T), num_hm (T), #valid boxes, Gaussian-mask sum] in ONE all-reduce that is in flight
     while the student forward runs; `get()` (first consumer: get_loss, after the whole forward) waits for it."""
 
-    def __init__(self, targets, valid, mask_sum):
-        tasks = sorted(targets["mask"].keys()) if isinstance(targets["mask"], dict) else list(range(len(targets["mask"])))
-        parts = [targets["mask"][t].float().sum() for t in tasks]
-        parts += [targets["heatmap"][t].eq(1).float().sum() for t in tasks]
-        parts += [valid.float().sum(), mask_sum]
-        self.T = len(tasks)
-        self.vec = torch.stack([p.reshape(()) for p in parts])
+    def __init__(self, targets, valid, mask_sum, vec=None, n_tasks=None):
+        """`vec`, `n_tasks`: a ready normaliser_vector (GraphedTargets builds it inside its graph)."""
+        if vec is None:
+            vec, n_tasks = normaliser_vector(targets, valid, mask_sum)
+        self.T = n_tasks
+        self.vec = vec
         self.world = torch_dist.get_world_size()
         self.work = dist.all_reduce(self.vec, op=dist.ReduceOp.SUM, async_op=True) if self.world > 1 else None
 
@@ -257,8 +310,10 @@ class DistillStep:
             teacher.use_cuda_graph(True)                       # dense trunk replayed from a CUDA graph
         self._teacher_buffers = [(b, b.detach().clone()) for b in teacher.buffers()]
         student.train()
+        self._graphed_targets = None
         if student_cuda_graph and next(student.parameters()).is_cuda:
             student.use_cuda_graph_training(True)              # dense trunk + loss, forward AND backward, from CUDA graphs
+            self._graphed_targets = GraphedTargets(self)       # and the ground-truth-only preparation
         self.bucket = FlatGradBucket(student.parameters(), bucket_bytes=bucket_bytes, overlap=overlap_allreduce)
         self.opt = self.sched = None
         if optimizer:
@@ -281,19 +336,25 @@ class DistillStep:
 
     def losses(self, batch):
         points, imgs, metas = batch.get("points"), batch.get("imgs"), batch.get("mats_dict")
-        gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
-        valid = D.valid_box_prefix(batch["gt_boxes"])                               # (:447-455)
-        corners = D.box_corners_bev(gt, self.pc_range, self.voxel_size, self.osf)   # (:470-483)
         # ---- everything that depends on the ground truth only: ONE target assignment (the reference runs the same
         # assignment twice, in the student's and the teacher's head) and the normalisers' all-reduce, in flight from here
-        head = self.student.det_head.dense_head
-        with torch.no_grad():
-            targets = head.assign_targets(gt)
-            for _, enc in targets["box_encoding"].items():
-                enc.masked_fill_(torch.isinf(enc), 0)                               # log(0) of padded boxes (quirk 10)
-            h, w = targets["heatmap"][0].shape[-2:]
-            mask = D.response_mask(gt, (h, w), self.pc_range, self.voxel_size, self.osf)
-            pending = AsyncNormalisers(targets, valid, mask.sum())
+        if self._graphed_targets is not None and batch["gt_boxes"].is_cuda:
+            gt, valid, corners, targets, vec, n_tasks = self._graphed_targets(batch["gt_boxes"], batch["gt_labels"])
+            pending = AsyncNormalisers(None, None, None, vec=vec, n_tasks=n_tasks)
+            persistent = True
+        else:
+            gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
+            valid = D.valid_box_prefix(batch["gt_boxes"])                               # (:447-455)
+            corners = D.box_corners_bev(gt, self.pc_range, self.voxel_size, self.osf)   # (:470-483)
+            head = self.student.det_head.dense_head
+            with torch.no_grad():
+                targets = head.assign_targets(gt)
+                for _, enc in targets["box_encoding"].items():
+                    enc.masked_fill_(torch.isinf(enc), 0)                           # log(0) of padded boxes (quirk 10)
+                h, w = targets["heatmap"][0].shape[-2:]
+                mask = D.response_mask(gt, (h, w), self.pc_range, self.voxel_size, self.osf)
+                pending = AsyncNormalisers(targets, valid, mask.sum())
+            persistent = False
         norm = {}
 
         def normalisers(ret):
@@ -303,7 +364,8 @@ class DistillStep:
 
         geometry = {}       # voxels + rulebooks of the step's clouds, shared by the two LiDAR encoders (if there are two)
         ret_dict, tb, feat_s, bev_s, resp_s, _ = self.student(points, imgs, metas, gt, normalisers=normalisers,
-                                                              targets=targets, geometry=geometry)
+                                                              targets=targets, geometry=geometry,
+                                                              persistent_targets=persistent)
         with torch.no_grad():
             feat_t, bev_t, resp_t = self.teacher(points, imgs, metas, gt, return_feature=True, targets=targets,
                                                  geometry=geometry)

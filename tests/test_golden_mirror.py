@@ -118,6 +118,43 @@ def test_head_loss_with_prereduced_normalisers_is_identical():
     assert abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
 
 
+def test_batched_head_loss_matches_reference_and_the_per_task_loop(monkeypatch):
+    """With pre-reduced normalisers get_loss runs once over a task dimension (_get_loss_batched): same loss as the
+    reference fixture, same tb_dict, same side effects and the same gradients as the per-task loop."""
+    from unidistill.layers.head.det3d import center_head_iou_aware as M
+
+    g = _load("head_loss.npz")
+    out = []
+    for batched in (True, False):
+        monkeypatch.setattr(M, "BATCH_LOSS", batched)
+        head = _head(g).train()
+        x = torch.from_numpy(g["x"]).clone().requires_grad_(True)
+        ret = head(x, torch.from_numpy(g["gt_boxes"]))
+        for _, enc in ret["box_encoding"].items():
+            enc[torch.isinf(enc)] = 0
+        ret["num_pos_reduced"] = torch.stack([ret["mask"][t].float().sum() for t in range(6)])
+        ret["num_hm_reduced"] = torch.stack([ret["heatmap"][t].eq(1).float().sum() for t in range(6)])
+        assert head._can_batch_loss(ret) == batched
+        loss, tb = head.get_loss(ret)
+        loss.backward()
+        out.append((loss, tb, ret, x.grad, {n: p.grad for n, p in head.named_parameters()}))
+    (lb, tbb, rb, gxb, gpb), (ll, tbl, rl, gxl, gpl) = out
+    assert abs(float(lb) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    assert abs(float(lb) - float(ll)) <= 1e-5 * abs(float(ll))
+    assert set(tbb) == set(tbl)
+    for k in tbl:
+        assert tbb[k].shape == tbl[k].shape and torch.allclose(tbb[k], tbl[k], rtol=1e-5, atol=1e-6), k
+    for t in range(6):
+        assert np.allclose(rb["multi_head_features"][t]["hm"].detach().numpy(), g["hm_sig_%d" % t], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(rb["pred_box_encoding"][t], rl["pred_box_encoding"][t])
+    assert torch.allclose(gxb, gxl, rtol=1e-4, atol=1e-7)
+    for n in gpl:
+        if gpl[n] is None:
+            assert gpb[n] is None, n
+        else:
+            assert torch.allclose(gpb[n], gpl[n], rtol=1e-4, atol=1e-6), n
+
+
 def test_bev_backbone_and_mean_vfe_match_reference():
     from unidistill.layers.blocks_2d.det3d import BaseBEVBackbone
     from unidistill.layers.blocks_3d.det3d import MeanVFE
