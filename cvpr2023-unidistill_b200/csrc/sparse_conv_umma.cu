@@ -35,6 +35,7 @@ constexpr int TS_GROUP = 128;          // threads of one gather set
 constexpr int TS_ACC_COLS = 256;       // TMEM columns holding accumulators; the other 256 hold the A-operand ring
 
 __host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
+
 // taps that share one 64-channel stage (narrow layers)
 __host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin : 1; }
 // bytes of one weight slice: [COUT x 64] bf16 W_hi + [COUT x 64] bf16 W_lo
@@ -207,14 +208,36 @@ __device__ __forceinline__ void split_bf16_pair(float f0, float f1, uint32_t& hi
 // splits them into bf16 hi/lo in registers and stores them to the stage's TMEM columns.
 //   warps 0-15 : four gather sets (set = stage % 4 = TMEM A slot; warp & 3 = TMEM lane quadrant); epilogue afterwards
 //   warp 16    : MMA issuer          warp 17 : weight slices (bulk copies)          warp 18 : row-index segments (bulk copies)
+// -DUD_DG_PROBE: cycle accounting of the roles of k_spconv_umma_dg (tools/gpu_dg_probe.py builds such a library; the shipped
+// one has none of it).  Slots: 0 stages seen by gather warp 0 of a set, 1 index wait, 2 index read + load issue, 3 data wait +
+// conversion, 4 TMEM slot wait, 5 TMEM stores + arrive | 8 MMA stages, 9 wait weights, 10 wait A, 11 issue + commit |
+// 12 CTAs, 13 CTA cycles from start to the end of the main loop (MMA warp), 14 epilogue cycles (warp 0) | 6 the MMA warp's
+// tcgen05.fence::after_thread_sync after its A wait
+#ifdef UD_DG_PROBE
+__device__ unsigned long long ud_dg_probe_acc[16];
+#define DG_PROBE_DECL(n) long long pr_[n] = {}; long long pt_ = clock64();
+#define DG_PROBE_LAP(i) { const long long now_ = clock64(); pr_[i] += now_ - pt_; pt_ = now_; }
+#define DG_PROBE_FLUSH(base, n, cond) if (cond) { for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&ud_dg_probe_acc[(base) + i_], (unsigned long long)pr_[i_]); }
+#else
+#define DG_PROBE_DECL(n)
+#define DG_PROBE_LAP(i)
+#define DG_PROBE_FLUSH(base, n, cond)
+#endif
+
 constexpr int DG_THREADS = 608;
 constexpr int DG_SETS = 4;
 constexpr int DG_IDX_STAGES = 16;
 constexpr int DG_B_STAGES = 4;
 // statistics buffer: [0, 4096) final sums (2 * COUT doubles), then the workspace of det_reduce.cuh
 constexpr int DG_STAT_FINAL_BYTES = 4096;
+// staging buffer of the epilogue (dg_epilogue): one [32 rows x 36 floats] tile per epilogue warp
+constexpr int DG_EP_PITCH = 36;                          // floats per staged row: 16-byte aligned, conflict-free LDS/STS.128
+constexpr int DG_EP_STAGE_FLOATS = 32 * DG_EP_PITCH;
+constexpr size_t DG_EP_STAGE_BYTES = (size_t)16 * DG_EP_STAGE_FLOATS * 4;
 __host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout) {
-    return (size_t)DG_B_STAGES * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 + 1024;
+    // the epilogue's staging tiles alias the weight ring when that is large enough (it is idle by then), else follow the index ring
+    return (size_t)DG_B_STAGES * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 +
+           ((size_t)DG_B_STAGES * dg_b_bytes(cout) >= DG_EP_STAGE_BYTES ? 0 : DG_EP_STAGE_BYTES) + 1024;
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const float* p) {
@@ -239,14 +262,19 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
 }
 
 // Epilogue shared by the tensor-core forward kernels (called by ALL threads; warps 0-15 do the work: warp w -> TMEM lane
-// quadrant w & 3, tiles (w >> 2), (w >> 2) + 4, ...): tcgen05.ld -> + bias -> st.global.v4, plus the per-channel sum / sum of
-// squares of the output for the BatchNorm that follows, reduced in a fixed order (det_reduce.cuh).
+// quadrant w & 3, tiles (w >> 2), (w >> 2) + 4, ...): tcgen05.ld -> shared-memory transpose -> + bias -> st.global.v4, plus the
+// per-channel sum / sum of squares of the output for the BatchNorm that follows, reduced in a fixed order (det_reduce.cuh).
+// The accumulator chunk a warp has read (`stage`: DG_EP_STAGE_FLOATS floats per warp) -- thread = row,
+// 32 consecutive columns -- is transposed through shared memory so that a store instruction writes 4 rows x 128 contiguous
+// bytes instead of 32 rows x 16 bytes (the role-cycle probe showed the epilogue at ~20 % of a CTA's life, bound by the 32
+// partial lines per store), and the per-column sums need 2 shuffle rounds instead of 5.
+
 template <int COUT, int NTHREADS>
 __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, int tiles, int rows_cta, int row0,
                                             const unsigned int* tile_mask_s, uint32_t tmem_acc,
                                             const float* __restrict__ bias, float* __restrict__ out,
                                             unsigned char* __restrict__ stats, float* wpart_s, int stat_group,
-                                            int* stat_last_s) {
+                                            int* stat_last_s, float* stage) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
@@ -256,13 +284,17 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
             tc_fence_after();
         }
         const int q = warp & 3;
-        constexpr int CW = COUT >= 32 ? 32 : 16;
+        constexpr int CW = COUT >= 32 ? 32 : 16;         // columns per chunk
+        constexpr int LPR = CW / 4;                      // lanes per row when reading back (one float4 each)
+        constexpr int RPI = 32 / LPR;                    // rows per store instruction
+        float* const st = stage + warp * DG_EP_STAGE_FLOATS;
+        const int rsub = lane / LPR;
+        const int c4 = (lane % LPR) * 4;
 #pragma unroll 1
         for (int t = warp >> 2; t < tiles; t += DG_SETS) {
             if (t * TILE_M >= rows_cta) break;
             const bool has_acc = tile_mask_s[t] != 0u;
-            const int r_local = t * TILE_M + q * 32 + lane;
-            const int row = row0 + r_local;
+            const int r_base = t * TILE_M + q * 32;       // first row (CTA-local) of this warp's 32
 #pragma unroll 1
             for (int c0 = 0; c0 < COUT; c0 += CW) {
                 uint32_t v[32];
@@ -274,56 +306,38 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
 #pragma unroll
                     for (int i = 0; i < CW; ++i) v[i] = 0u;
                 }
-                const bool row_ok = r_local < rows_cta;
-                float* dst = out + (size_t)row * COUT + c0;
+                __syncwarp();                             // the previous chunk has been read back
 #pragma unroll
-                for (int i = 0; i < CW; i += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[i + 0]);
-                    o.y = __uint_as_float(v[i + 1]);
-                    o.z = __uint_as_float(v[i + 2]);
-                    o.w = __uint_as_float(v[i + 3]);
-                    if (bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (row_ok) *reinterpret_cast<float4*>(dst + i) = o;
-                    if (stats != nullptr) {
-                        v[i + 0] = __float_as_uint(row_ok ? o.x : 0.f);
-                        v[i + 1] = __float_as_uint(row_ok ? o.y : 0.f);
-                        v[i + 2] = __float_as_uint(row_ok ? o.z : 0.f);
-                        v[i + 3] = __float_as_uint(row_ok ? o.w : 0.f);
+                for (int i = 0; i < CW; i += 4)
+                    *reinterpret_cast<uint4*>(st + lane * DG_EP_PITCH + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + c0 + c4));
+                float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 32 / RPI; ++j) {
+                    const int r = j * RPI + rsub;
+                    float4 o = *reinterpret_cast<const float4*>(st + r * DG_EP_PITCH + c4);
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    if (r_base + r < rows_cta) {
+                        *reinterpret_cast<float4*>(out + (size_t)(row0 + r_base + r) * COUT + c0 + c4) = o;
+                        sa.x += o.x; sa.y += o.y; sa.z += o.z; sa.w += o.w;
+                        sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
                     }
                 }
                 if (stats != nullptr) {
-                    float a[32], sq[32];
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) {
-                        a[i] = __uint_as_float(v[i]);
-                        sq[i] = a[i] * a[i];
+                    for (int sft = LPR; sft < 32; sft <<= 1) {      // fold the RPI row groups: fixed order
+                        sa.x += __shfl_xor_sync(0xffffffffu, sa.x, sft); sa.y += __shfl_xor_sync(0xffffffffu, sa.y, sft);
+                        sa.z += __shfl_xor_sync(0xffffffffu, sa.z, sft); sa.w += __shfl_xor_sync(0xffffffffu, sa.w, sft);
+                        sq.x += __shfl_xor_sync(0xffffffffu, sq.x, sft); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, sft);
+                        sq.z += __shfl_xor_sync(0xffffffffu, sq.z, sft); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, sft);
                     }
-                    int col = 0;
-#pragma unroll
-                    for (int sft = CW / 2; sft >= 1; sft >>= 1) {
-                        const bool up = (lane & sft) != 0;
-#pragma unroll
-                        for (int i = 0; i < sft; ++i) {
-                            const float sa = up ? a[i] : a[i + sft];
-                            const float sb = up ? sq[i] : sq[i + sft];
-                            const float ra = __shfl_xor_sync(0xffffffffu, sa, sft);
-                            const float rq = __shfl_xor_sync(0xffffffffu, sb, sft);
-                            a[i] = (up ? a[i + sft] : a[i]) + ra;
-                            sq[i] = (up ? sq[i + sft] : sq[i]) + rq;
-                        }
-                        if (up) col += sft;
-                    }
-                    if (CW == 16) {
-                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);
-                        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 16);
-                    }
-                    if (CW == 32 || lane < 16) {          // the warp's own slot, tiles in ascending order: no atomics
-                        wpart_s[(warp * 2 + 0) * COUT + c0 + col] += a[0];
-                        wpart_s[(warp * 2 + 1) * COUT + c0 + col] += sq[0];
+                    if (lane < LPR) {                     // the warp's own slot, tiles in ascending order: no atomics
+                        float* pa = wpart_s + (warp * 2 + 0) * COUT + c0 + c4;
+                        float* pq = wpart_s + (warp * 2 + 1) * COUT + c0 + c4;
+                        pa[0] += sa.x; pa[1] += sa.y; pa[2] += sa.z; pa[3] += sa.w;
+                        pq[0] += sq.x; pq[1] += sq.y; pq[2] += sq.z; pq[3] += sq.w;
                     }
                 }
             }
@@ -444,9 +458,15 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
         const int q = warp & 3;
         const int rsub = lane >> 2;                      // row within an 8-row group
         const int csub = (lane & 3) * 4;                 // first of this thread's 4 channels within a 16-channel unit
+        DG_PROBE_DECL(6)
         for (int it = set; it < n_a; it += DG_SETS) {
             const int islot = it % DG_IDX_STAGES;
+#ifdef UD_DG_PROBE
+            pr_[0] += 1;
+            pt_ = clock64();
+#endif
             mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / DG_IDX_STAGES)) & 1u);
+            DG_PROBE_LAP(1)
             // rows 32 q + 16 h + rsub + 8 rr of the tile, for every tap of the stage
             int idx[2][2][TAPG];
 #pragma unroll
@@ -491,6 +511,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                         }
             }
             const int aslot = it % A_STAGES;             // == set
+            DG_PROBE_LAP(2)
             uint32_t hi[2][16], lo[2][16];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -511,9 +532,21 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                                             lo[h][4 * j + 2 * rr + 1]);
                         }
                     }
+#ifdef UD_DG_PROBE
+            {   // the lap must not start before the converted values exist
+                uint32_t dep = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dep ^= hi[h][i] ^ lo[h][i];
+                asm volatile("" :: "r"(dep));
+            }
+#endif
+            DG_PROBE_LAP(3)
             // the conversions do not need the TMEM slot: only the stores wait for the MMAs that read it last
             mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
             tc_fence_after();
+            DG_PROBE_LAP(4)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
@@ -523,14 +556,21 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar_a_full + 8 * aslot);
+            DG_PROBE_LAP(5)
         }
+        DG_PROBE_FLUSH(0, 6, q == 0 && lane == 0)
     } else if (warp == 16) {
         // ============ MMA issuer ============
         unsigned int started = 0u;
         int it = 0;
+        DG_PROBE_DECL(6)
+#ifdef UD_DG_PROBE
+        const long long cta_t0 = pt_;
+#endif
         for (int ib = 0; ib < n_b; ++ib) {
             const int bslot = ib % DG_B_STAGES;
             mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / DG_B_STAGES)) & 1u);
+            DG_PROBE_LAP(1)
             const uint32_t b_base = smem_b + bslot * B_BYTES;
             const uint64_t db_hi = umma_desc_sw128(b_base);
             const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
@@ -539,7 +579,9 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                 const int aslot = it % A_STAGES;
                 const int tile = a_sched[it] >> 8;
                 mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+                DG_PROBE_LAP(2)
                 tc_fence_after();
+                DG_PROBE_LAP(4)
                 if (elect_one_sync()) {
                     const uint32_t a_stage = tmem_a + (uint32_t)(aslot * A_COLS);
                     const uint32_t d = tmem_acc + (uint32_t)(tile * COUT);
@@ -557,12 +599,24 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                 }
                 started |= 1u << tile;
                 __syncwarp();
+#ifdef UD_DG_PROBE
+                pr_[0] += 1;
+#endif
+                DG_PROBE_LAP(3)
             }
             if (elect_one_sync()) umma_commit(bar_b_empty + 8 * bslot);
             __syncwarp();
         }
         if (elect_one_sync()) umma_commit(bar_acc);
         __syncwarp();
+#ifdef UD_DG_PROBE
+        if (lane == 0) {
+            atomicAdd(&ud_dg_probe_acc[6], (unsigned long long)pr_[4]);      // tcgen05.fence::after_thread_sync after the A wait
+            atomicAdd(&ud_dg_probe_acc[12], 1ull);
+            atomicAdd(&ud_dg_probe_acc[13], (unsigned long long)(clock64() - cta_t0));
+        }
+#endif
+        DG_PROBE_FLUSH(8, 4, lane == 0)
     } else {
         // ============ warp 17: weight slices, warp 18: per-stage row-index segments (bulk async copies) ============
         if (warp == 17 && lane == 0) {
@@ -591,8 +645,16 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
         __syncwarp();
     }
 
+#ifdef UD_DG_PROBE
+    const long long ep_t0 = clock64();
+#endif
     dg_epilogue<COUT, DG_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
-                                  stat_group, &stat_last_s);
+                                         stat_group, &stat_last_s,
+                                  reinterpret_cast<float*>(smem_al + ((size_t)DG_B_STAGES * B_BYTES >= DG_EP_STAGE_BYTES
+                                                                          ? 0 : DG_B_STAGES * B_BYTES + DG_IDX_STAGES * IDX_INTS * 4)));
+#ifdef UD_DG_PROBE
+    if (tid == 0) atomicAdd(&ud_dg_probe_acc[14], (unsigned long long)(clock64() - ep_t0));
+#endif
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
@@ -903,8 +965,9 @@ k_spconv_umma_win(const __grid_constant__ CUtensorMap idx_map, const __grid_cons
         __syncwarp();
     }
 
+    static_assert((size_t)WIN_SLOTS * WIN_BYTES >= DG_EP_STAGE_BYTES, "the epilogue stages its tiles in the (idle) window ring");
     dg_epilogue<COUT, WIN_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
-                                   stat_group, &stat_last_s);
+                                   stat_group, &stat_last_s, reinterpret_cast<float*>(smem_al + W_OFF));
     if (warp == 16) tmem_dealloc(tmem_acc, 512);
 }
 
@@ -1138,3 +1201,14 @@ int ud_sparse_conv_tc_forward(const float* in, int in_is_split, const void* wpac
 }
 
 }  // extern "C"
+
+#ifdef UD_DG_PROBE
+extern "C" int ud_debug_dg_probe(unsigned long long* host_out16, int reset) {
+    if (host_out16 != nullptr) UD_CUDA_TRY(cudaMemcpyFromSymbol(host_out16, ud_dg_probe_acc, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long zero[16] = {};
+        UD_CUDA_TRY(cudaMemcpyToSymbol(ud_dg_probe_acc, zero, sizeof(zero)));
+    }
+    return UD_OK;
+}
+#endif

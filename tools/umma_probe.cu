@@ -33,9 +33,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d, uint64_t a, uint64_t b, u
                  ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
+__device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode 9 = bf16 TS same accumulator (K=16), 10 = bf16 TS in the conv kernel's hi/lo pattern (3 MMAs per 16 channels, two
+// weight planes, four accumulator tiles round robin every 12 MMAs)
 // mode: 0 = SS same accumulator, 1 = SS alternating 2 accumulators, 2 = TS same, 3 = TS alternating,
 //       4 = SS 4 accumulators round robin, 5 = bf16 SS same accumulator (K=16)
-__global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mma, long long* out, int st_iters) {
+template <int mode>
+__global__ void __launch_bounds__(256, 1) probe(int N, int M, int n_mma, long long* out, int st_iters) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ __align__(8) unsigned long long bar2[4];
@@ -59,7 +67,7 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mm
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
-    const uint32_t fmt = mode == 5 ? 1u : 2u;      // bf16 : tf32
+    const uint32_t fmt = (mode == 5 || mode == 9 || mode == 10) ? 1u : 2u;      // bf16 : tf32
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     if (warp == 1) {
         long long t0 = 0, t1 = 0;
@@ -93,12 +101,21 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mm
             } else
             if (elect_one_sync()) {
                 const uint64_t da = desc_sw128(base), db = desc_sw128(base + 16384);
+#pragma unroll 12
                 for (int i = 0; i < n_mma; ++i) {
                     const uint64_t adv = (uint64_t)((i & 3) * 2);
                     uint32_t d = tmem;
                     if (mode == 1 || mode == 3) d = tmem + (uint32_t)((i & 1) * 256);
                     if (mode == 4) d = tmem + (uint32_t)((i & 3) * 128);
-                    if (mode == 2 || mode == 3) mma_ts(d, tmem + 480 + (i & 3) * 8, db + adv, idesc, 1u);
+                    if (mode == 9) mma_f16_ts(d, tmem + 480 + (i & 3) * 8, db + adv, idesc, 1u);
+                    else if (mode == 10) {
+                        const int k16 = (i / 3) & 3, term = i % 3, stage = i / 12;
+                        const uint32_t a_hi = tmem + 256 + (uint32_t)((stage & 3) * 64 + k16 * 8), a_lo = a_hi + 32;
+                        const uint64_t b_hi = db + (uint64_t)(k16 * 2), b_lo = desc_sw128(base + 16384 + 8192) + (uint64_t)(k16 * 2);
+                        const uint32_t dd = tmem + (uint32_t)((stage & 3) * (N > 64 ? 0 : 64));
+                        mma_f16_ts(dd, term == 0 ? a_lo : a_hi, term == 1 ? b_lo : b_hi, idesc, 1u);
+                    }
+                    else if (mode == 2 || mode == 3) mma_ts(d, tmem + 480 + (i & 3) * 8, db + adv, idesc, 1u);
                     else if (mode == 5) mma_f16_ss(d, da + adv, db + adv, idesc, 1u);
                     else mma_ss(d, da + adv, db + adv, idesc, 1u);
                 }
@@ -138,19 +155,23 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int N, int M, int n_mm
 int main() {
     long long* d_out;
     cudaMalloc(&d_out, 148 * sizeof(long long));
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc", "?", "TS staged d2", "TS staged d4"};
+    const char* names[] = {"SS same acc", "SS 2 accs", "TS same acc", "TS 2 accs", "SS 4 accs", "bf16 SS same acc", "?", "TS staged d2", "TS staged d4", "bf16 TS same acc", "bf16 TS hi/lo x3"};
     const int Ns[] = {16, 32, 64, 128, 256};
     for (int grid : {148})
-        for (int mode : {2, 7, 8})
+        for (int mode : {2, 9, 10})
             for (int N : Ns) {
                 if ((mode == 1 || mode == 3) && N > 256) continue;
                 if (mode == 4 && N > 128) continue;
-                if ((mode == 2 || mode == 3 || mode >= 7) && N > 224) continue;   // acc must not overlap the A columns at 480
-                for (int n_mma : {256}) {
+                if ((mode == 2 || mode == 3 || mode >= 7) && N > 224) continue;
+                if (mode == 10 && N > 128) continue;   // acc must not overlap the A columns at 480
+                for (int n_mma : {12, 48, 240}) {
                   for (int st_iters : {0, 100000}) {
-                    if (st_iters && (mode != 2 || n_mma != 256)) continue;
-                    probe<<<grid, 256, 64 * 1024>>>(mode, N, 128, n_mma, d_out, st_iters);
+                    if (st_iters && n_mma != 240) continue;
+                    auto launch = [&](auto kern) {
+                        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                        kern<<<grid, 256, 64 * 1024>>>(N, 128, n_mma, d_out, st_iters);
+                    };
+                    if (mode == 2) launch(probe<2>); else if (mode == 9) launch(probe<9>); else launch(probe<10>);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     long long h[148];
