@@ -525,6 +525,14 @@ def _algorithmic(name, a, meta, cache):
         kern = meta.get("kernel", "k_spconv_umma_dg" if tc else "k_spconv_gather_gemm")
         return ("%s<%d,%d> K=%d (fwd/dgrad)" % (kern, cin, cout, K), "tensor" if (tc and cin >= 32) else "hbm",
                 4 * (n_in * cin + n_out * cout + n_out * K + K * cin * cout), 2.0 * P * cin * cout)
+    if name == "ud_sparse_conv_tc_forward_affine":
+        n_out, K, cin, cout = a[9], a[10], a[11], a[12]
+        n_in = meta.get("n_in", n_out)
+        P = _lazy_int(cache, meta["table"], lambda t: (t >= 0).sum().item()) if "table" in meta else n_out * K
+        return ("k_spconv_umma_dg<%d,%d> K=%d (fwd + eval-BN/residual/ReLU epilogue)" % (cin, cout, K),
+                "tensor" if cin >= 32 else "hbm",
+                4 * (n_in * cin + n_out * cout * (2 if meta.get("residual") else 1) + n_out * K + K * cin * cout),
+                2.0 * P * cin * cout)
     if name in ("ud_sparse_conv_tc_wgrad", "ud_sparse_conv_wgrad"):
         tc = name == "ud_sparse_conv_tc_wgrad"
         n_rows, K, cin, cout = (a[4], a[5], a[6], a[7]) if tc else (a[3], a[4], a[5], a[6])

@@ -230,6 +230,16 @@ constexpr int DG_IDX_STAGES = 16;
 constexpr int DG_B_STAGES = 4;
 // statistics buffer: [0, 4096) final sums (2 * COUT doubles), then the workspace of det_reduce.cuh
 constexpr int DG_STAT_FINAL_BYTES = 4096;
+// Optional output transform of the forward kernels (inference: the eval-mode BatchNorm1d, residual add and ReLU that follow a
+// convolution in spconv_backbone.py:50-56,97-113 folded into its epilogue): out = relu?((acc + bias[c]) * scale[c] + shift[c] (+ residual)).
+// Same arithmetic as k_bn_apply (fmaf, then the residual, then the clamp), so fused and unfused results are bit-identical.
+struct DgPost {
+    const float* scale;        // (cout) or nullptr = no transform (bias path)
+    const float* shift;        // (cout)
+    const float* residual;     // (n_out, cout) or nullptr
+    int relu;
+};
+
 // staging buffer of the epilogue (dg_epilogue): one [32 rows x 36 floats] tile per epilogue warp
 constexpr int DG_EP_PITCH = 36;                          // floats per staged row: 16-byte aligned, conflict-free LDS/STS.128
 constexpr int DG_EP_STAGE_FLOATS = 32 * DG_EP_PITCH;
@@ -274,7 +284,7 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
                                             const unsigned int* tile_mask_s, uint32_t tmem_acc,
                                             const float* __restrict__ bias, float* __restrict__ out,
                                             unsigned char* __restrict__ stats, float* wpart_s, int stat_group,
-                                            int* stat_last_s, float* stage) {
+                                            int* stat_last_s, float* stage, const DgPost post = DgPost{nullptr, nullptr, nullptr, 0}) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
     // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
@@ -311,15 +321,31 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
                 for (int i = 0; i < CW; i += 4)
                     *reinterpret_cast<uint4*>(st + lane * DG_EP_PITCH + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 __syncwarp();
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = b;
                 if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + c0 + c4));
+                if (post.scale) {
+                    sc = __ldg(reinterpret_cast<const float4*>(post.scale + c0 + c4));
+                    sh = __ldg(reinterpret_cast<const float4*>(post.shift + c0 + c4));
+                }
                 float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 32 / RPI; ++j) {
                     const int r = j * RPI + rsub;
                     float4 o = *reinterpret_cast<const float4*>(st + r * DG_EP_PITCH + c4);
                     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    if (post.scale) {
+                        o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y);
+                        o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
+                    }
                     if (r_base + r < rows_cta) {
+                        if (post.residual) {
+                            const float4 rs = __ldg(reinterpret_cast<const float4*>(
+                                post.residual + (size_t)(row0 + r_base + r) * COUT + c0 + c4));
+                            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+                        }
+                        if (post.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
                         *reinterpret_cast<float4*>(out + (size_t)(row0 + r_base + r) * COUT + c0 + c4) = o;
                         sa.x += o.x; sa.y += o.y; sa.z += o.z; sa.w += o.w;
                         sq.x += o.x * o.x; sq.y += o.y * o.y; sq.z += o.z * o.z; sq.w += o.w * o.w;
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1)
 k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __restrict__ in,
                  const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
-                 int tiles, float* __restrict__ out, unsigned char* __restrict__ stats, int stat_group) {
+                 int tiles, float* __restrict__ out, unsigned char* __restrict__ stats, int stat_group, const DgPost post) {
     constexpr int TAPG = ts_tapg(CIN);               // kernel taps per 64-channel stage
     constexpr int KS = 64;
     constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
@@ -651,7 +677,8 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     dg_epilogue<COUT, DG_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
                                          stat_group, &stat_last_s,
                                   reinterpret_cast<float*>(smem_al + ((size_t)DG_B_STAGES * B_BYTES >= DG_EP_STAGE_BYTES
-                                                                          ? 0 : DG_B_STAGES * B_BYTES + DG_IDX_STAGES * IDX_INTS * 4)));
+                                                                          ? 0 : DG_B_STAGES * B_BYTES + DG_IDX_STAGES * IDX_INTS * 4)),
+                                  post);
 #ifdef UD_DG_PROBE
     if (tid == 0) atomicAdd(&ud_dg_probe_acc[14], (unsigned long long)(clock64() - ep_t0));
 #endif
@@ -1010,7 +1037,7 @@ size_t dg_stat_bytes(int n_out, int cout) {
 template <int CIN, int COUT, bool SPLIT>
 int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
                    const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const DgPost post = DgPost{nullptr, nullptr, nullptr, 0}) {
     const size_t smem = dg_smem_bytes(CIN, COUT);
     auto kern = k_spconv_umma_dg<CIN, COUT, SPLIT>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1024,7 +1051,7 @@ int launch_umma_dg(const float* in, const float* wpacked, const float* bias, con
                                  (uint32_t)ts_tapg(CIN), TILE_M);
     if (rc != UD_OK) return rc;
     kern<<<ctas, DG_THREADS, smem, stream>>>(idx_map, in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
-                                             ud_det_group(ctas));
+                                             ud_det_group(ctas), post);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }
@@ -1069,6 +1096,9 @@ bool tc_shape_ok(int K, int cin, int cout) {
     if (cin == CI && cout == CO)                                                                                            \
         return in_is_split ? launch_umma_dg<CI, CO, true>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream)  \
                            : launch_umma_dg<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream);
+#define UD_DISPATCH_DG_POST(CI, CO)                                                                                          \
+    if (cin == CI && cout == CO)                                                                                            \
+        return launch_umma_dg<CI, CO, false>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, nullptr, stream, post);
 
 extern "C" {
 
@@ -1197,6 +1227,32 @@ int ud_sparse_conv_tc_forward(const float* in, int in_is_split, const void* wpac
     UD_DISPATCH_DG(64, 128)
     UD_DISPATCH_DG(128, 64)
     UD_DISPATCH_DG(128, 128)
+    return UD_ERR_UNSUPPORTED;
+}
+
+// Inference form: out = relu?((conv(in) + bias) * scale[c] + shift[c] (+ residual)) -- the eval-mode BatchNorm1d (+ residual)
+// + ReLU that follows every convolution of the backbone, folded into the convolution's epilogue.
+int ud_sparse_conv_tc_forward_affine(const float* in, const void* wpacked_, const float* bias, const float* scale, const float* shift,
+                                     const float* residual, int relu, const int* nbr_t, const unsigned int* tile_masks,
+                                     int n_out, int K, int cin, int cout, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float* wpacked = (const float*)wpacked_;
+    if (!in || !wpacked || !scale || !shift || !nbr_t || !tile_masks || !out || n_out < 0) return UD_ERR_INVALID_ARG;
+    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)in | (uintptr_t)wpacked | (uintptr_t)out | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)residual) & 15u) != 0)
+        return UD_ERR_INVALID_ARG;
+    if (n_out == 0) return UD_OK;
+    const DgPost post{scale, shift, residual, relu};
+    UD_DISPATCH_DG_POST(16, 16)
+    UD_DISPATCH_DG_POST(16, 32)
+    UD_DISPATCH_DG_POST(32, 16)
+    UD_DISPATCH_DG_POST(32, 32)
+    UD_DISPATCH_DG_POST(32, 64)
+    UD_DISPATCH_DG_POST(64, 32)
+    UD_DISPATCH_DG_POST(64, 64)
+    UD_DISPATCH_DG_POST(64, 128)
+    UD_DISPATCH_DG_POST(128, 64)
+    UD_DISPATCH_DG_POST(128, 128)
     return UD_ERR_UNSUPPORTED;
 }
 

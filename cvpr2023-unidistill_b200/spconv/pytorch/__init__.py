@@ -152,10 +152,20 @@ class SparseConvolution(SparseModule):
             x.indice_dict[self.indice_key] = rb
         return rb
 
-    def forward(self, x):
+    def forward(self, x, bn=None, relu=False, residual=None):
+        """`bn` (extension used by SparseSequential / SparseBasicBlock): an eval-mode BatchNorm1d whose application, the
+        optional residual add and ReLU are folded into this convolution's epilogue when no gradient is needed; returns
+        None in that case if the fused form does not apply (the caller then runs the modules one by one)."""
         assert isinstance(x, SparseConvTensor)
         rb = self._rulebook(x)
-        feats = _sp.sparse_conv(x.features, self.weight, self.bias, rb, self.inverse)
+        if bn is not None:
+            if self.inverse:
+                return None
+            feats = _sp.sparse_conv_eval_bn_act(x.features, self.weight, self.bias, rb, bn, relu=relu, residual=residual)
+            if feats is None:
+                return None
+        else:
+            feats = _sp.sparse_conv(x.features, self.weight, self.bias, rb, self.inverse)
         if self.subm:
             out = SparseConvTensor(feats, x.indices, x.spatial_shape, x.batch_size, x.grid, x.voxel_num,
                                    x.indice_dict, x.benchmark)
@@ -239,6 +249,16 @@ class SparseSequential(SparseModule):
             module = mods[i]
             if is_spconv_module(module):
                 assert isinstance(input, SparseConvTensor)
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if (isinstance(module, SparseConvolution) and type(nxt) is nn.BatchNorm1d and not nxt.training
+                        and input.features.is_cuda and input.indices.shape[0] > 0):
+                    # [conv, eval-mode BatchNorm1d(, ReLU)] without gradients: one kernel
+                    relu = i + 2 < len(mods) and type(mods[i + 2]) is nn.ReLU
+                    fused = module(input, bn=nxt, relu=relu)
+                    if fused is not None:
+                        input = fused
+                        i += 3 if relu else 2
+                        continue
                 input = module(input)
                 i += 1
                 continue

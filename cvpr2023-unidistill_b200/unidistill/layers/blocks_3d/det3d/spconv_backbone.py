@@ -58,6 +58,13 @@ class SparseBasicBlock(spconv.SparseModule):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
+        if not self.bn1.training and not self.bn2.training and x.features.is_cuda and x.indices.shape[0] > 0:
+            # frozen / inference: BatchNorm, residual and ReLU ride in the convolutions' epilogues (None = not applicable)
+            out = self.conv1(x, bn=self.bn1, relu=True)
+            if out is not None:
+                out2 = self.conv2(out, bn=self.bn2, relu=True, residual=identity.features)
+                if out2 is not None:
+                    return out2
         out = self.conv1(x)
         if _fusable(self.bn1, out.features):
             out = out.replace_feature(batch_norm_act(out.features, self.bn1, relu=True))

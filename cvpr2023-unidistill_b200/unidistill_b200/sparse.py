@@ -257,7 +257,9 @@ def _packed_weights(w_k, K, cin, cout, sp, weight=None):
     return packed
 
 
-def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None, want_stats=False):
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None, want_stats=False, post=None):
+    """`post` = (scale, shift, residual | None, relu): inference epilogue relu?(conv * scale + shift (+ residual)); only the
+    tensor-core kernel has it (the caller checks ud_sparse_conv_tc_supported)."""
     lib = native.load()
     dev = feats.device
     out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
@@ -269,6 +271,17 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
         if meta is not None:
             meta["kernel"] = "k_spconv_umma_dg"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
+        if post is not None:
+            scale, shift, residual, relu = post
+            if meta is not None:
+                meta["residual"] = residual is not None
+            native.TIMER.meta = meta
+            rc = lib.ud_sparse_conv_tc_forward_affine(native.ptr(feats), native.ptr(packed), native.ptr(bias), native.ptr(scale),
+                                                      native.ptr(shift), native.ptr(residual), 1 if relu else 0,
+                                                      native.ptr(table_t), native.ptr(masks), n_out, K, cin, cout,
+                                                      native.ptr(out), sp)
+            native.check(rc, "ud_sparse_conv_tc_forward_affine")
+            return out
         stats = None
         if want_stats and FUSE_BN_STATS:
             # scratch of the kernel's fixed-order statistics reduction; its first 2 * cout doubles are the result
@@ -424,6 +437,64 @@ PRE_SPLIT_INPUT = os.environ.get("UD_SPCONV_PRESPLIT", "0") != "0"
 # tcgen05 forward and weight-gradient kernels instead of the fp32 SIMT pair (measured per step: wgrad 1.23 -> 0.16 ms,
 # forward 0.15 -> 0.10 ms); the padded channels contribute exact zeros, the weight gradient is sliced back by autograd.
 PAD_NARROW_INPUT = os.environ.get("UD_SPCONV_PAD_INPUT", "1") != "0"
+
+
+FUSE_EVAL_BN = os.environ.get("UD_SPCONV_FUSE_EVAL_BN", "1") != "0"
+_EVAL_COEFFS = {}
+
+
+def _eval_bn_coeffs(bn):
+    """(scale, shift) of an eval-mode BatchNorm1d, cached until a parameter or buffer of the module is written to (tensor
+    version counters)."""
+    tensors = (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+    key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (bn.eps,)
+    hit = _EVAL_COEFFS.get(id(bn))
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    lib = native.load()
+    C = int(bn.running_mean.shape[0])
+    dev = bn.running_mean.device
+    scale = torch.empty((C,), dtype=torch.float32, device=dev)
+    shift = torch.empty((C,), dtype=torch.float32, device=dev)
+    rc = lib.ud_bn_eval_coeffs(native.ptr(bn.running_mean), native.ptr(bn.running_var), native.ptr(bn.weight),
+                               native.ptr(bn.bias), float(bn.eps), C, native.ptr(scale), native.ptr(shift),
+                               native.stream_ptr(dev))
+    native.check(rc, "ud_bn_eval_coeffs")
+    _EVAL_COEFFS[id(bn)] = (key, scale, shift)
+    return scale, shift
+
+
+def sparse_conv_eval_bn_act(features, weight, bias, rulebook, bn, relu=True, residual=None):
+    """relu?(bn(sparse_conv(features)) (+ residual)) for an eval-mode BatchNorm1d `bn` as ONE kernel (the convolution's
+    epilogue applies scale / shift / residual / ReLU) when nothing needs a gradient; returns None when the fused form does
+    not apply (the caller then runs convolution and batch_norm_act separately -- bit-identical results either way)."""
+    if not (FUSE_EVAL_BN and USE_TENSOR_CORES and features.is_cuda and not bn.training and bn.running_mean is not None):
+        return None
+    if torch.is_grad_enabled() and (features.requires_grad or weight.requires_grad
+                                    or (bn.weight is not None and bn.weight.requires_grad)
+                                    or (residual is not None and residual.requires_grad)):
+        return None
+    if USE_WINDOW_KERNEL or PRE_SPLIT_INPUT:
+        return None
+    cin, cout = int(weight.shape[-1]), int(weight.shape[0])
+    lib = native.load()
+    feats, w = features, weight
+    if cin < 16:
+        if not PAD_NARROW_INPUT:
+            return None
+        feats = torch.nn.functional.pad(features, (0, 16 - cin))
+        w = torch.nn.functional.pad(weight.detach(), (0, 16 - cin))
+        cin = 16
+    rb = rulebook
+    if rb.n_out <= 0 or not lib.ud_sparse_conv_tc_supported(rb.K, cin, cout):
+        return None
+    feats = feats.detach().contiguous().float()
+    scale, shift = _eval_bn_coeffs(bn)
+    res = residual.detach().contiguous().float() if residual is not None else None
+    w_det = w.detach()
+    b = bias.detach().float().contiguous() if bias is not None else None
+    return _conv_forward_raw(feats, lambda: weight_to_taps(w_det.float()), b, rb.nbr_out, rb.n_out, rb.K, cin, cout, rb,
+                             weight if w is weight else None, post=(scale, shift, res, relu))
 
 
 def sparse_conv(features, weight, bias, rulebook, inverse=False):

@@ -145,6 +145,13 @@ int ud_split_bf16(const float* x, int n, int C, void* out, void* stream);
 int ud_sparse_conv_tc_forward(const float* in, int in_is_split, const void* packed, const float* bias, const int* nbr_t,
                               const unsigned int* tile_masks, int n_out, int K, int cin, int cout, float* out,
                               void* bn_stats, void* stream);
+/* Inference form of ud_sparse_conv_tc_forward: out = relu?((conv(in) + bias[c]) * scale[c] + shift[c] (+ residual[o][c])),
+ * i.e. the eval-mode BatchNorm1d (scale / shift from ud_bn_eval_coeffs), the residual add of SparseBasicBlock and the ReLU
+ * that follow the convolution (spconv_backbone.py:50-56,97-113), applied in its epilogue with the arithmetic of
+ * ud_bn_apply (bit-identical to ud_sparse_conv_tc_forward -> ud_bn_apply).  bias and residual nullable. */
+int ud_sparse_conv_tc_forward_affine(const float* in, const void* packed, const float* bias, const float* scale, const float* shift,
+                                     const float* residual, int relu, const int* nbr_t, const unsigned int* tile_masks,
+                                     int n_out, int K, int cin, int cout, float* out, void* stream);
 /* Window-staged variant for 3x3x3 kernels with 64 input channels (raster row order): TMA stages, once per (tile, kz, ky),
  * the 160-row window of the feature matrix that holds the rows the three kx taps gather (97 % of them on the bench
  * clouds) and the operands are built from shared memory; rows outside the window come from global memory, so any table is

@@ -415,6 +415,51 @@ def test_backbone_forward_parity(cuda, native_lib, training):
     assert _rel_err(bev.detach().cpu().numpy(), ref_bev) < REL_TOL
 
 
+def test_eval_bn_epilogue_fusion_is_bit_identical(cuda, native_lib, monkeypatch):
+    """Frozen / inference encoder: BatchNorm1d(eval) + residual + ReLU folded into the convolutions' epilogues
+    (ud_sparse_conv_tc_forward_affine) against the same encoder running convolution and ud_bn_apply separately."""
+    from unidistill.layers.blocks_3d.det3d import VoxelResBackBone8x
+    from unidistill_b200 import sparse as SP
+
+    torch.manual_seed(0)
+    rng = np.random.default_rng(12)
+    sparse_shape = [41, 64, 64]
+    net = VoxelResBackBone8x(5, np.array([64, 64, 40]))
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.weight.uniform_(0.6, 1.4)
+                mod.bias.uniform_(-0.3, 0.3)
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+    net = net.to(cuda).eval()
+    coords, feat = _clustered_sparse(rng, 2, sparse_shape, 6000, 5)
+    f, c = torch.from_numpy(feat).to(cuda), torch.from_numpy(coords).to(cuda)
+    calls = []
+    orig = SP.sparse_conv_eval_bn_act
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        calls.append(out is not None)
+        return out
+
+    monkeypatch.setattr(SP, "sparse_conv_eval_bn_act", spy)
+    with torch.no_grad():
+        fused, _, scales_f = net(f, c, 2)
+        assert len(calls) == 21 and all(calls)          # every convolution of the encoder took the fused form
+        monkeypatch.setattr(SP, "FUSE_EVAL_BN", False)
+        plain, _, scales_p = net(f, c, 2)
+    assert torch.equal(fused.indices, plain.indices)
+    assert torch.equal(fused.features, plain.features)
+    for k in scales_p:
+        assert torch.equal(scales_f[k].features, scales_p[k].features), k
+    # with gradients required the modules run one by one (autograd needs the intermediate tensors)
+    calls.clear()
+    monkeypatch.setattr(SP, "FUSE_EVAL_BN", True)
+    out, _, _ = net(f.clone().requires_grad_(True), c, 2)
+    assert out.features.requires_grad and not any(calls)
+
+
 def test_backbone_gradients_through_the_whole_stack(cuda, native_lib):
     """End-to-end backward of the 21-layer encoder (tcgen05 dgrad, TF32 wgrad, fused BatchNorm backward, scatter backward)
     against autograd through the CPU oracle of the same stack: every parameter gradient and the input-feature gradient.
