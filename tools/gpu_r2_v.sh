@@ -2,7 +2,7 @@
 # session V: eval-BN / residual / ReLU folded into the conv epilogue for frozen encoders
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_lidar.py tests/test_gpu_sparse_tc.py tests/test_gpu_step.py -x -q -m gpu --timeout 600 > gpurun_out/v_tests.log 2>&1
+timeout 1200 python -m pytest tests/test_gpu_lidar.py tests/test_gpu_sparse_tc.py tests/test_gpu_step.py tests/test_gpu_glue.py -x -q -m gpu --timeout 600 > gpurun_out/v_tests.log 2>&1
 echo "tests rc=$?"; tail -3 gpurun_out/v_tests.log
 timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/v_bench.json 2> gpurun_out/v_bench.err
 echo "bench rc=$?"; tail -3 gpurun_out/v_bench.err
