@@ -529,7 +529,8 @@ def _algorithmic(name, a, meta, cache):
         n_out, K, cin, cout = a[9], a[10], a[11], a[12]
         n_in = meta.get("n_in", n_out)
         P = _lazy_int(cache, meta["table"], lambda t: (t >= 0).sum().item()) if "table" in meta else n_out * K
-        return ("k_spconv_umma_dg<%d,%d> K=%d (fwd + eval-BN/residual/ReLU epilogue)" % (cin, cout, K),
+        # the same kernel instantiation as ud_sparse_conv_tc_forward (epilogue flags are run-time): one roofline group
+        return ("k_spconv_umma_dg<%d,%d> K=%d (fwd/dgrad)" % (cin, cout, K),
                 "tensor" if cin >= 32 else "hbm",
                 4 * (n_in * cin + n_out * cout * (2 if meta.get("residual") else 1) + n_out * K + K * cin * cout),
                 2.0 * P * cin * cout)
@@ -785,29 +786,37 @@ def _allreduce_report(step_fn, wl, world, device, args):
     rep["standalone_ms"] = round(_reduce(e0.elapsed_time(e1), world, device, "max"), 3)
     b.flat.zero_()
     # exposed cost: K steps with the hooks disabled and no exchange at all (NOT a valid training step: timing probe only)
+    # against K steps with it, timed like pass 1 (per-step events, L2 flushed between steps, collector off: a generational
+    # collection on one rank stalls every rank through the exchange and would be booked as "exposed")
+    import gc
+
+    flush = L2Flusher(device)
+
+    def k_steps(warm):
+        for _ in range(warm):
+            wl.step()
+        events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        _barrier(world)
+        for a, c in events:
+            flush()
+            a.record()
+            wl.step()
+            c.record()
+        _barrier(world)
+        torch.cuda.synchronize()
+        return _reduce(sum(a.elapsed_time(c) for a, c in events), world, device, "max") / args.steps
+
+    gc.collect()
+    gc.disable()
     b.enabled = False
     orig_fire = b._fire
     b._fire = lambda i: b._fired.__setitem__(i, True)
-    for _ in range(2):
-        wl.step()
-    _barrier(world)
-    e0.record()
-    for _ in range(args.steps):
-        wl.step()
-    e1.record()
-    _barrier(world)
-    no_xchg = _reduce(e0.elapsed_time(e1), world, device, "max") / args.steps
+    no_xchg = k_steps(2)
     b._fire = orig_fire
     b.enabled = True
-    for _ in range(1):
-        wl.step()
-    _barrier(world)
-    e0.record()
-    for _ in range(args.steps):
-        wl.step()
-    e1.record()
-    _barrier(world)
-    with_xchg = _reduce(e0.elapsed_time(e1), world, device, "max") / args.steps
+    with_xchg = k_steps(1)
+    gc.enable()
     rep["step_ms_without_exchange"] = round(no_xchg, 3)
     rep["step_ms_with_exchange"] = round(with_xchg, 3)
     rep["exposed_ms"] = round(with_xchg - no_xchg, 3)
