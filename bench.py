@@ -401,7 +401,8 @@ class DistillTrainStep:
         student = models.BEVFusionCenterHead(s_cfg).to(device).use_channels_last(cl)
         self.step_fn = DistillStep(student, teacher, t_cfg["geometry"], preset=self.preset, teacher_mode=teacher_mode,
                                    overlap_allreduce=os.environ.get("UD_OVERLAP_ALLREDUCE", "1") != "0",
-                                   student_cuda_graph=os.environ.get("UD_STUDENT_GRAPH", "1") != "0")
+                                   student_cuda_graph=os.environ.get("UD_STUDENT_GRAPH", "1") != "0",
+                                   overlap_teacher_camera=os.environ.get("UD_OVERLAP_CAMERA", "0") != "0")
         self.bn_note = ("student: train-mode batch statistics under autograd%s; teacher: frozen, %s" % (
             ", dense trunk + loss + their backward replayed from CUDA graphs" if student._train_graph is not None else "",
             "eval mode, BatchNorm2d folded into its convolutions, dense trunk replayed from a CUDA graph"

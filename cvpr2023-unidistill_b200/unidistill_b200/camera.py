@@ -139,8 +139,9 @@ def lss_geometry_index(frustum, sensor2ego_mat, intrin_mat, ida_mat, bda_mat, vo
     B, ncam = int(sensor2ego_mat.shape[0]), int(sensor2ego_mat.shape[1])
     D, H, W = [int(s) for s in frustum.shape[:3]]
     dev = frustum.device
-    ida_inv = ida_mat.reshape(B * ncam, 4, 4).float().inverse().contiguous()
-    cam2ego = sensor2ego_mat.float().matmul(torch.inverse(intrin_mat.float())).reshape(B * ncam, 4, 4).contiguous()
+    # linalg.inv_ex == inverse() without the host-side singularity check (a device -> host read per call)
+    ida_inv = torch.linalg.inv_ex(ida_mat.reshape(B * ncam, 4, 4).float())[0].contiguous()
+    cam2ego = sensor2ego_mat.float().matmul(torch.linalg.inv_ex(intrin_mat.float())[0]).reshape(B * ncam, 4, 4).contiguous()
     bda = bda_mat.reshape(B, 4, 4).float().contiguous() if bda_mat is not None else None
     fr = frustum.float().contiguous()
     key = (voxel_coord.data_ptr(), voxel_size.data_ptr(), voxel_coord._version, voxel_size._version)

@@ -388,6 +388,7 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self._channels_last = False
         self._dense_graph = None
         self._train_graph = None
+        self._camera_stream = None
 
     def use_cuda_graph_training(self, enable=True):
         """Training steps that hand in pre-assigned `targets` and `normalisers` run the dense 2-D part, its loss and its
@@ -411,13 +412,35 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         self._channels_last = bool(enable)
         return self
 
-    def extract_bev(self, lidar_points, cameras_imgs, metas, geometry=None):
+    def start_camera(self, cameras_imgs, metas):
+        """Gradient-free camera branch launched on a side stream; hand the result to forward(camera_future=...).  The
+        LiDAR encoders between here and there synchronise with the host several times (voxel and row counts); the GPU then
+        has the camera branch's dense kernels to run instead of idling, and its memory-bound stretches overlap them."""
+        dev = cameras_imgs.device
+        if self._camera_stream is None:
+            self._camera_stream = torch.cuda.Stream(device=dev)
+        side = self._camera_stream
+        side.wait_stream(torch.cuda.current_stream(dev))          # the inputs are ready on the current stream
+        with torch.cuda.stream(side), torch.no_grad():
+            out = self.camera_encoder(cameras_imgs, metas)
+            done = torch.cuda.Event()
+            done.record(side)
+        cameras_imgs.record_stream(side)
+        return out, done
+
+    def extract_bev(self, lidar_points, cameras_imgs, metas, geometry=None, camera_future=None):
         out = None
         if self.with_lidar_encoder:
             lidar_out = self.lidar_encoder(lidar_points, geometry=geometry)
             out = lidar_out
         if self.with_camera_encoder:
-            camera_out = self.camera_encoder(cameras_imgs, metas)
+            if camera_future is not None:
+                camera_out, done = camera_future
+                cur = torch.cuda.current_stream(camera_out.device)
+                cur.wait_event(done)
+                camera_out.record_stream(cur)
+            else:
+                camera_out = self.camera_encoder(cameras_imgs, metas)
             out = camera_out
         if self.with_fusion_encoder:
             out = self.fusion_encoder(lidar_out, camera_out)
@@ -429,8 +452,10 @@ class BEVFusionCenterHead(BaseMultiSensorFusion):
         pre-reduced `num_pos_reduced` / `num_hm_reduced` tensors into ret_dict (one fused all-reduce per step
         instead of the reference's per-loss scalar reduce_mean calls; unidistill_b200.step uses it).
         `geometry`: optional per-step dict through which LiDAR encoders fed the same clouds share voxels + rulebooks.
-        `targets`: optional pre-computed `assign_targets(gt_boxes)` dict (infs zeroed), shared by student and teacher."""
-        model_output = self.extract_bev(lidar_points, cameras_imgs, metas, geometry=geometry)
+        `targets`: optional pre-computed `assign_targets(gt_boxes)` dict (infs zeroed), shared by student and teacher.
+        `camera_future` (kwarg): result of `start_camera` on the same inputs."""
+        model_output = self.extract_bev(lidar_points, cameras_imgs, metas, geometry=geometry,
+                                        camera_future=kwargs.get("camera_future"))
         if self._channels_last:
             model_output = model_output.contiguous(memory_format=torch.channels_last)
         if (self._train_graph is not None and self.training and torch.is_grad_enabled() and targets is not None

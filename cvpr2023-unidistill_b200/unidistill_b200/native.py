@@ -144,13 +144,15 @@ def query_bytes(fn_name, *args):
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C ABI (never shared across streams)."""
+    """Grow-only scratch buffer per (device, slot, current stream) handed to the C ABI."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, nbytes, device, slot=0):
-        key = (str(device), slot)
+        dev = torch.device(device)
+        stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+        key = (str(device), slot, stream)          # one buffer per stream: work on a side stream never shares scratch
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

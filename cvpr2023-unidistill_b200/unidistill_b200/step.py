@@ -274,7 +274,7 @@ class DistillStep:
                  fold_teacher_bn=True, teacher_cuda_graph=True, weights=None, preset="camera_exp_distill_lidar",
                  grad_clip=0.1, lr_milestones=(10, 15), lr_gamma=0.1, teacher_mode="eval", overlap_allreduce=True,
                  bucket_bytes=16 << 20, fuse_teacher_epilogues=True,
-                 student_cuda_graph=True):
+                 student_cuda_graph=True, overlap_teacher_camera=False):
         cfg = PRESETS[preset]
         self.weights = tuple(float(w) for w in (weights if weights is not None else cfg["weights"]))
         self.clamp_min = float(clamp_min if clamp_min is not None else cfg["clamp_min"])
@@ -310,6 +310,7 @@ class DistillStep:
             teacher.use_cuda_graph(True)                       # dense trunk replayed from a CUDA graph
         self._teacher_buffers = [(b, b.detach().clone()) for b in teacher.buffers()]
         student.train()
+        self.overlap_teacher_camera = bool(overlap_teacher_camera)
         self._graphed_targets = None
         if student_cuda_graph and next(student.parameters()).is_cuda:
             student.use_cuda_graph_training(True)              # dense trunk + loss, forward AND backward, from CUDA graphs
@@ -363,12 +364,19 @@ class DistillStep:
             norm["n_valid"], norm["mask_sum"] = n_valid, mask_sum
 
         geometry = {}       # voxels + rulebooks of the step's clouds, shared by the two LiDAR encoders (if there are two)
+        cam_future = None
+        if (self.overlap_teacher_camera and imgs is not None and imgs.is_cuda and self.teacher.with_camera_encoder
+                and self.teacher.with_lidar_encoder):
+            # the frozen teacher's camera branch on a side stream under the LiDAR encoders (which stall on host reads).
+            # Off by default: measured on B200 at bs = 4 it changes nothing (59.16 ms per step either way) -- the bubbles it
+            # fills are paid back by the kernels it shares the SMs with.
+            cam_future = self.teacher.start_camera(imgs, metas)
         ret_dict, tb, feat_s, bev_s, resp_s, _ = self.student(points, imgs, metas, gt, normalisers=normalisers,
                                                               targets=targets, geometry=geometry,
                                                               persistent_targets=persistent)
         with torch.no_grad():
             feat_t, bev_t, resp_t = self.teacher(points, imgs, metas, gt, return_feature=True, targets=targets,
-                                                 geometry=geometry)
+                                                 geometry=geometry, camera_future=cam_future)
             self._restore_teacher()
         loss_feature = L.FeatureDistillLoss(feat_s, feat_t, corners, valid, weight=norm["n_valid"])
         loss_rel = L.BEVDistillLoss(bev_s, bev_t, corners, valid, weight=norm["n_valid"])

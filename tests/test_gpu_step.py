@@ -170,3 +170,29 @@ def test_graphed_student_trunk_matches_eager(cuda, native_lib):
             assert torch.allclose(bg[name].float(), b.float(), rtol=1e-4, atol=1e-5), name
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_camera_branch_on_a_side_stream_gives_the_same_teacher(cuda, native_lib):
+    """start_camera() runs the gradient-free camera branch on a side stream (its scratch buffers are per stream);
+    forward(camera_future=...) must see exactly what the in-line branch produces."""
+    from unidistill_b200 import models
+    from unidistill_b200.step import gt_with_labels
+
+    torch.manual_seed(0)
+    cfg = models.make_model_cfg(bev=128, lidar=True, camera=True, img_depth=18)
+    teacher = models.BEVFusionCenterHead(cfg).to(cuda).eval()
+    teacher.det_head.dense_head.distill = True
+    batch = _batch(cuda, bs=2)
+    gt = gt_with_labels(batch["gt_boxes"], batch["gt_labels"])
+    with torch.no_grad():
+        ref = teacher(batch["points"], batch["imgs"], batch["mats_dict"], gt, return_feature=True)
+        ref = [ref[0].clone(), ref[1].clone(), [{k: v.clone() for k, v in t.items()} for t in ref[2]]]
+        for _ in range(2):
+            fut = teacher.start_camera(batch["imgs"], batch["mats_dict"])
+            got = teacher(batch["points"], batch["imgs"], batch["mats_dict"], gt, return_feature=True, camera_future=fut)
+            torch.cuda.synchronize()
+            assert torch.allclose(got[0], ref[0], rtol=1e-5, atol=1e-6)
+            assert torch.allclose(got[1], ref[1], rtol=1e-4, atol=1e-5)
+            for tg, tr in zip(got[2], ref[2]):
+                for k in tr:
+                    assert torch.allclose(tg[k], tr[k], rtol=1e-4, atol=1e-5), k
