@@ -786,7 +786,7 @@ def _allreduce_report(step_fn, wl, world, device, args):
         torch.cuda.synchronize()
     rep["standalone_ms"] = round(_reduce(e0.elapsed_time(e1), world, device, "max"), 3)
     b.flat.zero_()
-    # exposed cost: K steps with the hooks disabled and no exchange at all (NOT a valid training step: timing probe only)
+    # exposed cost: K steps without the all-reduces themselves (NOT a valid training step at N > 1: timing probe only)
     # against K steps with it, timed like pass 1 (per-step events, L2 flushed between steps, collector off: a generational
     # collection on one rank stalls every rank through the exchange and would be booked as "exposed")
     import gc
@@ -810,12 +810,9 @@ def _allreduce_report(step_fn, wl, world, device, args):
 
     gc.collect()
     gc.disable()
-    b.enabled = False
-    orig_fire = b._fire
-    b._fire = lambda i: b._fired.__setitem__(i, True)
+    b.exchange = False
     no_xchg = k_steps(2)
-    b._fire = orig_fire
-    b.enabled = True
+    b.exchange = True
     with_xchg = k_steps(1)
     gc.enable()
     rep["step_ms_without_exchange"] = round(no_xchg, 3)

@@ -19,6 +19,8 @@ issued BEFORE the student forward (they depend on the ground truth only) instead
 `reduce_mean`s inside it, and the teacher's buffers are restored from a device-side snapshot instead of
 `load_state_dict` from host memory every step (:465).
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -44,9 +46,15 @@ class FlatGradBucket:
     REVERSE registration order -- the order backward produces them.  With `overlap`, a bucket's all-reduce is issued
     (asynchronously, on the process group's own stream) from a post-accumulate hook as soon as its last gradient has
     landed, so the exchange runs under the rest of the backward pass; `finish()` waits for the stragglers.  Works with
-    any backend (gloo in the CPU tests)."""
+    any backend (gloo in the CPU tests).
 
-    def __init__(self, params, bucket_bytes=16 << 20, overlap=True):
+    `steal` (default): during the backward `param.grad` is None, so autograd's AccumulateGrad keeps the incoming gradient
+    tensor instead of launching `grad += incoming` per parameter (~250 small kernels per step here); when a bucket is
+    complete its gradients are copied into the flat buffer with ONE `_foreach_copy_`, and `finish()` points every
+    `param.grad` at its view of the (reduced) buffer again for clipping and the optimizer."""
+
+    def __init__(self, params, bucket_bytes=16 << 20, overlap=True, steal=True):
+        self.steal = bool(steal)
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
@@ -55,24 +63,34 @@ class FlatGradBucket:
         self.overlap = overlap
         self.buckets = []            # (lo, hi) element ranges of self.flat, in expected completion order
         self._bucket_of = {}
+        self._view = {}              # id(param) -> its view of the flat buffer
+        self._members = []           # per bucket: its parameters
         self._pending = []
         self._works = []
         self._hooks = []
         self.enabled = True
+        self.exchange = True         # False: everything but the all-reduce itself (bench.py's exposed-cost probe)
         # lay the parameters out back to front so that bucket 0 (completed first) holds the LAST layers
         off = 0
         lo, cnt = 0, 0
         for p in reversed(self.params):
             # same strides as the parameter (NHWC-format conv weights stay NHWC): dense, so the segment is exact
-            p.grad = self.flat[off: off + p.numel()].as_strided(p.size(), p.stride())
+            view = self.flat[off: off + p.numel()].as_strided(p.size(), p.stride())
+            self._view[id(p)] = view
+            p.grad = None if self.steal else view
             off += p.numel()
             self._bucket_of[id(p)] = len(self.buckets)
+            if len(self._members) == len(self.buckets):
+                self._members.append([])
+            self._members[-1].append(p)
             cnt += 1
             if (off - lo) * 4 >= bucket_bytes:
                 self.buckets.append((lo, off, cnt))
                 lo, cnt = off, 0
         if off > lo or not self.buckets:
             self.buckets.append((lo, off, cnt))
+        while len(self._members) < len(self.buckets):
+            self._members.append([])
         if overlap:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -85,14 +103,31 @@ class FlatGradBucket:
 
     def zero(self):
         self.flat.zero_()
+        if self.steal:
+            for p in self.params:
+                p.grad = None
         self._reset()
+
+    def _collect(self, b):
+        """steal mode: the bucket's gradients (wherever autograd left them) -> their views of the flat buffer"""
+        dst, src = [], []
+        for p in self._members[b]:
+            g = p.grad
+            view = self._view[id(p)]
+            if g is not None and g.data_ptr() != view.data_ptr():
+                dst.append(view)
+                src.append(g)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def _fire(self, b):
         if self._fired[b]:
             return
         self._fired[b] = True
+        if self.steal:
+            self._collect(b)
         lo, hi, _ = self.buckets[b]
-        if torch_dist.get_world_size() > 1 and hi > lo:
+        if self.exchange and torch_dist.get_world_size() > 1 and hi > lo:
             self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def _on_grad(self, p):
@@ -111,6 +146,9 @@ class FlatGradBucket:
         for w in self._works:
             w.wait()
         self._works = []
+        if self.steal:
+            for p in self.params:
+                p.grad = self._view[id(p)]
         return self.flat
 
     def all_reduce_mean(self):
@@ -315,7 +353,8 @@ class DistillStep:
         if student_cuda_graph and next(student.parameters()).is_cuda:
             student.use_cuda_graph_training(True)              # dense trunk + loss, forward AND backward, from CUDA graphs
             self._graphed_targets = GraphedTargets(self)       # and the ground-truth-only preparation
-        self.bucket = FlatGradBucket(student.parameters(), bucket_bytes=bucket_bytes, overlap=overlap_allreduce)
+        self.bucket = FlatGradBucket(student.parameters(), bucket_bytes=bucket_bytes, overlap=overlap_allreduce,
+                                     steal=os.environ.get("UD_GRAD_STEAL", "1") != "0")
         self.opt = self.sched = None
         if optimizer:
             fused = self.bucket.flat.is_cuda

@@ -42,19 +42,31 @@ def _worker(rank, world, port, out_dir):
         # flat bucket: gradients of a tiny model, different data per rank -> identical averaged grads everywhere
         torch.manual_seed(0)
         net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
-        bucket = FlatGradBucket(net.parameters())
+        bucket = FlatGradBucket(net.parameters(), overlap=False)
         assert bucket.numel == sum(p.numel() for p in net.parameters())
         g = torch.Generator().manual_seed(100 + rank)
         x = torch.randn(7, 6, generator=g)
         bucket.zero()
+        assert all(p.grad is None for p in net.parameters())      # steal mode: autograd keeps its own gradient tensors
         net(x).square().sum().backward()
-        local = bucket.flat.clone()
-        for p in net.parameters():                       # backward accumulated INTO the flat views
-            assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+        # the flat buffer is laid out back to front
+        local = torch.cat([p.grad.reshape(-1) for p in reversed(list(net.parameters()))]).clone()
         bucket.all_reduce_mean()
+        lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + 4 * bucket.numel
+        for p in net.parameters():                       # finish() pointed every .grad at its view of the flat buffer
+            assert lo <= p.grad.data_ptr() < hi
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         assert torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-6)
+        # legacy mode: .grad ARE the views and backward accumulates into them
+        torch.manual_seed(0)
+        net_l = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        b_l = FlatGradBucket(net_l.parameters(), overlap=False, steal=False)
+        b_l.zero()
+        net_l(x).square().sum().backward()
+        assert torch.allclose(b_l.flat, local, atol=1e-7)
+        for p in net_l.parameters():
+            assert lo != p.grad.data_ptr() and b_l.flat.data_ptr() <= p.grad.data_ptr() < b_l.flat.data_ptr() + 4 * b_l.numel
 
         # overlapped path: 3 buckets (tiny bucket size), all-reduces fired from the gradient hooks during backward,
         # then average + global-norm clip in place == clip_grad_norm_ of the averaged gradients
