@@ -213,6 +213,16 @@ __device__ __forceinline__ void split_bf16_pair(float f0, float f1, uint32_t& hi
 // conversion, 4 TMEM slot wait, 5 TMEM stores + arrive | 8 MMA stages, 9 wait weights, 10 wait A, 11 issue + commit |
 // 12 CTAs, 13 CTA cycles from start to the end of the main loop (MMA warp), 14 epilogue cycles (warp 0) | 6 the MMA warp's
 // tcgen05.fence::after_thread_sync after its A wait
+#ifdef UD_DG_TRACE
+// event trace of ONE CTA (blockIdx.x == UD_DG_TRACE): [event][stage] = clock64().  Events: 0 set: indices landed, 1 set: rows
+// converted (ready to store), 2 set: TMEM slot free, 3 set: arrived | 4 MMA warp: A full, 5 MMA warp: stage issued + committed,
+// 6 MMA warp: weights full
+#define DG_TRACE_STAGES 128
+__device__ long long ud_dg_trace[8][DG_TRACE_STAGES];
+#define DG_TRACE(ev, st, cond) if (blockIdx.x == UD_DG_TRACE && (st) < DG_TRACE_STAGES && (cond)) ud_dg_trace[ev][st] = clock64();
+#else
+#define DG_TRACE(ev, st, cond)
+#endif
 #ifdef UD_DG_PROBE
 __device__ unsigned long long ud_dg_probe_acc[16];
 #define DG_PROBE_DECL(n) long long pr_[n] = {}; long long pt_ = clock64();
@@ -224,8 +234,33 @@ __device__ unsigned long long ud_dg_probe_acc[16];
 #define DG_PROBE_FLUSH(base, n, cond)
 #endif
 
+// A gather warp hands its part of an A stage to the MMA warp: ONE mbarrier arrive per warp.  (Every thread arriving on its
+// own -- 128 same-address arrivals per stage, 32 of them serialised inside each warp instruction -- delayed the phase flip
+// by ~150 cycles per stage, all of it on the MMA warp's critical path: profiles/r03_pipeline_probes.md.)  tcgen05.wait::st
+// is warp-collective, so after it every lane's TMEM stores are complete; the fence orders them before the arrive.
+__device__ __forceinline__ void dg_set_arrive(uint32_t bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+#if defined(UD_MBAR_SPIN_MMA)
+#define DG_MMA_WAIT mbar_wait_spin
+#else
+#define DG_MMA_WAIT mbar_wait
+#endif
 constexpr int DG_THREADS = 608;
 constexpr int DG_SETS = 4;
+// Per-CTA configuration of k_spconv_umma_dg, template parameter NSETS = gather sets = TMEM A slots:
+//   NSETS 4: one CTA per SM -- 512 TMEM columns (256 accumulators | 4 x 64 A ring), 16 gather warps + MMA + weights + indices warp
+//   NSETS 2: TWO CTAs per SM -- 256 TMEM columns each (128 accumulators | 2 x 64 A ring), 8 gather warps + MMA + one loader warp.
+// Why two: the event trace of a CTA (profiles/r03_pipeline_probes.md) shows the single MMA-issuing warp as the serial
+// bottleneck of the wide layers -- ~660-730 cycles of dependent instruction latency per stage (barrier tests, schedule reads,
+// R2UR moves, 12 UTCHMMA + commit) for 390 cycles of tensor work -- while gather sets and tensor pipe both have slack.  Two
+// resident CTAs give the SM two independent issuers, and one CTA's epilogue / prologue overlaps the other's main loop.
+__host__ __device__ constexpr int dg_threads(int nsets) { return nsets == 4 ? 608 : (4 * nsets + 2) * 32; }
+__host__ __device__ constexpr int dg_acc_cols(int nsets) { return 64 * nsets; }
+__host__ __device__ constexpr int dg_tiles_max(int nsets, int cout) { return dg_acc_cols(nsets) / cout < 8 ? dg_acc_cols(nsets) / cout : 8; }
+__host__ __device__ constexpr int dg_b_stages(int nsets, int cout) { return (nsets == 2 && cout >= 128) ? 2 : 4; }
 constexpr int DG_IDX_STAGES = 16;
 constexpr int DG_B_STAGES = 4;
 // statistics buffer: [0, 4096) final sums (2 * COUT doubles), then the workspace of det_reduce.cuh
@@ -244,10 +279,11 @@ struct DgPost {
 constexpr int DG_EP_PITCH = 36;                          // floats per staged row: 16-byte aligned, conflict-free LDS/STS.128
 constexpr int DG_EP_STAGE_FLOATS = 32 * DG_EP_PITCH;
 constexpr size_t DG_EP_STAGE_BYTES = (size_t)16 * DG_EP_STAGE_FLOATS * 4;
-__host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout) {
+__host__ __device__ constexpr size_t dg_ep_stage_bytes(int nsets) { return (size_t)4 * nsets * DG_EP_STAGE_FLOATS * 4; }
+__host__ __device__ constexpr size_t dg_smem_bytes(int cin, int cout, int nsets = 4) {
     // the epilogue's staging tiles alias the weight ring when that is large enough (it is idle by then), else follow the index ring
-    return (size_t)DG_B_STAGES * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 +
-           ((size_t)DG_B_STAGES * dg_b_bytes(cout) >= DG_EP_STAGE_BYTES ? 0 : DG_EP_STAGE_BYTES) + 1024;
+    return (size_t)dg_b_stages(nsets, cout) * dg_b_bytes(cout) + (size_t)DG_IDX_STAGES * ts_tapg(cin) * TILE_M * 4 +
+           ((size_t)dg_b_stages(nsets, cout) * dg_b_bytes(cout) >= dg_ep_stage_bytes(nsets) ? 0 : dg_ep_stage_bytes(nsets)) + 1024;
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const float* p) {
@@ -279,7 +315,7 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
 // bytes instead of 32 rows x 16 bytes (the role-cycle probe showed the epilogue at ~20 % of a CTA's life, bound by the 32
 // partial lines per store), and the per-column sums need 2 shuffle rounds instead of 5.
 
-template <int COUT, int NTHREADS>
+template <int COUT, int NTHREADS, int NSETS = 4>
 __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, int tiles, int rows_cta, int row0,
                                             const unsigned int* tile_mask_s, uint32_t tmem_acc,
                                             const float* __restrict__ bias, float* __restrict__ out,
@@ -287,8 +323,8 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
                                             int* stat_last_s, float* stage, const DgPost post = DgPost{nullptr, nullptr, nullptr, 0}) {
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    // ============ epilogue (warps 0-15: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+4, ...) ============
-    if (warp < 16) {
+    // ============ epilogue (warps 0 .. 4 NSETS - 1: warp w -> quadrant w&3, tiles (w>>2), (w>>2)+NSETS, ...) ============
+    if (warp < 4 * NSETS) {
         if (n_a > 0) {
             mbar_wait(bar_acc, 0u);
             tc_fence_after();
@@ -301,7 +337,7 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
         const int rsub = lane / LPR;
         const int c4 = (lane % LPR) * 4;
 #pragma unroll 1
-        for (int t = warp >> 2; t < tiles; t += DG_SETS) {
+        for (int t = warp >> 2; t < tiles; t += NSETS) {
             if (t * TILE_M >= rows_cta) break;
             const bool has_acc = tile_mask_s[t] != 0u;
             const int r_base = t * TILE_M + q * 32;       // first row (CTA-local) of this warp's 32
@@ -377,7 +413,7 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
         float v = 0.f;
         if (tid < 2 * COUT) {
 #pragma unroll
-            for (int w = 0; w < 16; ++w) v += wpart_s[(w * 2 + tid / COUT) * COUT + tid % COUT];
+            for (int w = 0; w < 4 * NSETS; ++w) v += wpart_s[(w * 2 + tid / COUT) * COUT + tid % COUT];
         }
         ud_det_reduce((double)v, tid, 2 * COUT, stats + DG_STAT_FINAL_BYTES, stat_group,
                       reinterpret_cast<double*>(stats), stat_last_s);
@@ -385,8 +421,8 @@ __device__ __forceinline__ void dg_epilogue(int tid, int n_a, uint32_t bar_acc, 
     }
 }
 
-template <int CIN, int COUT, bool SPLIT>
-__global__ void __launch_bounds__(DG_THREADS, 1)
+template <int CIN, int COUT, bool SPLIT, int NSETS>
+__global__ void __launch_bounds__(dg_threads(NSETS), NSETS == 4 ? 1 : 2)
 k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __restrict__ in,
                  const float* __restrict__ wpacked, const float* __restrict__ bias,
                  const int* __restrict__ nbr_t, const unsigned int* __restrict__ tile_masks, int n_out, int K,
@@ -396,14 +432,19 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     constexpr int NCHUNK = CIN * TAPG / KS;          // stages per (super-)tap
     constexpr int IDX_INTS = TAPG * TILE_M;
     constexpr int A_COLS = KS;                       // TMEM columns of one A stage: 32 hi | 32 lo (bf16 pairs)
-    constexpr int A_STAGES = (512 - TS_ACC_COLS) / A_COLS;
+    constexpr int A_STAGES = NSETS;                  // one gather set per TMEM A slot
+    constexpr int ACC_COLS = dg_acc_cols(NSETS);     // accumulators [0, ACC_COLS), A ring [ACC_COLS, 2 ACC_COLS)
+    constexpr int NTHREADS = dg_threads(NSETS);
+    constexpr int GW = 4 * NSETS;                    // gather (and epilogue) warps; warp GW issues the MMAs
+    constexpr int DG_B_STAGES = dg_b_stages(NSETS, COUT);
     constexpr int B_BYTES = dg_b_bytes(COUT);
     constexpr int BBF_BYTES = COUT * KS * 2;
     constexpr uint32_t IDESC_BF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                   ((uint32_t)(TILE_M >> 4) << 24);
-    static_assert(A_STAGES == DG_SETS, "one gather set per TMEM A slot");
+    static_assert(NSETS == 4 || NSETS == 2, "4 gather sets (one CTA per SM) or 2 (two CTAs per SM)");
+    static_assert(A_STAGES * A_COLS == ACC_COLS, "A ring and accumulators split the allocation in halves");
     static_assert((CIN * TAPG) % KS == 0 && COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "unsupported channel count");
-    static_assert(MAX_TAPS * NCHUNK * ts_tiles_max(COUT) <= MAX_SCHED, "schedule list too small");
+    static_assert(MAX_TAPS * NCHUNK * dg_tiles_max(NSETS, COUT) <= MAX_SCHED, "schedule list too small");
     constexpr int NBAR = 2 * A_STAGES + 2 * DG_B_STAGES + 2 * DG_IDX_STAGES + 1;
 
     extern __shared__ unsigned char smem_raw[];
@@ -414,7 +455,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     __shared__ unsigned short b_sched[MAX_TAPS * 4];
     __shared__ unsigned short b_count[MAX_TAPS * 4];
     __shared__ int n_a_s, n_b_s;
-    __shared__ float wpart_s[16 * 2 * COUT];               // fused BatchNorm statistics: per epilogue warp, sum | sum of squares
+    __shared__ float wpart_s[GW * 2 * COUT];               // fused BatchNorm statistics: per epilogue warp, sum | sum of squares
     __shared__ int stat_last_s;
 
     const int tid = threadIdx.x;
@@ -424,7 +465,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
     const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
     if (stats != nullptr)
-        for (int i = tid; i < 16 * 2 * COUT; i += DG_THREADS) wpart_s[i] = 0.f;
+        for (int i = tid; i < GW * 2 * COUT; i += NTHREADS) wpart_s[i] = 0.f;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -441,7 +482,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 
     if (tid == 0) {
         for (int s = 0; s < A_STAGES; ++s) {
-            mbar_init(bar_a_full + 8 * s, TS_GROUP);         // every thread of the owning gather set
+            mbar_init(bar_a_full + 8 * s, TS_GROUP / 32);    // lane 0 of each warp of the owning gather set (see dg_set_arrive)
             mbar_init(bar_a_empty + 8 * s, 1);
         }
         for (int s = 0; s < DG_B_STAGES; ++s) {
@@ -467,7 +508,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
         }
         tile_mask_s[tid] = m;
     }
-    if (warp == 16) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (warp == GW) tmem_alloc(smem_u32(&tmem_base_s), 2 * ACC_COLS);
     __syncthreads();
     if (warp == 0) build_schedule<NCHUNK>(tile_mask_s, tiles, K_eff, lane, a_sched, b_sched, b_count, &n_a_s, &n_b_s);
     tc_fence_before();
@@ -476,16 +517,16 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     const int n_a = n_a_s;
     const int n_b = n_b_s;
     const uint32_t tmem_acc = tmem_base_s;
-    const uint32_t tmem_a = tmem_acc + TS_ACC_COLS;
+    const uint32_t tmem_a = tmem_acc + ACC_COLS;
 
-    if (warp < 16) {
+    if (warp < GW) {
         // ============ gather sets: global -> registers (st.16x256b fragment layout) -> bf16 hi/lo -> TMEM ============
         const int set = warp >> 2;
         const int q = warp & 3;
         const int rsub = lane >> 2;                      // row within an 8-row group
         const int csub = (lane & 3) * 4;                 // first of this thread's 4 channels within a 16-channel unit
         DG_PROBE_DECL(6)
-        for (int it = set; it < n_a; it += DG_SETS) {
+        for (int it = set; it < n_a; it += NSETS) {
             const int islot = it % DG_IDX_STAGES;
 #ifdef UD_DG_PROBE
             pr_[0] += 1;
@@ -493,6 +534,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 #endif
             mbar_wait(bar_idx_full + 8 * islot, ((uint32_t)(it / DG_IDX_STAGES)) & 1u);
             DG_PROBE_LAP(1)
+            DG_TRACE(0, it, q == 0 && lane == 0)
             // rows 32 q + 16 h + rsub + 8 rr of the tile, for every tap of the stage
             int idx[2][2][TAPG];
 #pragma unroll
@@ -521,7 +563,11 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                             const int r = idx[h][rr][g];
                             x[h][rr][2 * j2] = make_uint4(0u, 0u, 0u, 0u);
                             x[h][rr][2 * j2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+#if !defined(UD_DG_EXP) || (UD_DG_EXP != 1 && UD_DG_EXP != 3 && UD_DG_EXP != 4)
                             if (r >= 0) ldg_stream256(in + (size_t)r * CIN + ch, x[h][rr][2 * j2], x[h][rr][2 * j2 + 1]);
+#else
+                            if (r == -12345) ldg_stream256(in + (size_t)r * CIN + ch, x[h][rr][2 * j2], x[h][rr][2 * j2 + 1]);
+#endif
                         }
             } else {
 #pragma unroll
@@ -533,7 +579,11 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                             // TAPG 4 (CIN 16): unit j = tap j, 64-byte rows: 16-byte loads, natural K order
                             const int r = idx[h][rr][j];
                             x[h][rr][j] = make_uint4(0u, 0u, 0u, 0u);
+#if !defined(UD_DG_EXP) || (UD_DG_EXP != 1 && UD_DG_EXP != 3 && UD_DG_EXP != 4)
                             if (r >= 0) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + csub);
+#else
+                            if (r == -12345) x[h][rr][j] = ldg_stream(in + (size_t)r * CIN + csub);
+#endif
                         }
             }
             const int aslot = it % A_STAGES;             // == set
@@ -569,23 +619,31 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
             }
 #endif
             DG_PROBE_LAP(3)
+            DG_TRACE(1, it, q == 0 && lane == 0)
             // the conversions do not need the TMEM slot: only the stores wait for the MMAs that read it last
             mbar_wait(bar_a_empty + 8 * aslot, (((uint32_t)(it / A_STAGES)) & 1u) ^ 1u);
             tc_fence_after();
             DG_PROBE_LAP(4)
+            DG_TRACE(2, it, q == 0 && lane == 0)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t taddr = tmem_a + (uint32_t)(aslot * A_COLS) + ((uint32_t)(q * 32 + h * 16) << 16);
+#if defined(UD_DG_EXP) && (UD_DG_EXP == 3 || UD_DG_EXP == 4)
+                if (hi[h][0] == 0x12345u) {
+#endif
                 tmem_st_16x256b_x4(taddr, hi[h]);
                 tmem_st_16x256b_x4(taddr + KS / 2, lo[h]);
+#if defined(UD_DG_EXP) && (UD_DG_EXP == 3 || UD_DG_EXP == 4)
+                }
+#endif
             }
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(bar_a_full + 8 * aslot);
+            dg_set_arrive(bar_a_full + 8 * aslot, lane);
             DG_PROBE_LAP(5)
+            DG_TRACE(3, it, q == 0 && lane == 0)
         }
         DG_PROBE_FLUSH(0, 6, q == 0 && lane == 0)
-    } else if (warp == 16) {
+    } else if (warp == GW) {
         // ============ MMA issuer ============
         unsigned int started = 0u;
         int it = 0;
@@ -595,8 +653,9 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 #endif
         for (int ib = 0; ib < n_b; ++ib) {
             const int bslot = ib % DG_B_STAGES;
-            mbar_wait(bar_b_full + 8 * bslot, ((uint32_t)(ib / DG_B_STAGES)) & 1u);
+            DG_MMA_WAIT(bar_b_full + 8 * bslot, ((uint32_t)(ib / DG_B_STAGES)) & 1u);
             DG_PROBE_LAP(1)
+            DG_TRACE(6, it, lane == 0)
             const uint32_t b_base = smem_b + bslot * B_BYTES;
             const uint64_t db_hi = umma_desc_sw128(b_base);
             const uint64_t db_lo = umma_desc_sw128(b_base + BBF_BYTES);
@@ -604,8 +663,9 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
             for (int c = 0; c < cnt; ++c, ++it) {
                 const int aslot = it % A_STAGES;
                 const int tile = a_sched[it] >> 8;
-                mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+                DG_MMA_WAIT(bar_a_full + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
                 DG_PROBE_LAP(2)
+                DG_TRACE(4, it, lane == 0)
                 tc_fence_after();
                 DG_PROBE_LAP(4)
                 if (elect_one_sync()) {
@@ -617,9 +677,14 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                         const uint32_t a_hi = a_stage + (uint32_t)(k16 * 8);
                         const uint32_t a_lo = a_hi + KS / 2;
                         const uint64_t adv = (uint64_t)(k16 * 2);
+#if defined(UD_DG_EXP) && UD_DG_EXP == 2
+                        if (n_out == -7)
+#endif
+                        {
                         umma_bf16_ts(d, a_lo, db_hi + adv, IDESC_BF, (first || k16 > 0) ? 1u : 0u);
                         umma_bf16_ts(d, a_hi, db_lo + adv, IDESC_BF, 1u);
                         umma_bf16_ts(d, a_hi, db_hi + adv, IDESC_BF, 1u);
+                        }
                     }
                     umma_commit(bar_a_empty + 8 * aslot);
                 }
@@ -629,6 +694,12 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                 pr_[0] += 1;
 #endif
                 DG_PROBE_LAP(3)
+                DG_TRACE(5, it, lane == 0)
+#if defined(UD_DG_EXP) && UD_DG_EXP == 4
+                // serialised: wait for this stage's own MMAs (slot 5 = cycles from the end of the issue to their completion)
+                mbar_wait(bar_a_empty + 8 * aslot, ((uint32_t)(it / A_STAGES)) & 1u);
+                DG_PROBE_LAP(5)
+#endif
             }
             if (elect_one_sync()) umma_commit(bar_b_empty + 8 * bslot);
             __syncwarp();
@@ -638,14 +709,18 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 #ifdef UD_DG_PROBE
         if (lane == 0) {
             atomicAdd(&ud_dg_probe_acc[6], (unsigned long long)pr_[4]);      // tcgen05.fence::after_thread_sync after the A wait
+            atomicAdd(&ud_dg_probe_acc[15], (unsigned long long)pr_[5]);     // UD_DG_EXP 4: end of issue -> completion of the stage's MMAs
             atomicAdd(&ud_dg_probe_acc[12], 1ull);
             atomicAdd(&ud_dg_probe_acc[13], (unsigned long long)(clock64() - cta_t0));
         }
 #endif
         DG_PROBE_FLUSH(8, 4, lane == 0)
     } else {
-        // ============ warp 17: weight slices, warp 18: per-stage row-index segments (bulk async copies) ============
-        if (warp == 17 && lane == 0) {
+        // ============ weight slices and per-stage row-index segments (bulk async copies): lane 0 of warps GW + 1 and GW + 2
+        // (NSETS 4), lanes 0 and 1 of warp GW + 1 (NSETS 2: one warp less so that two CTAs fit the register file) ============
+        const bool w_role = warp == GW + 1 && lane == 0;
+        const bool i_role = NSETS == 4 ? (warp == GW + 2 && lane == 0) : (warp == GW + 1 && lane == 1);
+        if (w_role) {
             for (int ib = 0; ib < n_b; ++ib) {
                 const int bslot = ib % DG_B_STAGES;
                 mbar_wait(bar_b_empty + 8 * bslot, (((uint32_t)(ib / DG_B_STAGES)) & 1u) ^ 1u);
@@ -655,7 +730,7 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
                 mbar_arrive_expect_tx(bar_b_full + 8 * bslot, B_BYTES);
                 bulk_g2s(smem_b + bslot * B_BYTES, src, B_BYTES, bar_b_full + 8 * bslot);
             }
-        } else if (warp == 18 && lane == 0) {
+        } else if (i_role) {
             // row-index segments of every stage: ONE TMA tensor load per stage -- a [TAPG taps x 128 rows] box of the tap-major
             // table (2-D tensor map over nbr_t: K4 x ld int32), landing as TAPG consecutive 512-byte segments
             tma_prefetch_desc(&idx_map);
@@ -674,15 +749,15 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
 #ifdef UD_DG_PROBE
     const long long ep_t0 = clock64();
 #endif
-    dg_epilogue<COUT, DG_THREADS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
-                                         stat_group, &stat_last_s,
-                                  reinterpret_cast<float*>(smem_al + ((size_t)DG_B_STAGES * B_BYTES >= DG_EP_STAGE_BYTES
-                                                                          ? 0 : DG_B_STAGES * B_BYTES + DG_IDX_STAGES * IDX_INTS * 4)),
-                                  post);
+    dg_epilogue<COUT, NTHREADS, NSETS>(tid, n_a, bar_acc, tiles, rows_cta, row0, tile_mask_s, tmem_acc, bias, out, stats, wpart_s,
+                                       stat_group, &stat_last_s,
+                                       reinterpret_cast<float*>(smem_al + ((size_t)DG_B_STAGES * B_BYTES >= dg_ep_stage_bytes(NSETS)
+                                                                               ? 0 : DG_B_STAGES * B_BYTES + DG_IDX_STAGES * IDX_INTS * 4)),
+                                       post);
 #ifdef UD_DG_PROBE
     if (tid == 0) atomicAdd(&ud_dg_probe_acc[14], (unsigned long long)(clock64() - ep_t0));
 #endif
-    if (warp == 16) tmem_dealloc(tmem_acc, 512);
+    if (warp == GW) tmem_dealloc(tmem_acc, 2 * ACC_COLS);
 }
 
 // =====================================================================================================================
@@ -808,7 +883,7 @@ k_spconv_umma_win(const __grid_constant__ CUtensorMap idx_map, const __grid_cons
 
     if (tid == 0) {
         for (int s = 0; s < A_STAGES; ++s) {
-            mbar_init(bar_a_full + 8 * s, TS_GROUP);
+            mbar_init(bar_a_full + 8 * s, TS_GROUP / 32);
             mbar_init(bar_a_empty + 8 * s, 1);
         }
         for (int s = 0; s < WIN_B_RING; ++s) {
@@ -913,8 +988,7 @@ k_spconv_umma_win(const __grid_constant__ CUtensorMap idx_map, const __grid_cons
                 tmem_st_16x256b_x4(taddr + KS / 2, lo_);
             }
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(bar_a_full + 8 * aslot);
+            dg_set_arrive(bar_a_full + 8 * aslot, lane);
         }
     } else if (warp == 16) {
         // ============ MMA issuer ============
@@ -1016,33 +1090,55 @@ k_window_lo(const int* __restrict__ nbr_t, int ld, int* __restrict__ win_lo) {
     if (lane == 0) win_lo[(size_t)tile * WIN_GROUPS + g] = m;
 }
 
-// tiles per CTA and grid size for n_out rows (one wave-balanced choice shared by the launcher and the size queries)
-void dg_grid(int n_out, int cout, int* tiles_out, int* ctas_out) {
+// tiles per CTA and grid size for n_out rows (one wave-balanced choice shared by the launcher and the size queries);
+// nsets 4: one CTA per SM with up to 256 / cout tiles, nsets 2: two CTAs per SM with up to 128 / cout tiles each
+void dg_grid(int n_out, int cout, int* tiles_out, int* ctas_out, int nsets = 4) {
     const int n_tiles = (n_out + TILE_M - 1) / TILE_M;
-    const int tmax = ts_tiles_max(cout);
-    const int waves = (n_tiles + UD_NUM_SMS * tmax - 1) / (UD_NUM_SMS * tmax);
-    int tiles = (n_tiles + UD_NUM_SMS * waves - 1) / (UD_NUM_SMS * (waves > 0 ? waves : 1));
+    const int tmax = dg_tiles_max(nsets, cout);
+    const int slots = UD_NUM_SMS * (nsets == 4 ? 1 : 2);
+    const int waves = (n_tiles + slots * tmax - 1) / (slots * tmax);
+    int tiles = (n_tiles + slots * waves - 1) / (slots * (waves > 0 ? waves : 1));
     if (tiles < 1) tiles = 1;
     if (tiles > tmax) tiles = tmax;
     *tiles_out = tiles;
     *ctas_out = (n_tiles + tiles - 1) / tiles;
 }
 
-size_t dg_stat_bytes(int n_out, int cout) {
-    int tiles, ctas;
-    dg_grid(n_out, cout, &tiles, &ctas);
-    return (size_t)DG_STAT_FINAL_BYTES + ud_det_reduce_bytes(ctas, 2 * cout);
+// Gather sets per CTA for a layer shape: 2 (two CTAs per SM) where it measured faster on B200 (profiles/r03_pipeline_probes.md).
+// UD_DG_NSETS=2|4 overrides the table (diagnostic).
+int dg_nsets(int cin, int cout) {
+    static const int forced = [] {
+        const char* e = getenv("UD_DG_NSETS");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 2 || forced == 4) return forced;
+    (void)cin;
+    (void)cout;
+    return 2;       // B200, bs-4 distillation step: 64->64 0.527 -> 0.432 ms, 128->128 0.405 -> 0.369, 32->32 0.301 -> 0.253, 16->16 0.100 -> 0.088
 }
 
-template <int CIN, int COUT, bool SPLIT>
-int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
-                   const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
-                   cudaStream_t stream, const DgPost post = DgPost{nullptr, nullptr, nullptr, 0}) {
-    const size_t smem = dg_smem_bytes(CIN, COUT);
-    auto kern = k_spconv_umma_dg<CIN, COUT, SPLIT>;
+size_t dg_stat_bytes(int n_out, int cout) {           // the larger of the two configurations (the query does not know cin)
+    size_t best = 0;
+    for (int nsets = 2; nsets <= 4; nsets += 2) {
+        int tiles, ctas;
+        dg_grid(n_out, cout, &tiles, &ctas, nsets);
+        const size_t b = (size_t)DG_STAT_FINAL_BYTES + ud_det_reduce_bytes(ctas, 2 * cout);
+        best = b > best ? b : best;
+    }
+    return best;
+}
+
+template <int CIN, int COUT, bool SPLIT, int NSETS>
+int launch_umma_dg_n(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                     const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
+                     cudaStream_t stream, const DgPost post) {
+    const size_t smem = dg_smem_bytes(CIN, COUT, NSETS);
+    auto kern = k_spconv_umma_dg<CIN, COUT, SPLIT, NSETS>;
     UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NSETS == 2)         // two CTAs per SM need the large shared-memory carve-out
+        UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int tiles, ctas;
-    dg_grid(n_out, COUT, &tiles, &ctas);
+    dg_grid(n_out, COUT, &tiles, &ctas, NSETS);
     if (stats != nullptr)       // arrival counters of the statistics reduction
         UD_CUDA_TRY(cudaMemsetAsync(stats + DG_STAT_FINAL_BYTES, 0, UD_DET_COUNTER_BYTES, stream));
     CUtensorMap idx_map;        // tap-major table as a 2-D tensor: (K rounded up to 4) rows x (n_out rounded up to 128) int32
@@ -1050,10 +1146,19 @@ int launch_umma_dg(const float* in, const float* wpacked, const float* bias, con
     int rc = ud_make_tmap_2d_b32(&idx_map, nbr_t, CU_TENSOR_MAP_DATA_TYPE_INT32, (uint64_t)((K + 3) / 4 * 4), ld, ld * 4,
                                  (uint32_t)ts_tapg(CIN), TILE_M);
     if (rc != UD_OK) return rc;
-    kern<<<ctas, DG_THREADS, smem, stream>>>(idx_map, in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
-                                             ud_det_group(ctas), post);
+    kern<<<ctas, dg_threads(NSETS), smem, stream>>>(idx_map, in, wpacked, bias, nbr_t, tile_masks, n_out, K, tiles, out, stats,
+                                                    ud_det_group(ctas), post);
     UD_LAUNCH_CHECK();
     return UD_OK;
+}
+
+template <int CIN, int COUT, bool SPLIT>
+int launch_umma_dg(const float* in, const float* wpacked, const float* bias, const int* nbr_t,
+                   const unsigned int* tile_masks, int n_out, int K, float* out, unsigned char* stats,
+                   cudaStream_t stream, const DgPost post = DgPost{nullptr, nullptr, nullptr, 0}) {
+    if (dg_nsets(CIN, COUT) == 2)
+        return launch_umma_dg_n<CIN, COUT, SPLIT, 2>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream, post);
+    return launch_umma_dg_n<CIN, COUT, SPLIT, 4>(in, wpacked, bias, nbr_t, tile_masks, n_out, K, out, stats, stream, post);
 }
 
 template <int COUT>
@@ -1258,6 +1363,12 @@ int ud_sparse_conv_tc_forward_affine(const float* in, const void* wpacked_, cons
 
 }  // extern "C"
 
+#ifdef UD_DG_TRACE
+extern "C" int ud_debug_dg_trace(long long* host_out) {
+    UD_CUDA_TRY(cudaMemcpyFromSymbol(host_out, ud_dg_trace, sizeof(long long) * 8 * DG_TRACE_STAGES));
+    return UD_OK;
+}
+#endif
 #ifdef UD_DG_PROBE
 extern "C" int ud_debug_dg_probe(unsigned long long* host_out16, int reset) {
     if (host_out16 != nullptr) UD_CUDA_TRY(cudaMemcpyFromSymbol(host_out16, ud_dg_probe_acc, sizeof(unsigned long long) * 16));

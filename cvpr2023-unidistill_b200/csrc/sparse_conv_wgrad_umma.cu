@@ -120,11 +120,11 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
 
     if (tid == 0) {
         for (int s = 0; s < WG_A_STAGES; ++s) {
-            mbar_init(bar_a_full + 8 * s, WG_GROUP_THREADS);
+            mbar_init(bar_a_full + 8 * s, WG_GROUP_THREADS / 32);   // lane 0 of each producer warp
             mbar_init(bar_a_empty + 8 * s, 1);
         }
         for (int s = 0; s < WG_G_STAGES; ++s) {
-            mbar_init(bar_g_full + 8 * s, WG_GROUP_THREADS);
+            mbar_init(bar_g_full + 8 * s, WG_GROUP_THREADS / 32);
             mbar_init(bar_g_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -188,7 +188,8 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                     for (int j = 0; j < G_NJ; ++j)
                         *reinterpret_cast<uint4*>(base + swz32_off(rb + G_STEP * j, c16)) = rna_tf32(v[j]);
                     fence_proxy_async();
-                    mbar_arrive(bar_g_full + 8 * slot);
+                    __syncwarp();                     // one arrive per warp (32 same-address arrivals serialise)
+                    if (lane == 0) mbar_arrive(bar_g_full + 8 * slot);
                 }
                 ++ig;
                 for (unsigned int rem = m; rem; rem &= rem - 1u) {
@@ -219,7 +220,8 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                         for (int j = 0; j < 16; ++j)
                             *reinterpret_cast<uint4*>(base + swz32_off(rb + 4 * j, c16)) = rna_tf32(v[j]);
                         fence_proxy_async();
-                        mbar_arrive(bar_a_full + 8 * slot);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_a_full + 8 * slot);
                     }
                     ++ia;
                 }
