@@ -33,19 +33,21 @@ using namespace ud_umma;
 
 constexpr int WG_TILE = 128;                 // rows per tile of the tap-major table / per tile-mask word
 constexpr int WG_RS = 64;                    // rows per pipeline stage
-constexpr int WG_GROUPS = 4;                 // producer groups
+// Template parameter NG = producer groups = gathered-stage ring slots of a CTA:
+//   NG 4: one CTA per SM, 512 TMEM columns of accumulators (the round-1 form);
+//   NG 2: TWO CTAs per SM with 256 TMEM columns each -- as in k_spconv_umma_dg (profiles/r03_pipeline_probes.md) the single
+//         MMA-issuing warp is a serial chain of long-latency instructions per stage, and two resident CTAs give the SM two
+//         of them.  Costs: half the accumulator slots per CTA, so twice as many super-tap groups re-read dout.
 constexpr int WG_GROUP_THREADS = 128;
-constexpr int WG_MMA_WARP = WG_GROUPS * WG_GROUP_THREADS / 32;
-constexpr int WG_THREADS = WG_GROUPS * WG_GROUP_THREADS + 32;
-constexpr int WG_A_STAGES = 4;
 constexpr int WG_G_STAGES = 2;
-static_assert(WG_A_STAGES == WG_GROUPS && WG_G_STAGES <= WG_GROUPS, "one producer group per ring slot");
 constexpr int WG_ATOM_BYTES = WG_RS * 128;   // one [64 rows x 32 fp32] swizzled sub-tile
 constexpr int WG_A_BYTES = 4 * WG_ATOM_BYTES;   // 64 rows x 128 columns
 constexpr int WG_MAX_TAPS = 32;
+__host__ __device__ constexpr int wg_threads(int ng) { return ng * WG_GROUP_THREADS + 32; }
+__host__ __device__ constexpr int wg_tmem_cols(int ng) { return ng == 4 ? 512 : 256; }
 
-__host__ __device__ constexpr size_t wg_smem_bytes(int cout) {
-    return (size_t)WG_A_STAGES * WG_A_BYTES + (size_t)WG_G_STAGES * WG_RS * cout * 4 + 1024;
+__host__ __device__ constexpr size_t wg_smem_bytes(int cout, int ng = 4) {
+    return (size_t)ng * WG_A_BYTES + (size_t)WG_G_STAGES * WG_RS * cout * 4 + 1024;
 }
 
 // MN-major TF32 operand.  The only swizzled layout tcgen05 accepts for 32-bit MN-major data is SWIZZLE_128B_BASE32B
@@ -75,8 +77,8 @@ __device__ __forceinline__ uint4 rna_tf32(uint4 v) {
     return make_uint4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
 }
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+template <int CIN, int COUT, int NG>
+__global__ void __launch_bounds__(wg_threads(NG), NG == 4 ? 1 : 2)
 k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout, const int* __restrict__ nbr_t,
                     const unsigned int* __restrict__ tile_masks, int n_rows, int K, int tiles_per_cta, int st_per_cta,
                     float* __restrict__ dw) {
@@ -89,6 +91,12 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
     // kind::tf32, fp32 accumulate, A and B MN-major, N = COUT, M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int WG_GROUPS = NG;                     // producer groups, one per gathered-stage ring slot
+    constexpr int WG_A_STAGES = NG;
+    constexpr int WG_MMA_WARP = NG * WG_GROUP_THREADS / 32;
+    constexpr int WG_THREADS = wg_threads(NG);
+    constexpr int TMEM_COLS = wg_tmem_cols(NG);
+    static_assert((NG == 4 || NG == 2) && WG_G_STAGES <= WG_GROUPS, "one producer group per ring slot");
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "CIN must divide 128 in whole 16-byte chunks");
     static_assert(COUT == 16 || COUT == 32 || COUT == 64 || COUT == 128, "unsupported COUT");
 
@@ -131,7 +139,7 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
         fence_barrier_init();
         chunk_mask_s = 0u;
     }
-    if (warp == WG_MMA_WARP) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (warp == WG_MMA_WARP) tmem_alloc(smem_u32(&tmem_base_s), TMEM_COLS);
     __syncthreads();
 
     // bit s <- super-tap st0 + s has at least one of its taps in the 128-row tile whose tap mask is m
@@ -246,13 +254,15 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                     mbar_wait(bar_a_full + 8 * aslot, ((uint32_t)(ia / WG_A_STAGES)) & 1u);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const uint32_t a0 = smem_base + aslot * WG_A_BYTES;
+                        // one descriptor per operand and stage; 8 rows further = +1024 B = +64 in the 16-byte address field
+                        // (a stage never crosses the 256 KB the field spans)
+                        const uint64_t da = umma_desc_mn_sw128_32b(smem_base + aslot * WG_A_BYTES);
+                        const uint64_t dg = umma_desc_mn_sw128_32b(g0);
                         const uint32_t d = tmem_acc + (uint32_t)(s * NCOL);
                         const uint32_t first = (started >> s) & 1u;
 #pragma unroll
                         for (int ks = 0; ks < WG_RS / 8; ++ks)      // 8 rows per MMA = two 512-byte swizzle groups
-                            umma_tf32(d, umma_desc_mn_sw128_32b(a0 + ks * 1024), umma_desc_mn_sw128_32b(g0 + ks * 1024), IDESC,
-                                      (first || ks > 0) ? 1u : 0u);
+                            umma_tf32(d, da + (uint64_t)(ks * 64), dg + (uint64_t)(ks * 64), IDESC, (first || ks > 0) ? 1u : 0u);
                         umma_commit(bar_a_empty + 8 * aslot);
                     }
                     started |= 1u << s;
@@ -295,30 +305,58 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == WG_MMA_WARP) tmem_dealloc(tmem_acc, 512);
+    if (warp == WG_MMA_WARP) tmem_dealloc(tmem_acc, TMEM_COLS);
+}
+
+template <int CIN, int COUT, int NG>
+int launch_wgrad_umma_n(const float* in, const float* dout, const int* nbr_t, const unsigned int* tile_masks, int n_rows,
+                        int K, float* dw, cudaStream_t stream) {
+    constexpr int TAPG = 128 / CIN;
+    const int k_eff = (K + TAPG - 1) / TAPG;
+    const int st_max = wg_tmem_cols(NG) / (COUT < 32 ? 32 : COUT);     // accumulator slots TMEM holds
+    const int ngroups = (k_eff + st_max - 1) / st_max;
+    const int st_per_cta = (k_eff + ngroups - 1) / ngroups;
+    const int n_tiles = (n_rows + WG_TILE - 1) / WG_TILE;
+    int chunks = UD_NUM_SMS * (NG == 4 ? 1 : 2) / ngroups;             // about one CTA per SM (NG 4) / two (NG 2)
+    if (chunks < 1) chunks = 1;
+    if (chunks > n_tiles) chunks = n_tiles;
+    const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
+    chunks = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    const size_t smem = wg_smem_bytes(COUT < 32 ? 32 : COUT, NG);
+    auto kern = k_spconv_wgrad_umma<CIN, COUT, NG>;
+    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NG == 2)
+        UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    dim3 grid(chunks, (k_eff + st_per_cta - 1) / st_per_cta);
+    kern<<<grid, wg_threads(NG), smem, stream>>>(in, dout, nbr_t, tile_masks, n_rows, K, tiles_per_cta, st_per_cta, dw);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// Producer groups per CTA for a layer shape (UD_WG_NG=2|4 overrides, diagnostic).  NG 2 needs two CTAs' shared memory on
+// one SM: 2 x (2 x 32 KB gathered stages + 2 dout stages), i.e. COUT <= 64.
+int wg_ng(int cin, int cout) {
+    static const int forced = [] {
+        const char* e = getenv("UD_WG_NG");
+        return e ? atoi(e) : 0;
+    }();
+    (void)cin;
+    if (cout > 64) return 4;
+    if (forced == 2 || forced == 4) return forced;
+    // measured on B200 (bs-4 distillation step): NG 2 is slower where it matters (64 -> 64: 0.671 -> 0.810 ms: twice the
+    // super-tap groups re-read dout and split 14 super-taps 4/4/4/2) and within 2 % elsewhere -- unlike the forward kernel,
+    // this one is not bound by its issuing warp.  Kept as an option.
+    return 4;
 }
 
 template <int CIN, int COUT>
 int launch_wgrad_umma(const float* in, const float* dout, const int* nbr_t, const unsigned int* tile_masks, int n_rows,
                       int K, float* dw, cudaStream_t stream) {
-    constexpr int TAPG = 128 / CIN;
-    const int k_eff = (K + TAPG - 1) / TAPG;
-    const int st_max = 512 / (COUT < 32 ? 32 : COUT);            // accumulator slots TMEM holds
-    const int ngroups = (k_eff + st_max - 1) / st_max;
-    const int st_per_cta = (k_eff + ngroups - 1) / ngroups;
-    const int n_tiles = (n_rows + WG_TILE - 1) / WG_TILE;
-    int chunks = UD_NUM_SMS / ngroups;                           // about one CTA per SM
-    if (chunks < 1) chunks = 1;
-    if (chunks > n_tiles) chunks = n_tiles;
-    const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
-    chunks = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    const size_t smem = wg_smem_bytes(COUT < 32 ? 32 : COUT);
-    auto kern = k_spconv_wgrad_umma<CIN, COUT>;
-    UD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(chunks, (k_eff + st_per_cta - 1) / st_per_cta);
-    kern<<<grid, WG_THREADS, smem, stream>>>(in, dout, nbr_t, tile_masks, n_rows, K, tiles_per_cta, st_per_cta, dw);
-    UD_LAUNCH_CHECK();
-    return UD_OK;
+    if constexpr (COUT <= 64) {
+        if (wg_ng(CIN, COUT) == 2)
+            return launch_wgrad_umma_n<CIN, COUT, 2>(in, dout, nbr_t, tile_masks, n_rows, K, dw, stream);
+    }
+    return launch_wgrad_umma_n<CIN, COUT, 4>(in, dout, nbr_t, tile_masks, n_rows, K, dw, stream);
 }
 
 bool wgrad_shape_ok(int K, int cin, int cout) {
