@@ -161,6 +161,92 @@ k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
     }
 }
 
+// float4 forms of the two passes (C % 4 == 0, 16-byte aligned tensors).  A thread owns 4 fixed channels (its per-channel
+// constants live in registers) and walks rows with a stride that is a multiple of C/4 vectors.
+//   reduce: block = 256 threads = (256 / (C/4)) rows x C/4 vectors; per-thread fp32 partials over its rows, then the rows of
+//           the block are folded in index order (fixed order => bit-reproducible, like the scalar form).
+//   apply:  walks the tensors FROM THE END: the reduce pass has just streamed dy / y / x front to back, so their tails are
+//           what the 126 MB L2 still holds.
+__global__ void __launch_bounds__(256)
+k_bn_bwd_reduce4(const float4* __restrict__ dy, const float4* __restrict__ y, const float4* __restrict__ x, int n, int C4,
+                 const float4* __restrict__ mean, const float4* __restrict__ invstd, int relu,
+                 double* __restrict__ sums, unsigned char* __restrict__ ws, int group) {
+    __shared__ float4 s_a[256];
+    __shared__ float4 s_b[256];
+    __shared__ int flag_s;
+    const int c4 = threadIdx.x % C4;
+    const int rl = threadIdx.x / C4;
+    const int RL = 256 / C4;
+    const float4 m = mean[c4], is = invstd[c4];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (long long r = (long long)blockIdx.x * RL + rl; r < n; r += (long long)gridDim.x * RL) {
+        const long long t = r * C4 + c4;
+        float4 g = __ldg(dy + t);              // default caching: the apply pass re-reads the tail of all three from L2
+        const float4 xv = __ldg(x + t);
+        if (relu) {
+            const float4 yv = __ldg(y + t);
+            if (!(yv.x > 0.f)) g.x = 0.f;
+            if (!(yv.y > 0.f)) g.y = 0.f;
+            if (!(yv.z > 0.f)) g.z = 0.f;
+            if (!(yv.w > 0.f)) g.w = 0.f;
+        }
+        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        b.x = fmaf(g.x, (xv.x - m.x) * is.x, b.x);
+        b.y = fmaf(g.y, (xv.y - m.y) * is.y, b.y);
+        b.z = fmaf(g.z, (xv.z - m.z) * is.z, b.z);
+        b.w = fmaf(g.w, (xv.w - m.w) * is.w, b.w);
+    }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+    __syncthreads();
+    const int C = 4 * C4;
+    double v = 0.0;
+    if (threadIdx.x < 2 * C) {
+        const float* src = reinterpret_cast<const float*>(threadIdx.x < C ? s_a : s_b);
+        const int cc = threadIdx.x % C;
+        for (int j = 0; j < RL; ++j) v += (double)src[j * C + cc];
+    }
+    ud_det_reduce(v, threadIdx.x, 2 * C, ws, group, sums, &flag_s);      // sums[0..C) = sum g, [C..2C) = sum g * xhat
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply4(const float4* __restrict__ dy, const float4* __restrict__ y, const float4* __restrict__ x,
+                long long total4, int C4, int n, const float4* __restrict__ mean, const float4* __restrict__ invstd,
+                const float* __restrict__ gamma, const double* __restrict__ sum_g, const double* __restrict__ sum_gx,
+                int relu, float4* __restrict__ dx, float4* __restrict__ dres) {
+    const long long stride = (long long)gridDim.x * blockDim.x;          // multiple of C4 (256 % C4 == 0)
+    long long t = total4 - 1 - ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (t < 0) return;
+    const int c4 = (int)(t % C4);
+    const float inv_n = 1.f / (float)n;
+    const float4 m = mean[c4], is = invstd[c4];
+    float4 mg, mgx, k;
+    mg.x = (float)sum_g[4 * c4 + 0] * inv_n; mg.y = (float)sum_g[4 * c4 + 1] * inv_n;
+    mg.z = (float)sum_g[4 * c4 + 2] * inv_n; mg.w = (float)sum_g[4 * c4 + 3] * inv_n;
+    mgx.x = (float)sum_gx[4 * c4 + 0] * inv_n; mgx.y = (float)sum_gx[4 * c4 + 1] * inv_n;
+    mgx.z = (float)sum_gx[4 * c4 + 2] * inv_n; mgx.w = (float)sum_gx[4 * c4 + 3] * inv_n;
+    k.x = (gamma ? gamma[4 * c4 + 0] : 1.f) * is.x; k.y = (gamma ? gamma[4 * c4 + 1] : 1.f) * is.y;
+    k.z = (gamma ? gamma[4 * c4 + 2] : 1.f) * is.z; k.w = (gamma ? gamma[4 * c4 + 3] : 1.f) * is.w;
+    for (; t >= 0; t -= stride) {
+        float4 g = __ldcs(dy + t);
+        const float4 xv = __ldcs(x + t);
+        if (relu) {
+            const float4 yv = __ldcs(y + t);
+            if (!(yv.x > 0.f)) g.x = 0.f;
+            if (!(yv.y > 0.f)) g.y = 0.f;
+            if (!(yv.z > 0.f)) g.z = 0.f;
+            if (!(yv.w > 0.f)) g.w = 0.f;
+        }
+        float4 o;       // same expression as the scalar kernel: gamma * invstd * (g - mean_g - xhat * mean_gx)
+        o.x = k.x * (g.x - mg.x - ((xv.x - m.x) * is.x) * mgx.x);
+        o.y = k.y * (g.y - mg.y - ((xv.y - m.y) * is.y) * mgx.y);
+        o.z = k.z * (g.z - mg.z - ((xv.z - m.z) * is.z) * mgx.z);
+        o.w = k.w * (g.w - mg.w - ((xv.w - m.w) * is.w) * mgx.w);
+        dx[t] = o;
+        if (dres) dres[t] = g;
+    }
+}
+
 // ---- scatter to BEV ---------------------------------------------------------------------------
 // CTA = 32 consecutive rows (rows of one conv output are sorted by (b,z,y,x), so they are mostly x-adjacent) x all C
 // channels.  The 32 x C voxel tile is staged in shared memory by TMA: C/32 tensor loads (cp.async.bulk.tensor.2d) of a
@@ -357,10 +443,28 @@ int ud_bn_backward(const float* dy, const float* y, const float* x, int n, int C
     UD_CUDA_TRY(cudaMemsetAsync(workspace, 0, UD_DET_COUNTER_BYTES, stream));
     double* sum_g = sums;
     double* sum_gx = sums + C;
+    long long total = (long long)n * C;
+    const bool vec = C % 4 == 0 && C >= 4 &&
+                     ((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean |
+                        (uintptr_t)invstd) & 15u) == 0);
+    if (vec) {
+        // same grid as the scalar form (the workspace was sized for it); a block covers 4x the rows per iteration
+        k_bn_bwd_reduce4<<<grid, 256, 0, stream>>>((const float4*)dy, (const float4*)y, (const float4*)x, n, C / 4,
+                                                   (const float4*)mean, (const float4*)invstd, relu, sums,
+                                                   (unsigned char*)workspace, ud_det_group(grid));
+        UD_LAUNCH_CHECK();
+        const long long total4 = total / 4;
+        const long long want4 = (total4 + 255) / 256;
+        const int grid4 = (int)(want4 < UD_NUM_SMS * 8 ? want4 : UD_NUM_SMS * 8);
+        k_bn_bwd_apply4<<<grid4, 256, 0, stream>>>((const float4*)dy, (const float4*)y, (const float4*)x, total4, C / 4, n,
+                                                   (const float4*)mean, (const float4*)invstd, gamma, sum_g, sum_gx, relu,
+                                                   (float4*)dx, (float4*)dres);
+        UD_LAUNCH_CHECK();
+        return UD_OK;
+    }
     k_bn_bwd_reduce<<<grid, 256, 0, stream>>>(dy, y, x, n, C, mean, invstd, relu, sums, (unsigned char*)workspace,
                                               ud_det_group(grid));
     UD_LAUNCH_CHECK();
-    long long total = (long long)n * C;
     long long want2 = (total + 255) / 256;
     int grid2 = (int)(want2 < UD_NUM_SMS * 16 ? want2 : UD_NUM_SMS * 16);
     k_bn_bwd_apply<<<grid2, 256, 0, stream>>>(dy, y, x, total, C, n, mean, invstd, gamma, sum_g, sum_gx, relu,

@@ -219,11 +219,18 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             v[j] = make_uint4(0u, 0u, 0u, 0u);
+#if defined(UD_WG_EXP) && (UD_WG_EXP == 1 || UD_WG_EXP == 3)
+                            if (idx[j] == -12345)
+#else
                             if (idx[j] >= 0)
+#endif
                                 v[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)idx[j] * CIN + coff));
                         }
                         mbar_wait(bar_a_empty + 8 * slot, (((uint32_t)(ia / WG_A_STAGES)) & 1u) ^ 1u);
                         unsigned char* base = smem_al + slot * WG_A_BYTES + atom * WG_ATOM_BYTES;
+#if defined(UD_WG_EXP) && UD_WG_EXP == 3
+                        if (idx[0] == -12345)
+#endif
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             *reinterpret_cast<uint4*>(base + swz32_off(rb + 4 * j, c16)) = rna_tf32(v[j]);
@@ -262,6 +269,9 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
                         const uint32_t first = (started >> s) & 1u;
 #pragma unroll
                         for (int ks = 0; ks < WG_RS / 8; ++ks)      // 8 rows per MMA = two 512-byte swizzle groups
+#if defined(UD_WG_EXP) && UD_WG_EXP == 2
+                            if (n_rows == -7)
+#endif
                             umma_tf32(d, da + (uint64_t)(ks * 64), dg + (uint64_t)(ks * 64), IDESC, (first || ks > 0) ? 1u : 0u);
                         umma_commit(bar_a_empty + 8 * aslot);
                     }
