@@ -87,26 +87,41 @@ k_hash_build(const int4* __restrict__ coords, int n, int D, int H, int W, unsign
 //                  segment; K4 = K rounded up to 4, ld = n rounded up to 128, padding -1)  -- optional
 // plus tile_masks[row / 128] |= 1 << k for every tap that occurs in the 128-row tile (zeroed by the launcher).  This is the
 // round-1 builder and its separate transpose kernel (0.8 ms per step) in one pass.
+// ncu (profiles/r03_rulebook_ncu.md) showed the round-2 form of this kernel at 78 % SM throughput with 277 warp instructions per
+// row: the per-(row, tap) integer divisions by the run-time kernel size and the three multiplies of the key, not memory, bound
+// it.  Now a block decodes the K taps ONCE into (dz, dy, dx) and the key delta dz*H*W + dy*W + dx (shared memory), and a
+// (row, tap) thread does three range checks, one add and the hash probe.
 __global__ void __launch_bounds__(256)
 k_subm_table(const int4* __restrict__ coords, int n, UdConvGeom g, const unsigned long long* __restrict__ table,
              uint32_t mask, int ld, int* __restrict__ nbr, int* __restrict__ nbr_t, unsigned int* __restrict__ tile_masks) {
     __shared__ int tile[32][33];
+    __shared__ int4 tap_s[32];                         // (dz, dy, dx, key delta) of tap k
     const int K = g.kD * g.kH * g.kW;
     const int r0 = blockIdx.x * 32;
-    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-        const int rl = e >> 5, k = e & 31;            // a warp = one row, lanes = taps: the 27 probes of a row together
+    if (threadIdx.x < 32) {
+        const int k = threadIdx.x;
+        int4 t = make_int4(0, 0, 0, 0);
+        if (k < K) {
+            t.x = (k / (g.kW * g.kH) - g.kD / 2) * g.dD;
+            t.y = ((k / g.kW) % g.kH - g.kH / 2) * g.dH;
+            t.z = (k % g.kW - g.kW / 2) * g.dW;
+            t.w = (t.x * g.iH + t.y) * g.iW + t.z;
+        }
+        tap_s[k] = t;
+    }
+    __syncthreads();
+    const int k = threadIdx.x & 31;                    // a warp = one row, lanes = taps: the 27 probes of a row together
+    const int4 tp = tap_s[k];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int rl = (threadIdx.x >> 5) + 8 * it;
         const int o = r0 + rl;
         int r = -1;
         if (o < n && k < K) {
-            const int kx = k % g.kW;
-            const int ky = (k / g.kW) % g.kH;
-            const int kz = k / (g.kW * g.kH);
-            const int4 c = coords[o];
-            const int z = c.y + (kz - g.kD / 2) * g.dD;
-            const int y = c.z + (ky - g.kH / 2) * g.dH;
-            const int x = c.w + (kx - g.kW / 2) * g.dW;
-            if (z >= 0 && z < g.iD && y >= 0 && y < g.iH && x >= 0 && x < g.iW) {
-                const uint32_t key = (((uint32_t)c.x * g.iD + z) * g.iH + y) * g.iW + x;
+            const int4 c = __ldg(coords + o);          // same address for the whole warp: one broadcast load
+            const int z = c.y + tp.x, y = c.z + tp.y, x = c.w + tp.z;
+            if ((unsigned)z < (unsigned)g.iD && (unsigned)y < (unsigned)g.iH && (unsigned)x < (unsigned)g.iW) {
+                const uint32_t key = (((uint32_t)c.x * g.iD + c.y) * g.iH + c.z) * g.iW + c.w + (uint32_t)tp.w;
                 r = ud_hash_lookup(table, mask, key);
             }
         }
@@ -121,10 +136,10 @@ k_subm_table(const int4* __restrict__ coords, int n, UdConvGeom g, const unsigne
         const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // lanes = rows, warps = taps
         const int k_pad = (K + 3) / 4 * 4;
         unsigned int m = 0u;
-        for (int k = ty; k < k_pad; k += 8) {
-            const int v = k < K ? tile[tx][k] : -1;
-            if (r0 + tx < ld) nbr_t[(size_t)k * ld + r0 + tx] = v;
-            if (__ballot_sync(0xffffffffu, r0 + tx < n && v >= 0)) m |= 1u << k;
+        for (int kk = ty; kk < k_pad; kk += 8) {
+            const int v = kk < K ? tile[tx][kk] : -1;
+            if (r0 + tx < ld) nbr_t[(size_t)kk * ld + r0 + tx] = v;
+            if (__ballot_sync(0xffffffffu, r0 + tx < n && v >= 0)) m |= 1u << kk;
         }
         if (tile_masks != nullptr && tx == 0 && m) atomicOr(tile_masks + (r0 >> 7), m);
     }
@@ -134,8 +149,10 @@ k_subm_table(const int4* __restrict__ coords, int n, UdConvGeom g, const unsigne
 __device__ __forceinline__ int ud_out_coord(int in, int k, int stride, int pad, int dil, int out_dim) {
     int num = in + pad - k * dil;
     if (num < 0) return -1;
-    if (num % stride != 0) return -1;
-    int o = num / stride;
+    int o;
+    if (stride == 1) o = num;
+    else if (stride == 2) { if (num & 1) return -1; o = num >> 1; }      // the backbone's strides: no integer division
+    else { if (num % stride != 0) return -1; o = num / stride; }
     return o < out_dim ? o : -1;
 }
 
@@ -160,29 +177,29 @@ __device__ __forceinline__ uint32_t ud_out_key(const UdConvGeom& g, const uint32
     return ((uint32_t)b << g.kl.bits_total) | __ldg(tab + oz) | __ldg(tab + g.oD + oy) | __ldg(tab + g.oD + g.oH + ox);
 }
 
-__device__ __forceinline__ bool ud_pair_key(const int4 c, int k, const UdConvGeom& g, const uint32_t* __restrict__ tab,
-                                            uint32_t* key) {
-    int kx = k % g.kW;
-    int ky = (k / g.kW) % g.kH;
-    int kz = k / (g.kW * g.kH);
-    int oz = ud_out_coord(c.y, kz, g.sD, g.pD, g.dD, g.oD);
-    int oy = ud_out_coord(c.z, ky, g.sH, g.pH, g.dH, g.oH);
-    int ox = ud_out_coord(c.w, kx, g.sW, g.pW, g.dW, g.oW);
-    if ((oz | oy | ox) < 0) return false;
-    *key = ud_out_key(g, tab, c.x, oz, oy, ox);
-    return true;
-}
-
+// One thread per input row walks the taps axis by axis and only descends where the axis has an output coordinate (a
+// stride-2 3x3x3 kernel has 1 or 2 of 3 per axis: <= 8 of 27 taps).  The round-2 form -- one thread per (row, tap), three
+// divisions each -- ran at 81 % SM throughput, i.e. was bound by its integer arithmetic (profiles/r03_rulebook_ncu.md).
 __global__ void __launch_bounds__(256)
 k_conv_mark(const int4* __restrict__ coords, int n, UdConvGeom g, const uint32_t* __restrict__ tab,
             unsigned int* __restrict__ bitmap) {
-    int K = g.kD * g.kH * g.kW;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * K) return;
-    int i = (int)(t / K);
-    int k = (int)(t - (long long)i * K);
-    uint32_t key;
-    if (ud_pair_key(coords[i], k, g, tab, &key)) atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = coords[i];
+    for (int kz = 0; kz < g.kD; ++kz) {
+        const int oz = ud_out_coord(c.y, kz, g.sD, g.pD, g.dD, g.oD);
+        if (oz < 0) continue;
+        for (int ky = 0; ky < g.kH; ++ky) {
+            const int oy = ud_out_coord(c.z, ky, g.sH, g.pH, g.dH, g.oH);
+            if (oy < 0) continue;
+            for (int kx = 0; kx < g.kW; ++kx) {
+                const int ox = ud_out_coord(c.w, kx, g.sW, g.pW, g.dW, g.oW);
+                if (ox < 0) continue;
+                const uint32_t key = ud_out_key(g, tab, c.x, oz, oy, ox);
+                atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -244,27 +261,44 @@ k_conv_tables(const int4* __restrict__ coords, int n, UdConvGeom g, const uint32
     __shared__ int tile[32][33];
     const int K = g.kD * g.kH * g.kW;
     const int r0 = blockIdx.x * 32;
-    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-        const int rl = e >> 5, k = e & 31;
+    for (int e = threadIdx.x; e < 32 * 33; e += 256) (&tile[0][0])[e] = -1;
+    __syncthreads();
+    {
+        // 8 threads per row: each walks the row's taps axis by axis (only where an output coordinate exists, see
+        // k_conv_mark) and takes every 8th existing pair -- the rank lookups (two random reads) of a row run in parallel
+        const int rl = threadIdx.x >> 3, j = threadIdx.x & 7;
         const int i = r0 + rl;
-        int o = -1;
-        uint32_t key;
-        if (i < n && k < K && ud_pair_key(coords[i], k, g, tab, &key)) {
-            const unsigned int word = bitmap[key >> 5];
-            const unsigned int below = word & ((1u << (key & 31)) - 1u);
-            o = prefix[key >> 5] + __popc(below);
-            if (o < n_out) {
-                if (nbr_out) nbr_out[(size_t)o * K + k] = i;
-                if (nbr_out_t) {
-                    nbr_out_t[(size_t)k * ld_out + o] = i;
-                    unsigned int* mw = masks_out + (o >> 7);
-                    if (!((*reinterpret_cast<volatile unsigned int*>(mw) >> k) & 1u)) atomicOr(mw, 1u << k);
+        if (i < n) {
+            const int4 c = __ldg(coords + i);
+            int cnt = 0;
+            for (int kz = 0; kz < g.kD; ++kz) {
+                const int oz = ud_out_coord(c.y, kz, g.sD, g.pD, g.dD, g.oD);
+                if (oz < 0) continue;
+                for (int ky = 0; ky < g.kH; ++ky) {
+                    const int oy = ud_out_coord(c.z, ky, g.sH, g.pH, g.dH, g.oH);
+                    if (oy < 0) continue;
+                    for (int kx = 0; kx < g.kW; ++kx) {
+                        const int ox = ud_out_coord(c.w, kx, g.sW, g.pW, g.dW, g.oW);
+                        if (ox < 0) continue;
+                        if (((cnt++) & 7) != j) continue;
+                        const int k = (kz * g.kH + ky) * g.kW + kx;
+                        const uint32_t key = ud_out_key(g, tab, c.x, oz, oy, ox);
+                        const unsigned int word = __ldg(bitmap + (key >> 5));
+                        const unsigned int below = word & ((1u << (key & 31)) - 1u);
+                        const int o = __ldg(prefix + (key >> 5)) + __popc(below);
+                        if (o < n_out) {
+                            if (nbr_out) nbr_out[(size_t)o * K + k] = i;
+                            if (nbr_out_t) {
+                                nbr_out_t[(size_t)k * ld_out + o] = i;
+                                unsigned int* mw = masks_out + (o >> 7);
+                                if (!((*reinterpret_cast<volatile unsigned int*>(mw) >> k) & 1u)) atomicOr(mw, 1u << k);
+                            }
+                            tile[rl][k] = o;
+                        }
+                    }
                 }
-            } else {
-                o = -1;
             }
         }
-        tile[rl][k] = o;
     }
     __syncthreads();
     if (nbr_in != nullptr) {
@@ -477,7 +511,6 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
     UdConvWs L;
     rc = ud_conv_layout(workspace, workspace_bytes, g, &L);
     if (rc != UD_OK) return rc;
-    int K = g.kD * g.kH * g.kW;
     int words = (int)L.words;
     UD_CUDA_TRY(cudaMemsetAsync(L.bitmap, 0, L.words * 4, stream));
     if (g.kl.order != 0) {
@@ -485,8 +518,7 @@ int ud_rulebook_conv_count(const int* coords, int n_in, int batch_size, const in
         UD_LAUNCH_CHECK();
     }
     if (n_in > 0) {
-        k_conv_mark<<<ud_blocks((long long)n_in * K, 256), 256, 0, stream>>>((const int4*)coords, n_in, g, L.tab,
-                                                                             L.bitmap);
+        k_conv_mark<<<ud_blocks(n_in, 256), 256, 0, stream>>>((const int4*)coords, n_in, g, L.tab, L.bitmap);
         UD_LAUNCH_CHECK();
     }
     k_popc<<<ud_blocks(words + 1, 256), 256, 0, stream>>>(L.bitmap, words, L.pc);
