@@ -573,10 +573,15 @@ def _algorithmic(name, a, meta, cache):
     if name == "ud_voxel_pooling_backward":
         B, N, C, nx, ny = a[0:5]
         return "voxel_pooling bwd", "hbm", B * N * (C * 4 + 12) + B * nx * ny * C * 4, 0
-    if name in ("ud_box_distill_forward", "ud_box_distill_backward"):
-        mode, B, C, H, W, M = a[0], a[3], a[4], a[5], a[6], a[9]
-        byts = 2 * B * M * 9 * 4 * C * 4 + (B * C * H * W * 4 if name.endswith("backward") else 0)
-        return "%s distill %s" % ("feature" if mode == 0 else "relation", name.rsplit("_", 1)[1]), "hbm", byts, 0
+    if name in ("ud_box_distill_forward", "ud_box_distill_backward", "ud_box_distill_forward_layout",
+                "ud_box_distill_backward_layout"):
+        if name.endswith("_layout"):
+            mode, B, C, H, W, M = a[0], a[5], a[6], a[7], a[8], a[11]
+        else:
+            mode, B, C, H, W, M = a[0], a[3], a[4], a[5], a[6], a[9]
+        direction = "backward" if "backward" in name else "forward"
+        byts = 2 * B * M * 9 * 4 * C * 4 + (B * C * H * W * 4 if direction == "backward" else 0)
+        return "%s distill %s" % ("feature" if mode == 0 else "relation", direction), "hbm", byts, 0
     if name in ("ud_response_distill_forward", "ud_response_distill_backward"):
         B, n_cls, n_reg, H, W = a[4:9]
         ch = n_cls + n_reg

@@ -40,24 +40,35 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int W, int H) {
     return t;
 }
 
-__device__ __forceinline__ float sample(const float* __restrict__ plane, const Taps& t, int W, int H) {
+// Memory layout of a (B, C, H, W) map: element (c, y, x) of a sample = base + c * lc + y * ly + x * lx.
+//   NCHW: lc = H W, ly = W, lx = 1      NHWC (torch channels_last, what the dense trunk runs in): lc = 1, ly = W C, lx = C
+// With NHWC the C channels of a tap are contiguous, so the threads of a block (one channel each) read whole lines, and the
+// four layout copies per step that fed these kernels NCHW maps (0.15 ms each at 512 channels) are gone.
+struct MapLayout { int lc, ly, lx; };
+__host__ __device__ __forceinline__ MapLayout map_layout(int nhwc, int C, int H, int W) {
+    MapLayout l;
+    if (nhwc) { l.lc = 1; l.ly = W * C; l.lx = C; } else { l.lc = H * W; l.ly = W; l.lx = 1; }
+    return l;
+}
+
+__device__ __forceinline__ float sample(const float* __restrict__ plane, const Taps& t, int W, int H, const MapLayout l) {
     float v = 0.f;
     const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
     const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-    if (yin0 && xin0) v += __ldg(plane + t.y0 * W + t.x0) * t.w00;
-    if (yin0 && xin1) v += __ldg(plane + t.y0 * W + t.x0 + 1) * t.w01;
-    if (yin1 && xin0) v += __ldg(plane + (t.y0 + 1) * W + t.x0) * t.w10;
-    if (yin1 && xin1) v += __ldg(plane + (t.y0 + 1) * W + t.x0 + 1) * t.w11;
+    if (yin0 && xin0) v += __ldg(plane + t.y0 * l.ly + t.x0 * l.lx) * t.w00;
+    if (yin0 && xin1) v += __ldg(plane + t.y0 * l.ly + (t.x0 + 1) * l.lx) * t.w01;
+    if (yin1 && xin0) v += __ldg(plane + (t.y0 + 1) * l.ly + t.x0 * l.lx) * t.w10;
+    if (yin1 && xin1) v += __ldg(plane + (t.y0 + 1) * l.ly + (t.x0 + 1) * l.lx) * t.w11;
     return v;
 }
 
-__device__ __forceinline__ void scatter(float* plane, const Taps& t, int W, int H, float g) {
+__device__ __forceinline__ void scatter(float* plane, const Taps& t, int W, int H, float g, const MapLayout l) {
     const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
     const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-    if (yin0 && xin0) atomicAdd(plane + t.y0 * W + t.x0, g * t.w00);
-    if (yin0 && xin1) atomicAdd(plane + t.y0 * W + t.x0 + 1, g * t.w01);
-    if (yin1 && xin0) atomicAdd(plane + (t.y0 + 1) * W + t.x0, g * t.w10);
-    if (yin1 && xin1) atomicAdd(plane + (t.y0 + 1) * W + t.x0 + 1, g * t.w11);
+    if (yin0 && xin0) atomicAdd(plane + t.y0 * l.ly + t.x0 * l.lx, g * t.w00);
+    if (yin0 && xin1) atomicAdd(plane + t.y0 * l.ly + (t.x0 + 1) * l.lx, g * t.w01);
+    if (yin1 && xin0) atomicAdd(plane + (t.y0 + 1) * l.ly + t.x0 * l.lx, g * t.w10);
+    if (yin1 && xin1) atomicAdd(plane + (t.y0 + 1) * l.ly + (t.x0 + 1) * l.lx, g * t.w11);
 }
 
 // key-points of one box from its 4 BEV corners (cell units), normalised and column-swapped like the
@@ -100,6 +111,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_box_distill_fwd(const float* __restrict__ s_map, const float* __restrict__ t_map, int C, int H, int W,
+                  const MapLayout ls, const MapLayout lt,
                   const float* __restrict__ corners, const unsigned char* __restrict__ valid, int M,
                   float* __restrict__ out) {
     extern __shared__ float sm[];            // MODE 1: S_s[9][C], S_t[9][C]
@@ -123,7 +135,7 @@ k_box_distill_fwd(const float* __restrict__ s_map, const float* __restrict__ t_m
         for (int c = threadIdx.x; c < C; c += blockDim.x)
 #pragma unroll
             for (int p = 0; p < NKP; ++p)
-                acc += fabsf(sample(sb + c * plane, taps[p], W, H) - sample(tb + c * plane, taps[p], W, H));
+                acc += fabsf(sample(sb + c * ls.lc, taps[p], W, H, ls) - sample(tb + c * lt.lc, taps[p], W, H, lt));
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) out[box] = acc / (float)(NKP * C);
         return;
@@ -133,8 +145,8 @@ k_box_distill_fwd(const float* __restrict__ s_map, const float* __restrict__ t_m
     for (int c = threadIdx.x; c < C; c += blockDim.x)
 #pragma unroll
         for (int p = 0; p < NKP; ++p) {
-            Ss[p * C + c] = sample(sb + c * plane, taps[p], W, H);
-            St[p * C + c] = sample(tb + c * plane, taps[p], W, H);
+            Ss[p * C + c] = sample(sb + c * ls.lc, taps[p], W, H, ls);
+            St[p * C + c] = sample(tb + c * lt.lc, taps[p], W, H, lt);
         }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -174,6 +186,7 @@ k_box_distill_fwd(const float* __restrict__ s_map, const float* __restrict__ t_m
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_box_distill_bwd(const float* __restrict__ s_map, const float* __restrict__ t_map, int C, int H, int W,
+                  const MapLayout ls, const MapLayout lt,
                   const float* __restrict__ corners, const unsigned char* __restrict__ valid, int M,
                   const float* __restrict__ upstream, float* __restrict__ grad_s) {
     extern __shared__ float sm[];            // MODE 1: S_s[9][C], S_t[9][C] (S_t later reused for dN)
@@ -196,9 +209,9 @@ k_box_distill_bwd(const float* __restrict__ s_map, const float* __restrict__ t_m
         for (int c = threadIdx.x; c < C; c += blockDim.x)
 #pragma unroll
             for (int p = 0; p < NKP; ++p) {
-                float d = sample(sb + c * plane, taps[p], W, H) - sample(tb + c * plane, taps[p], W, H);
+                float d = sample(sb + c * ls.lc, taps[p], W, H, ls) - sample(tb + c * lt.lc, taps[p], W, H, lt);
                 float g = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
-                if (g != 0.f) scatter(gb + c * plane, taps[p], W, H, g);
+                if (g != 0.f) scatter(gb + c * ls.lc, taps[p], W, H, g, ls);
             }
         return;
     }
@@ -207,8 +220,8 @@ k_box_distill_bwd(const float* __restrict__ s_map, const float* __restrict__ t_m
     for (int c = threadIdx.x; c < C; c += blockDim.x)
 #pragma unroll
         for (int p = 0; p < NKP; ++p) {
-            Ss[p * C + c] = sample(sb + c * plane, taps[p], W, H);
-            St[p * C + c] = sample(tb + c * plane, taps[p], W, H);
+            Ss[p * C + c] = sample(sb + c * ls.lc, taps[p], W, H, ls);
+            St[p * C + c] = sample(tb + c * lt.lc, taps[p], W, H, lt);
         }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -271,7 +284,7 @@ k_box_distill_bwd(const float* __restrict__ s_map, const float* __restrict__ t_m
             float inv = inv_s[i];
             float g = St[i * C + c] * inv;
             if (nrm_s[i] > 0.f) g -= Ss[i * C + c] * dots[i] * inv * inv / nrm_s[i];
-            if (g != 0.f) scatter(gb + c * plane, taps[i], W, H, g);
+            if (g != 0.f) scatter(gb + c * ls.lc, taps[i], W, H, g, ls);
         }
 }
 
@@ -434,18 +447,21 @@ int ud_box_corners_bev(const float* boxes, int n, int stride, float x_min, float
 
 // mode 0: FeatureDistillLoss per-box terms, mode 1: BEVDistillLoss (relation) per-box terms.
 // s_map/t_map (B,C,H,W) f32; corners (B,M,4,2) f32 cell units; valid (B,M) u8; out (B*M) f32 (0 for invalid).
-int ud_box_distill_forward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
-                           const float* corners, const unsigned char* valid, int M, float* out, void* stream_) {
+// Same with the memory layout of each map stated: *_nhwc = 0 for (B,C,H,W) contiguous, 1 for torch channels_last (NHWC).
+int ud_box_distill_forward_layout(int mode, const float* s_map, int s_nhwc, const float* t_map, int t_nhwc, int B, int C,
+                                  int H, int W, const float* corners, const unsigned char* valid, int M, float* out,
+                                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!s_map || !t_map || !corners || !valid || !out || B < 1 || C < 1 || H < 1 || W < 1 || M < 1)
         return UD_ERR_INVALID_ARG;
+    const MapLayout ls = map_layout(s_nhwc, C, H, W), lt = map_layout(t_nhwc, C, H, W);
     if (mode == 0) {
-        k_box_distill_fwd<0><<<B * M, 256, 0, stream>>>(s_map, t_map, C, H, W, corners, valid, M, out);
+        k_box_distill_fwd<0><<<B * M, 256, 0, stream>>>(s_map, t_map, C, H, W, ls, lt, corners, valid, M, out);
     } else if (mode == 1) {
         size_t smem = (size_t)2 * NKP * C * sizeof(float);
         if (smem > 200 * 1024) return UD_ERR_UNSUPPORTED;
         UD_CUDA_TRY(cudaFuncSetAttribute(k_box_distill_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_box_distill_fwd<1><<<B * M, 256, smem, stream>>>(s_map, t_map, C, H, W, corners, valid, M, out);
+        k_box_distill_fwd<1><<<B * M, 256, smem, stream>>>(s_map, t_map, C, H, W, ls, lt, corners, valid, M, out);
     } else {
         return UD_ERR_INVALID_ARG;
     }
@@ -453,27 +469,40 @@ int ud_box_distill_forward(int mode, const float* s_map, const float* t_map, int
     return UD_OK;
 }
 
+int ud_box_distill_forward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
+                           const float* corners, const unsigned char* valid, int M, float* out, void* stream_) {
+    return ud_box_distill_forward_layout(mode, s_map, 0, t_map, 0, B, C, H, W, corners, valid, M, out, stream_);
+}
+
 // grad_s (B,C,H,W) f32 is fully written (zeroed here, then accumulated); upstream (B*M) f32 = dL/d out[box].
-int ud_box_distill_backward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
-                            const float* corners, const unsigned char* valid, int M, const float* upstream,
-                            float* grad_s, void* stream_) {
+// grad_s has the layout of s_map.
+int ud_box_distill_backward_layout(int mode, const float* s_map, int s_nhwc, const float* t_map, int t_nhwc, int B, int C,
+                                   int H, int W, const float* corners, const unsigned char* valid, int M,
+                                   const float* upstream, float* grad_s, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const MapLayout ls = map_layout(s_nhwc, C, H, W), lt = map_layout(t_nhwc, C, H, W);
     if (!s_map || !t_map || !corners || !valid || !upstream || !grad_s || B < 1 || C < 1 || H < 1 || W < 1 || M < 1)
         return UD_ERR_INVALID_ARG;
     UD_CUDA_TRY(cudaMemsetAsync(grad_s, 0, (size_t)B * C * H * W * sizeof(float), stream));
     if (mode == 0) {
-        k_box_distill_bwd<0><<<B * M, 256, 0, stream>>>(s_map, t_map, C, H, W, corners, valid, M, upstream, grad_s);
+        k_box_distill_bwd<0><<<B * M, 256, 0, stream>>>(s_map, t_map, C, H, W, ls, lt, corners, valid, M, upstream, grad_s);
     } else if (mode == 1) {
         size_t smem = (size_t)2 * NKP * C * sizeof(float);
         if (smem > 200 * 1024) return UD_ERR_UNSUPPORTED;
         UD_CUDA_TRY(cudaFuncSetAttribute(k_box_distill_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_box_distill_bwd<1><<<B * M, 256, smem, stream>>>(s_map, t_map, C, H, W, corners, valid, M, upstream,
+        k_box_distill_bwd<1><<<B * M, 256, smem, stream>>>(s_map, t_map, C, H, W, ls, lt, corners, valid, M, upstream,
                                                            grad_s);
     } else {
         return UD_ERR_INVALID_ARG;
     }
     UD_LAUNCH_CHECK();
     return UD_OK;
+}
+
+int ud_box_distill_backward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
+                            const float* corners, const unsigned char* valid, int M, const float* upstream,
+                            float* grad_s, void* stream_) {
+    return ud_box_distill_backward_layout(mode, s_map, 0, t_map, 0, B, C, H, W, corners, valid, M, upstream, grad_s, stream_);
 }
 
 // Response distillation, forward.  cls_s (B,n_cls,H,W) student heat-map (already clamp-sigmoid), cls_t teacher

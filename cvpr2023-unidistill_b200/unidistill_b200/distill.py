@@ -40,6 +40,15 @@ def box_corners_bev(gt_boxes, pc_range, voxel_size, out_size_factor):
     return out
 
 
+def _map_layout(x):
+    """(tensor the kernels can read in place, nhwc flag): a dense channels_last (NHWC) map is taken as it is -- the dense
+    trunk computes in that layout -- anything else is made (B, C, H, W) contiguous."""
+    x = x.float()
+    if x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+        return x, 1
+    return x.contiguous(), 0
+
+
 class BoxDistill(Function):
     """Per-box feature-L1 (mode 0) or relation/Gram-L1 (mode 1) terms: (B*M,) with 0 for invalid boxes."""
 
@@ -47,18 +56,20 @@ class BoxDistill(Function):
     def forward(ctx, student, teacher, corners, valid, mode):
         native.require_cuda(student, teacher, corners)
         lib = native.load()
-        s = student.contiguous().float()
-        t = teacher.detach().contiguous().float()
+        s, s_nhwc = _map_layout(student)
+        t, t_nhwc = _map_layout(teacher.detach())
         c = corners.detach().contiguous().float()
         v = valid.to(torch.uint8).contiguous()
         B, C, H, W = [int(x) for x in s.shape]
         M = int(c.shape[1])
         out = torch.empty((B * M,), dtype=torch.float32, device=s.device)
-        rc = lib.ud_box_distill_forward(int(mode), native.ptr(s), native.ptr(t), B, C, H, W, native.ptr(c),
-                                        native.ptr(v), M, native.ptr(out), native.stream_ptr(s.device))
-        native.check(rc, "ud_box_distill_forward")
+        rc = lib.ud_box_distill_forward_layout(int(mode), native.ptr(s), s_nhwc, native.ptr(t), t_nhwc, B, C, H, W,
+                                               native.ptr(c), native.ptr(v), M, native.ptr(out),
+                                               native.stream_ptr(s.device))
+        native.check(rc, "ud_box_distill_forward_layout")
         ctx.save_for_backward(s, t, c, v)
         ctx.mode = int(mode)
+        ctx.layout = (s_nhwc, t_nhwc)
         return out
 
     @staticmethod
@@ -68,11 +79,11 @@ class BoxDistill(Function):
         B, C, H, W = [int(x) for x in s.shape]
         M = int(c.shape[1])
         g = grad_out.contiguous().float()
-        grad_s = torch.empty_like(s)
-        rc = lib.ud_box_distill_backward(ctx.mode, native.ptr(s), native.ptr(t), B, C, H, W, native.ptr(c),
-                                         native.ptr(v), M, native.ptr(g), native.ptr(grad_s),
-                                         native.stream_ptr(s.device))
-        native.check(rc, "ud_box_distill_backward")
+        grad_s = torch.empty_like(s)          # preserve_format: the gradient has the student's layout
+        rc = lib.ud_box_distill_backward_layout(ctx.mode, native.ptr(s), ctx.layout[0], native.ptr(t), ctx.layout[1],
+                                                B, C, H, W, native.ptr(c), native.ptr(v), M, native.ptr(g),
+                                                native.ptr(grad_s), native.stream_ptr(s.device))
+        native.check(rc, "ud_box_distill_backward_layout")
         return grad_s, None, None, None, None
 
 

@@ -270,6 +270,16 @@ int ud_box_distill_forward(int mode, const float* s_map, const float* t_map, int
 int ud_box_distill_backward(int mode, const float* s_map, const float* t_map, int B, int C, int H, int W,
                             const float* corners, const unsigned char* valid, int M, const float* upstream,
                             float* grad_s, void* stream);
+/* The same two with the memory layout of each map stated (s_nhwc / t_nhwc: 0 = (B,C,H,W) contiguous, 1 = torch
+ * channels_last, i.e. NHWC -- the layout the dense trunk computes in; grad_s has the layout of s_map).  The reference
+ * samples these maps with F.grid_sample on NCHW tensors (..._distill_lidar.py:200-226); reading NHWC in place saves the
+ * four layout copies per step that fed the NCHW entry points. */
+int ud_box_distill_forward_layout(int mode, const float* s_map, int s_nhwc, const float* t_map, int t_nhwc, int B, int C,
+                                  int H, int W, const float* corners, const unsigned char* valid, int M, float* out,
+                                  void* stream);
+int ud_box_distill_backward_layout(int mode, const float* s_map, int s_nhwc, const float* t_map, int t_nhwc, int B, int C,
+                                   int H, int W, const float* corners, const unsigned char* valid, int M,
+                                   const float* upstream, float* grad_s, void* stream);
 int ud_response_distill_forward(const float* cls_s, const float* cls_t, const float* reg_s, const float* reg_t,
                                 int B, int n_cls, int n_reg, int H, int W, const float* boxes, int M, int stride,
                                 const int* n_rows, float x_min, float y_min, float cell_x, float cell_y,

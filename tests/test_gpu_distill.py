@@ -113,6 +113,39 @@ def test_box_distill_benchmark_shapes_vs_oracle(cuda, native_lib, C, mode):
     assert _rel(sg.grad.cpu().numpy(), so.grad.numpy()) < REL
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("s_cl,t_cl", [(True, True), (True, False), (False, True)])
+def test_box_distill_reads_channels_last_maps_in_place(cuda, native_lib, mode, s_cl, t_cl):
+    """NHWC (torch channels_last) maps go to the kernels as they are (ud_box_distill_*_layout): same per-box terms and the
+    same gradient -- returned in the student's layout -- as with (B, C, H, W) contiguous maps."""
+    from unidistill_b200 import distill as D, synthetic as S
+
+    torch.manual_seed(7 + mode)
+    B, C = 2, 96
+    gt = S.lidar_batch(B, seed=5, points_per_sweep=10, sweeps=1)["gt_boxes"].to(cuda)
+    corners = D.box_corners_bev(gt, S.PC_RANGE_128, S.VOXEL_SIZE_128, 8)
+    valid = D.valid_box_prefix(gt)
+    s0 = torch.randn(B, C, 128, 128, device=cuda)
+    t0 = torch.randn(B, C, 128, 128, device=cuda)
+    w = torch.rand(B * gt.shape[1], device=cuda)
+
+    def run(s, t):
+        s = s.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        out = D.BoxDistill.apply(s, t, corners, valid, mode)
+        (out * w).sum().backward()
+        return out.detach(), s.grad
+
+    ref_out, ref_grad = run(s0, t0)
+    s1 = s0.contiguous(memory_format=torch.channels_last) if s_cl else s0
+    t1 = t0.contiguous(memory_format=torch.channels_last) if t_cl else t0
+    out, grad = run(s1, t1)
+    assert grad.is_contiguous(memory_format=torch.channels_last) == s_cl or not s_cl
+    # feature mode: identical arithmetic per element -> bit-identical; relation mode sums over channels in the same order too
+    assert torch.equal(out, ref_out)
+    assert torch.allclose(grad, ref_grad, rtol=0, atol=1e-6 * float(ref_grad.abs().max()))
+
+
 def test_identical_maps_give_zero(cuda, native_lib):
     from unidistill.layers.losses.distill import BEVDistillLoss, FeatureDistillLoss
 
