@@ -44,7 +44,7 @@ constexpr int WG_ATOM_BYTES = WG_RS * 128;   // one [64 rows x 32 fp32] swizzled
 constexpr int WG_A_BYTES = 4 * WG_ATOM_BYTES;   // 64 rows x 128 columns
 constexpr int WG_MAX_TAPS = 32;
 __host__ __device__ constexpr int wg_threads(int ng) { return ng * WG_GROUP_THREADS + 32; }
-__host__ __device__ constexpr int wg_tmem_cols(int ng) { return ng == 4 ? 512 : 256; }
+__host__ __device__ constexpr int wg_tmem_cols(int ng) { return ng == 2 ? 256 : 512; }
 
 __host__ __device__ constexpr size_t wg_smem_bytes(int cout, int ng = 4) {
     return (size_t)ng * WG_A_BYTES + (size_t)WG_G_STAGES * WG_RS * cout * 4 + 1024;
@@ -78,7 +78,7 @@ __device__ __forceinline__ uint4 rna_tf32(uint4 v) {
 }
 
 template <int CIN, int COUT, int NG>
-__global__ void __launch_bounds__(wg_threads(NG), NG == 4 ? 1 : 2)
+__global__ void __launch_bounds__(wg_threads(NG), NG == 2 ? 2 : 1)
 k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout, const int* __restrict__ nbr_t,
                     const unsigned int* __restrict__ tile_masks, int n_rows, int K, int tiles_per_cta, int st_per_cta,
                     float* __restrict__ dw) {
@@ -172,6 +172,24 @@ k_spconv_wgrad_umma(const float* __restrict__ in, const float* __restrict__ dout
         // wait can only tell the current phase from the previous one, and groups drift apart by more than that.
         int ia = 0, ig = 0;
         for (int t = tile0; t < tile1; ++t) {
+#if !defined(UD_WG_NO_PREFETCH)
+            // row indices are on the critical path of every gathered stage (index load -> gather -> store are serial inside a
+            // group): one group per tile prefetches the NEXT tile's index segments (this CTA's taps x 128 rows = 4 lines per tap).
+            // Measured on B200 (bs-4 step): 64->64 0.677 -> 0.632 ms with the index prefetch, -> 0.621 with dout as well.
+            if (t + 1 < tile1 && ((t - tile0) % WG_GROUPS) == g) {
+                const int n_lines = nst * TAPG * 4;
+                if (tg < n_lines) {
+                    const int tap = st0 * TAPG + tg / 4;
+                    if (tap < K)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nbr_t + (size_t)tap * ld_t + (size_t)(t + 1) * WG_TILE + (tg & 3) * 32));
+                }
+                // and the next tile's dout rows (128 rows x COUT floats, contiguous) towards L2
+                for (int l = tg; l < WG_TILE * COUT / 32; l += WG_GROUP_THREADS) {
+                    const size_t off = (size_t)(t + 1) * WG_TILE * COUT + (size_t)l * 32;
+                    if (off < (size_t)n_rows * COUT) asm volatile("prefetch.global.L2 [%0];" ::"l"(dout + off));
+                }
+            }
+#endif
             const unsigned int m = group_mask(__ldg(tile_masks + t));
             if (!m) continue;
             for (int h = 0; h < WG_TILE / WG_RS; ++h) {
@@ -327,7 +345,7 @@ int launch_wgrad_umma_n(const float* in, const float* dout, const int* nbr_t, co
     const int ngroups = (k_eff + st_max - 1) / st_max;
     const int st_per_cta = (k_eff + ngroups - 1) / ngroups;
     const int n_tiles = (n_rows + WG_TILE - 1) / WG_TILE;
-    int chunks = UD_NUM_SMS * (NG == 4 ? 1 : 2) / ngroups;             // about one CTA per SM (NG 4) / two (NG 2)
+    int chunks = UD_NUM_SMS * (NG == 2 ? 2 : 1) / ngroups;             // about one CTA per SM (NG 4, 5) / two (NG 2)
     if (chunks < 1) chunks = 1;
     if (chunks > n_tiles) chunks = n_tiles;
     const int tiles_per_cta = (n_tiles + chunks - 1) / chunks;
@@ -355,7 +373,8 @@ int wg_ng(int cin, int cout) {
     if (forced == 2 || forced == 4) return forced;
     // measured on B200 (bs-4 distillation step): NG 2 is slower where it matters (64 -> 64: 0.671 -> 0.810 ms: twice the
     // super-tap groups re-read dout and split 14 super-taps 4/4/4/2) and within 2 % elsewhere -- unlike the forward kernel,
-    // this one is not bound by its issuing warp.  Kept as an option.
+    // this one is not bound by its issuing warp.  Kept as an option.  (Five producer groups instead of four were measured too:
+    // 0.68 -> 0.75 ms, the fifth group's registers spill.)
     return 4;
 }
 
