@@ -83,7 +83,9 @@ def test_one_optimizer_step_changes_student_only(step_and_batch):
     assert np.isfinite(float(terms["loss"]))
     assert float(step.bucket.flat.abs().sum()) > 0
     changed = sum(int(not torch.equal(a, p.detach())) for a, p in zip(s0, step.student.parameters()))
-    assert changed > 0.9 * len(s0)
+    # the 42 tower-convolution biases sit in front of a train-mode BatchNorm: their gradient is exactly zero (the reference
+    # gets round-off noise there), so one step does not move them (center_head.batched_towers)
+    assert changed > 0.85 * len(s0)
     assert all(torch.equal(a, p.detach()) for a, p in zip(t0, step.teacher.parameters()))
     step._restore_teacher()
     assert all(torch.equal(a, b) for a, b in zip(tb0, step.teacher.buffers()))
