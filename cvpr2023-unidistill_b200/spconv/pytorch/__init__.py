@@ -180,6 +180,23 @@ class SparseConvolution(SparseModule):
         return out
 
 
+def prebuild_rulebooks(module, indices, spatial_shape, batch_size, indice_dict):
+    """Extension: builds the rulebooks of every sparse convolution under `module` from the voxel coordinates alone, in
+    module-registration order (== execution order for sequential encoders such as VoxelResBackBone8x), into `indice_dict`.
+    Rulebooks depend on coordinates only, and the strided builders read the output row count back to the host; doing all of
+    that BEFORE the feature pass keeps the five host reads of an encoder in one short geometry phase, after which the
+    convolution / BatchNorm launches run ahead of the GPU without a single synchronisation.  A rulebook that does not fit the
+    tensor a layer later sees is simply rebuilt by that layer (`_rulebook` checks key, kernel, stride and row count)."""
+    x = SparseConvTensor(None, indices, spatial_shape, batch_size, indice_dict=indice_dict)
+    for m in module.modules():
+        if not isinstance(m, SparseConvolution) or m.inverse:
+            continue
+        rb = m._rulebook(x)
+        if not m.subm:
+            x = SparseConvTensor(None, rb.out_coords, rb.out_shape, batch_size, indice_dict=indice_dict)
+    return indice_dict
+
+
 class SubMConv3d(SparseConvolution):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, indice_key=None, algo=None, fp32_accum=None, name=None, **kwargs):

@@ -15,6 +15,11 @@ from spconv.core import ConvAlgo
 
 from unidistill_b200.sparse import batch_norm_act, morton_order
 
+# Build every rulebook of the encoder before its feature pass (spconv.prebuild_rulebooks of this repo's shim): the host reads
+# of the strided builders then sit in one short geometry phase instead of between the convolutions.  UD_PREBUILD_RULEBOOKS=0
+# restores the lazy, layer-by-layer construction of the reference.
+PREBUILD_RULEBOOKS = os.environ.get("UD_PREBUILD_RULEBOOKS", "1") != "0"
+
 SPCONV_ALGO_TYPE = ConvAlgo.Native
 
 
@@ -178,6 +183,9 @@ class VoxelResBackBone8x(nn.Module):
             voxel_coords = cached[2]
         x = spconv.SparseConvTensor(features=voxel_features, indices=voxel_coords,
                                     spatial_shape=self.sparse_shape, batch_size=batch_size, indice_dict=indice_dict)
+        if PREBUILD_RULEBOOKS and voxel_coords.is_cuda and hasattr(spconv, "prebuild_rulebooks"):
+            # geometry first: all rulebooks (and their host reads) before the first feature kernel
+            spconv.prebuild_rulebooks(self, x.indices, x.spatial_shape, batch_size, x.indice_dict)
         x = self.conv_input(x)
         x_conv1 = self.conv1(x)
         x_conv2 = self.conv2(x_conv1)
