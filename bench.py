@@ -634,7 +634,7 @@ def _dominant(roof_all):
     e = dict(max(cands, key=lambda x: x["ms_per_step"]))
     kname = e["kernel"].split(" ")[0]
     traffic = None
-    for fn in ("r02_traffic.json", "r01_traffic.json"):
+    for fn in ("r03_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", fn)                      # dram bytes/launch from an ncu --set full capture
         if os.path.exists(tpath):
             with open(tpath) as f:

@@ -67,6 +67,42 @@ BATCH_TOWERS = os.environ.get("UD_BATCH_TOWERS", "1") != "0"
 _ROWS_CACHE = {}
 
 
+class _ConvDgradAsFprop(torch.autograd.Function):
+    """conv2d (stride 1, dilation 1) whose input gradient is computed as a FORWARD convolution of the output gradient with
+    the flipped, transposed kernel.  For the towers' block-diagonal second layer (76 <- 2688 channels) cuDNN's dgrad pick is
+    an indexed sm80 kernel at 1.17 ms on B200, while the same arithmetic as an fprop (2688 <- 76) runs on the sm100 implicit
+    GEMM in ~0.3 ms (profiles/r03_step_timeline.txt).  Weight / bias gradients come from aten's convolution_backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, padding):
+        ctx.save_for_backward(x, w)
+        ctx.padding = tuple(int(p) for p in padding)
+        ctx.has_bias = b is not None
+        return F.conv2d(x, w, b, stride=1, padding=ctx.padding)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = gb = None
+        kh, kw = int(w.shape[2]), int(w.shape[3])
+        if ctx.needs_input_grad[0]:
+            wt = w.flip(2, 3).transpose(0, 1)
+            gg = g
+            if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+                # the gradient must come out in the layout of x (NHWC in the trunk): the output gradient is the small tensor
+                # here (76 channels), converting it costs microseconds; an NCHW result would cost a 700 MB layout pass
+                gg = g.contiguous(memory_format=torch.channels_last)
+                wt = wt.contiguous(memory_format=torch.channels_last)
+            gx = F.conv2d(gg, wt, None, stride=1, padding=(kh - 1 - ctx.padding[0], kw - 1 - ctx.padding[1]))
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            _, gw, gb = torch.ops.aten.convolution_backward(
+                g, x, w, [int(w.shape[0])] if ctx.has_bias else None, (1, 1), ctx.padding, (1, 1), False, (0, 0), 1,
+                [False, True, ctx.has_bias])
+            if not ctx.has_bias:
+                gb = None
+        return gx, gw, gb, None
+
+
 def batched_towers(tasks, x):
     """tasks: the ModuleList of SepHeads of one CenterHead; x (B, C, H, W).  Returns [ {head: (B, classes, H, W)} per task ]
     == [task(x) for task in tasks], or None when the towers do not have the regular conv-BN-ReLU-conv shape."""
@@ -145,7 +181,10 @@ def batched_towers(tasks, x):
     w2 = w2_all.new_zeros((w2_all.shape[0], n * cin2) + tuple(w2_all.shape[2:])).index_put(idx, w2_all)
     if y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous():
         w2 = w2.contiguous(memory_format=torch.channels_last)
-    z = F.conv2d(y, w2, b2, stride=1, padding=c2.padding)
+    if torch.is_grad_enabled() and y.requires_grad:
+        z = _ConvDgradAsFprop.apply(y, w2, b2, c2.padding)
+    else:
+        z = F.conv2d(y, w2, b2, stride=1, padding=c2.padding)
     starts = [0]
     for c_ in outs:
         starts.append(starts[-1] + c_)

@@ -30,7 +30,9 @@ def main():
     for r in data:
         if len(r) <= ki:
             continue
-        name = re.sub(r"^void |<unnamed>::|\(.*", "", r[ki]).strip()
+        name = re.sub(r"^void |<unnamed>::|\(anonymous namespace\)::|\(.*", "", r[ki]).strip()
+        # k_spconv_umma_dg<CIN, COUT, SPLIT, NSETS> / k_spconv_wgrad_umma<CIN, COUT, NG>: key by the layer shape only
+        name = re.sub(r"^(k_spconv_umma_dg|k_spconv_wgrad_umma)<(\d+), (\d+)[^>]*>", r"\1<\2, \3>", name)
         vals = []
         for i, _, scale in idx:
             try:
