@@ -415,6 +415,49 @@ def test_backbone_forward_parity(cuda, native_lib, training):
     assert _rel_err(bev.detach().cpu().numpy(), ref_bev) < REL_TOL
 
 
+def test_prebuilt_rulebooks_equal_lazy_ones(cuda, native_lib, monkeypatch):
+    """Geometry first (spconv.prebuild_rulebooks before the feature pass) against the reference's lazy, layer-by-layer
+    rulebook construction: identical tables, hence bit-identical encoder outputs and gradients."""
+    import spconv.pytorch as spconv
+
+    from unidistill.layers.blocks_3d.det3d import VoxelResBackBone8x
+    from unidistill.layers.blocks_3d.det3d import spconv_backbone as SB
+
+    torch.manual_seed(1)
+    rng = np.random.default_rng(5)
+    sparse_shape = [41, 64, 64]
+    net = VoxelResBackBone8x(5, np.array([64, 64, 40])).to(cuda).train()
+    coords, feat = _clustered_sparse(rng, 2, sparse_shape, 5000, 5)
+    c = torch.from_numpy(coords).to(cuda)
+
+    def run(prebuild):
+        monkeypatch.setattr(SB, "PREBUILD_RULEBOOKS", prebuild)
+        f = torch.from_numpy(feat).to(cuda).requires_grad_(True)
+        d = {}
+        out, _, _ = net(f, c, 2, indice_dict=d)
+        out.features.square().sum().backward()
+        grads = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+        net.zero_grad(set_to_none=True)
+        return out, d, grads
+
+    out_l, d_l, g_l = run(False)
+    out_p, d_p, g_p = run(True)
+    keys = [k for k in d_l if isinstance(k, str)]
+    assert keys and sorted(keys) == sorted(k for k in d_p if isinstance(k, str))
+    for k in keys:
+        assert torch.equal(d_l[k].nbr_out, d_p[k].nbr_out)
+        if d_l[k].nbr_in is not None:
+            assert torch.equal(d_l[k].nbr_in, d_p[k].nbr_in)
+    assert torch.equal(out_l.indices, out_p.indices)
+    assert torch.equal(out_l.features, out_p.features)
+    # a second tensor with other coordinates under the same keys: stale prebuilt tables must not be used
+    d_stale = spconv.prebuild_rulebooks(net, c[:4000].contiguous(), sparse_shape, 2, {})
+    out_s, _, _ = net(torch.from_numpy(feat).to(cuda), c, 2, indice_dict=d_stale)
+    assert torch.equal(out_s.features, out_l.features)
+    for a, b in zip(g_l, g_p):       # the weight gradient adds its per-CTA results with red.global.add: not bit-reproducible
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+
+
 def test_eval_bn_epilogue_fusion_is_bit_identical(cuda, native_lib, monkeypatch):
     """Frozen / inference encoder: BatchNorm1d(eval) + residual + ReLU folded into the convolutions' epilogues
     (ud_sparse_conv_tc_forward_affine) against the same encoder running convolution and ud_bn_apply separately."""

@@ -4,6 +4,8 @@ Tolerance: BASELINE.json's north_star allows 1e-3 relative for fp32 features; th
 the tensor-core path at ~1e-5 (the MMA accumulates with truncation), asserted here as 5e-5 relative to the
 largest output.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -353,3 +355,45 @@ def test_pre_split_input_is_bit_identical(cuda, native_lib, cin, cout):
     finally:
         sparse.PRE_SPLIT_INPUT = old
     assert torch.equal(a, b)
+
+
+def _conv_digest_script():
+    return r"""
+import hashlib, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.getcwd(), "cvpr2023-unidistill_b200"))
+from unidistill_b200 import sparse as SP
+torch.manual_seed(3)
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(4)
+coords = torch.stack([torch.zeros(60000, dtype=torch.long), torch.randint(0, 21, (60000,), generator=g),
+                      torch.randint(0, 96, (60000,), generator=g), torch.randint(0, 96, (60000,), generator=g)], 1)
+coords = torch.unique(coords, dim=0).int().to(dev).contiguous()
+rb = SP.build_subm_rulebook(coords, 1, [21, 96, 96], 3)
+h = hashlib.sha256()
+for cin, cout in ((16, 16), (32, 32), (64, 64), (64, 128), (128, 128)):
+    x = torch.randn(coords.shape[0], cin, device=dev)
+    w = torch.randn(cout, 3, 3, 3, cin, device=dev) * 0.05
+    y = SP.sparse_conv(x, w, None, rb, False)
+    h.update(y.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+@pytest.mark.gpu
+def test_one_and_two_ctas_per_sm_give_identical_outputs(cuda, native_lib):
+    """k_spconv_umma_dg with NSETS = 4 (one CTA per SM, 512 TMEM columns) and NSETS = 2 (two CTAs per SM, the default):
+    the accumulation order per output tile is the same, so every output bit is.  The configuration is read once per process
+    (UD_DG_NSETS), hence two subprocesses."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for nsets in ("2", "4"):
+        env = dict(os.environ, UD_DG_NSETS=nsets)
+        r = subprocess.run([sys.executable, "-c", _conv_digest_script()], cwd=root, env=env, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[nsets] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert digests["2"] == digests["4"]
