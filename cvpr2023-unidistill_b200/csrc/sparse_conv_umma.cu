@@ -55,7 +55,8 @@ __host__ __device__ __forceinline__ int dg_logical_k(int pe, int cin) {
 //   [COUT x 64 bf16 W_hi] [COUT x 64 bf16 W_lo],  W_hi = bf16(W), W_lo = bf16(W - W_hi), 128-byte swizzle.
 // Block size = 4 * COUT * 64 bytes.
 __global__ void __launch_bounds__(256)
-k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int tapg, unsigned char* __restrict__ packed) {
+k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int tapg, int mode,
+                   unsigned char* __restrict__ packed) {
     constexpr int ks = 64;
     const int cin_eff = cin * tapg;
     const int k_eff = (K + tapg - 1) / tapg;
@@ -66,7 +67,16 @@ k_pack_weights_bf3(const float* __restrict__ w, int K, int cin, int cout, int ta
     const int cv = (int)((t / cout) % cin_eff);             // virtual channel = g * cin + c
     const int kj = (int)(t / ((long long)cout * cin_eff));
     const int tap = kj * tapg + cv / cin, c = cv % cin;
-    const float v = tap < K ? w[((size_t)tap * cin + c) * cout + n] : 0.f;      // w[k][c][n]
+    // source layout: mode -1: w[k][c][n] (K, cin, cout); modes 0-2 read the spconv-2 PARAMETER (Cout_p, K, Cin_p) in place:
+    //   0 forward        (cin = Cin_p, cout = Cout_p):  w[k][c][n] = P[n][k][c]
+    //   1 dgrad, SubM    (cin = Cout_p, cout = Cin_p):  w[k][c][n] = P[c][K-1-k][n]   (transposed, taps mirrored)
+    //   2 dgrad, strided (cin = Cout_p, cout = Cin_p):  w[k][c][n] = P[c][k][n]
+    float v = 0.f;
+    if (tap < K) {
+        if (mode < 0) v = w[((size_t)tap * cin + c) * cout + n];
+        else if (mode == 0) v = w[((size_t)n * K + tap) * cin + c];
+        else v = w[((size_t)c * K + (mode == 1 ? K - 1 - tap : tap)) * cout + n];
+    }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const int nstage = cin_eff / ks;
@@ -1227,7 +1237,24 @@ int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, voi
     if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
     const int tapg = ts_tapg(cin);
     const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
-    k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, tapg, (unsigned char*)packed);
+    k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w, K, cin, cout, tapg, -1, (unsigned char*)packed);
+    UD_LAUNCH_CHECK();
+    return UD_OK;
+}
+
+// The same packed image straight from the spconv-2 parameter layout (Cout_p, kz, ky, kx, Cin_p) -- no (K, cin, cout) copy, no
+// flip / transpose passes in front of the data-gradient convolution.  cin / cout are those of the convolution that will RUN:
+//   mode 0: the forward convolution (cin = Cin_p, cout = Cout_p);
+//   mode 1: the data gradient of a submanifold convolution = the same kernel on the transposed weights with mirrored taps
+//           (cin = Cout_p, cout = Cin_p);   mode 2: the data gradient of a strided convolution (transposed, not mirrored).
+int ud_sparse_conv_tc_pack_weights_param(const float* w_param, int K, int cin, int cout, int mode, void* packed, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!w_param || !packed || mode < 0 || mode > 2) return UD_ERR_INVALID_ARG;
+    if (!tc_shape_ok(K, cin, cout)) return UD_ERR_UNSUPPORTED;
+    if (((uintptr_t)packed & 15u) != 0) return UD_ERR_INVALID_ARG;
+    const int tapg = ts_tapg(cin);
+    const long long total = (long long)((K + tapg - 1) / tapg) * cin * tapg * cout;
+    k_pack_weights_bf3<<<ud_blocks(total, 256), 256, 0, stream>>>(w_param, K, cin, cout, tapg, mode, (unsigned char*)packed);
     UD_LAUNCH_CHECK();
     return UD_OK;
 }

@@ -238,17 +238,30 @@ def invalidate_packed_weights(weight=None):
         _PACK_CACHE.pop(id(weight), None)
 
 
-def _packed_weights(w_k, K, cin, cout, sp, weight=None):
+# Pack straight from the parameter layout (ud_sparse_conv_tc_pack_weights_param) instead of making the (K, Cin, Cout) copy --
+# and, for the data gradient, the flipped / transposed copy -- first: three small copy kernels less per layer and step.
+PACK_FROM_PARAM = os.environ.get("UD_SPCONV_PACK_FROM_PARAM", "1") != "0"
+
+
+def _packed_weights(w_k, K, cin, cout, sp, weight=None, param=None, mode=0):
+    """`param` (optional): the weights in the spconv-2 parameter layout (Cout_p, kz, ky, kx, Cin_p), fp32 contiguous; `mode`
+    0 forward / 1 dgrad of a SubM convolution / 2 dgrad of a strided one (see the C entry point).  Else `w_k` (K, cin, cout)."""
     lib = native.load()
     if weight is not None:
         hit = _PACK_CACHE.get(id(weight))
         if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
             return hit[2]
-    w_k = w_k() if callable(w_k) else w_k
     nbytes = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, cin, cout)
-    packed = torch.empty((nbytes,), dtype=torch.uint8, device=w_k.device)
-    rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
-    native.check(rc, "ud_sparse_conv_tc_pack_weights")
+    if (PACK_FROM_PARAM and param is not None and param.dtype == torch.float32 and param.is_contiguous()
+            and param.dim() == 5):
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=param.device)
+        rc = lib.ud_sparse_conv_tc_pack_weights_param(native.ptr(param), K, cin, cout, int(mode), native.ptr(packed), sp)
+        native.check(rc, "ud_sparse_conv_tc_pack_weights_param")
+    else:
+        w_k = w_k() if callable(w_k) else w_k
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=w_k.device)
+        rc = lib.ud_sparse_conv_tc_pack_weights(native.ptr(w_k), K, cin, cout, native.ptr(packed), sp)
+        native.check(rc, "ud_sparse_conv_tc_pack_weights")
     if weight is not None:
         if len(_PACK_CACHE) > 256:
             for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
@@ -257,7 +270,8 @@ def _packed_weights(w_k, K, cin, cout, sp, weight=None):
     return packed
 
 
-def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None, want_stats=False, post=None):
+def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, weight=None, want_stats=False, post=None,
+                      param=None, param_mode=0):
     """`post` = (scale, shift, residual | None, relu): inference epilogue relu?(conv * scale + shift (+ residual)); only the
     tensor-core kernel has it (the caller checks ud_sparse_conv_tc_supported)."""
     lib = native.load()
@@ -267,7 +281,7 @@ def _conv_forward_raw(feats, w_k, bias, table, n_out, K, cin, cout, rb=None, wei
     meta = {"n_in": int(feats.shape[0]), "n_out": n_out, "K": K, "cin": cin, "cout": cout,
             "table": table} if native.TIMER.enabled else None
     if USE_TENSOR_CORES and n_out > 0 and lib.ud_sparse_conv_tc_supported(K, cin, cout):
-        packed = _packed_weights(w_k, K, cin, cout, sp, weight)
+        packed = _packed_weights(w_k, K, cin, cout, sp, weight, param, param_mode)
         if meta is not None:
             meta["kernel"] = "k_spconv_umma_dg"
         table_t, masks = (rb if rb is not None else Rulebook.for_table(table)).tap_major(table)
@@ -355,33 +369,38 @@ class SparseConvFunction(Function):
             table, n_out = rb.nbr_in, rb.n_in
         assert features.shape[1] == cin, "feature width %d != conv in_channels %d" % (features.shape[1], cin)
         b = bias.detach().float().contiguous() if bias is not None else None
-        out = _conv_forward_raw(features, w_k_fn, b, table, n_out, rb.K, cin, cout, rb, weight, want_stats=True)
+        w_param = weight.detach()
+        if w_param.dtype != torch.float32 or not w_param.is_contiguous():
+            w_param = w_param.float().contiguous()
+        out = _conv_forward_raw(features, w_k_fn, b, table, n_out, rb.K, cin, cout, rb, weight, want_stats=True,
+                                param=w_param, param_mode=0)
         ctx.rb, ctx.inverse = rb, inverse
         ctx.has_bias = bias is not None
         ctx.wshape = tuple(weight.shape)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            ctx.save_for_backward(features, w_k_fn())
+            ctx.save_for_backward(features, w_param)      # the parameter layout: the dgrad packs its own form from it
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, w_k = ctx.saved_tensors
+        features, w_param = ctx.saved_tensors
         rb, inverse = ctx.rb, ctx.inverse
         lib = native.load()
         grad_out = grad_out.contiguous().float()
-        K, cin, cout = w_k.shape
+        cout, cin = int(w_param.shape[0]), int(w_param.shape[-1])
+        K = rb.K
         dfeat = dweight = dbias = None
         if ctx.needs_input_grad[0]:
             if rb.subm:
-                w_t = w_k.flip(0).transpose(1, 2).contiguous()   # (K, cout, cin), taps mirrored
-                table, n_in = rb.nbr_out, rb.n_in
+                w_t = lambda: weight_to_taps(w_param).flip(0).transpose(1, 2).contiguous()   # (K, cout, cin), taps mirrored
+                table, n_in, mode = rb.nbr_out, rb.n_in, 1
             elif not inverse:
-                w_t = w_k.transpose(1, 2).contiguous()
-                table, n_in = rb.nbr_in, rb.n_in
+                w_t = lambda: weight_to_taps(w_param).transpose(1, 2).contiguous()
+                table, n_in, mode = rb.nbr_in, rb.n_in, 2
             else:
-                w_t = w_k.transpose(1, 2).contiguous()
-                table, n_in = rb.nbr_out, rb.n_out
-            dfeat = _conv_forward_raw(grad_out, w_t, None, table, n_in, K, cout, cin, rb)
+                w_t = lambda: weight_to_taps(w_param).transpose(1, 2).contiguous()
+                table, n_in, mode = rb.nbr_out, rb.n_out, 2
+            dfeat = _conv_forward_raw(grad_out, w_t, None, table, n_in, K, cout, cin, rb, param=w_param, param_mode=mode)
         if ctx.needs_input_grad[1]:
             dw = torch.zeros((K, cin, cout), dtype=torch.float32, device=grad_out.device)
             if not inverse:

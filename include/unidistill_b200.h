@@ -130,6 +130,11 @@ int ud_sparse_conv_wgrad(const float* in, const float* dout, const int* nbr, int
 int ud_sparse_conv_tc_supported(int K, int cin, int cout);
 int ud_sparse_conv_tc_weight_bytes(int K, int cin, int cout, size_t* bytes);
 int ud_sparse_conv_tc_pack_weights(const float* w, int K, int cin, int cout, void* packed, void* stream);
+/* The same image straight from the spconv-2 parameter layout (Cout_p, kz, ky, kx, Cin_p) of spconv.SubMConv3d /
+ * SparseConv3d.weight (spconv_backbone.py:259-340), for the convolution that will run with (cin, cout):
+ * mode 0 forward (cin = Cin_p, cout = Cout_p); mode 1 data gradient of a submanifold convolution (cin = Cout_p,
+ * cout = Cin_p: transposed weights, mirrored taps); mode 2 data gradient of a strided convolution (transposed). */
+int ud_sparse_conv_tc_pack_weights_param(const float* w_param, int K, int cin, int cout, int mode, void* packed, void* stream);
 /* nbr (n,K) row-major gather table -> nbr_t (K4,ld) tap-major with K4 = K rounded up to 4, ld = n rounded up to 128
  * (padding -1; 16-byte aligned base) + tile_masks (ceil(n/128)) uint32 with bit k set when tap k occurs in that 128-row
  * tile: the two table forms the tensor-core kernels read */

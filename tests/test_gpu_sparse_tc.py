@@ -397,3 +397,36 @@ def test_one_and_two_ctas_per_sm_give_identical_outputs(cuda, native_lib):
         assert r.returncode == 0, r.stderr[-2000:]
         digests[nsets] = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert digests["2"] == digests["4"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 64), (64, 64), (128, 64), (128, 128)])
+def test_packing_from_the_parameter_layout_is_bit_identical(cuda, native_lib, cin, cout):
+    """ud_sparse_conv_tc_pack_weights_param (reads the spconv-2 parameter (Cout, kz, ky, kx, Cin) in place; mode 0 forward,
+    1 dgrad of a SubM convolution = transposed + mirrored taps, 2 dgrad of a strided one = transposed) against
+    ud_sparse_conv_tc_pack_weights on the explicitly permuted / flipped copies."""
+    from unidistill_b200 import native, sparse as SP
+
+    lib = native.load()
+    torch.manual_seed(cin * 7 + cout)
+    K = 27
+    w = torch.randn(cout, 3, 3, 3, cin, device=cuda)
+    w_k = SP.weight_to_taps(w)                                             # (K, cin, cout)
+    sp = native.stream_ptr(cuda)
+
+    def pack_ref(wk, ci, co):
+        n = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, ci, co)
+        out = torch.zeros((n,), dtype=torch.uint8, device=cuda)
+        native.check(lib.ud_sparse_conv_tc_pack_weights(native.ptr(wk.contiguous()), K, ci, co, native.ptr(out), sp), "pack")
+        return out
+
+    def pack_param(mode, ci, co):
+        n = native.query_bytes("ud_sparse_conv_tc_weight_bytes", K, ci, co)
+        out = torch.zeros((n,), dtype=torch.uint8, device=cuda)
+        native.check(lib.ud_sparse_conv_tc_pack_weights_param(native.ptr(w), K, ci, co, mode, native.ptr(out), sp), "pack_param")
+        return out
+
+    assert torch.equal(pack_param(0, cin, cout), pack_ref(w_k, cin, cout))
+    if lib.ud_sparse_conv_tc_supported(K, cout, cin):
+        assert torch.equal(pack_param(1, cout, cin), pack_ref(w_k.flip(0).transpose(1, 2), cout, cin))
+        assert torch.equal(pack_param(2, cout, cin), pack_ref(w_k.transpose(1, 2), cout, cin))
