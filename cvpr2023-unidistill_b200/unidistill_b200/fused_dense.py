@@ -64,17 +64,45 @@ class FusedConvReLU(nn.Module):
         return conv_bias_relu(self.conv, x)
 
 
+def _shortcut(block, last_conv, x):
+    """(identity tensor, bias for the block's last convolution).  A projection shortcut is `conv1x1 (+ folded BN)`: PyTorch
+    runs its bias as a broadcast add over the whole activation (0.19 / 0.10 / 0.04 ms for the three projections of the
+    teacher's ResNet-50 on B200); here the projection runs WITHOUT its bias, which is added to the last convolution's bias
+    instead -- relu(conv3(out) + (b3 + b_ds) + conv_ds(x)) -- inside that convolution's cuDNN epilogue."""
+    ds = block.downsample
+    if ds is None:
+        return x, last_conv.bias
+    if (x.is_cuda and not torch.is_grad_enabled() and isinstance(ds, nn.Sequential) and len(ds) >= 1 and _fusable_conv(ds[0])
+            and all(isinstance(m, nn.Identity) for m in list(ds)[1:]) and ds[0].bias is not None
+            and last_conv.bias is not None and _fusable_conv(last_conv)):
+        conv = ds[0]
+        key = (conv.bias.data_ptr(), conv.bias._version, last_conv.bias.data_ptr(), last_conv.bias._version)
+        hit = getattr(block, "_ud_shortcut_bias", None)
+        if hit is None or hit[0] != key:
+            hit = (key, (last_conv.bias.detach() + conv.bias.detach()))
+            block._ud_shortcut_bias = hit
+        return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups), hit[1]
+    return ds(x), last_conv.bias
+
+
+def _conv_add_relu(conv, x, residual, bias):
+    if x.is_cuda and not torch.is_grad_enabled() and _fusable_conv(conv):
+        return torch.cudnn_convolution_add_relu(x, conv.weight, residual, 1.0, bias, conv.stride, conv.padding, conv.dilation,
+                                                conv.groups)
+    return F.relu(F.conv2d(x, conv.weight, bias, conv.stride, conv.padding, conv.dilation, conv.groups) + residual)
+
+
 def _bottleneck_forward(self, x):
-    identity = x if self.downsample is None else self.downsample(x)
+    identity, bias = _shortcut(self, self.conv3, x)
     out = conv_bias_relu(self.conv1, x)
     out = conv_bias_relu(self.conv2, out)
-    return conv_bias_relu(self.conv3, out, identity)
+    return _conv_add_relu(self.conv3, out, identity, bias)
 
 
 def _basicblock_forward(self, x):
-    identity = x if self.downsample is None else self.downsample(x)
+    identity, bias = _shortcut(self, self.conv2, x)
     out = conv_bias_relu(self.conv1, x)
-    return conv_bias_relu(self.conv2, out, identity)
+    return _conv_add_relu(self.conv2, out, identity, bias)
 
 
 def fuse_frozen_conv_relu(module, skip=()):
