@@ -415,6 +415,41 @@ def test_backbone_forward_parity(cuda, native_lib, training):
     assert _rel_err(bev.detach().cpu().numpy(), ref_bev) < REL_TOL
 
 
+def test_bias_gradient_in_front_of_train_mode_batchnorm_is_zero(cuda, native_lib, monkeypatch):
+    """conv(bias) -> BatchNorm1d(train) -> ReLU: the bias gradient is identically zero; SparseConvFunction.backward skips the
+    column-sum pass over dx when BatchNormActFunction.backward marked it.  The explicit column sums are round-off noise."""
+    from unidistill_b200 import sparse as SP
+
+    torch.manual_seed(2)
+    rng = np.random.default_rng(9)
+    coords, feat = _clustered_sparse(rng, 2, [21, 48, 48], 4000, 32)
+    c = torch.from_numpy(coords).to(cuda)
+    rb = SP.build_subm_rulebook(c, 2, [21, 48, 48], 3)
+    w = (torch.randn(32, 3, 3, 3, 32, device=cuda) * 0.05).requires_grad_(True)
+    b = torch.randn(32, device=cuda).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(32, eps=1e-3, momentum=0.01).to(cuda).train()
+    x = torch.from_numpy(feat).to(cuda)
+
+    def run(flag):
+        monkeypatch.setattr(SP, "ZERO_BIAS_GRAD_UNDER_BN", flag)
+        for t in (w, b):
+            t.grad = None
+        y = SP.batch_norm_act(SP.sparse_conv(x, w, b, rb), bn, relu=True)
+        (y * torch.linspace(0.5, 1.5, 32, device=cuda)).sum().backward()
+        return b.grad.clone(), w.grad.clone()
+
+    gb_sum, gw_sum = run(False)
+    gb_zero, gw_zero = run(True)
+    assert torch.count_nonzero(gb_zero) == 0
+    assert float(gb_sum.abs().max()) <= 1e-4 * float(gw_sum.abs().max())      # what the explicit pass computes is noise
+    assert torch.allclose(gw_zero, gw_sum, rtol=1e-4, atol=1e-6 * float(gw_sum.abs().max()))
+    # without the BatchNorm the bias gradient is the plain column sum
+    for t in (w, b):
+        t.grad = None
+    SP.sparse_conv(x, w, b, rb).sum().backward()
+    assert torch.allclose(b.grad, torch.full_like(b.grad, float(x.shape[0])), rtol=1e-5)
+
+
 def test_prebuilt_rulebooks_equal_lazy_ones(cuda, native_lib, monkeypatch):
     """Geometry first (spconv.prebuild_rulebooks before the feature pass) against the reference's lazy, layer-by-layer
     rulebook construction: identical tables, hence bit-identical encoder outputs and gradients."""
