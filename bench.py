@@ -188,10 +188,11 @@ class PipelinedE2E:
     step i-1 overlap the kernels of step i (double-buffered device inputs / host outputs).  All K copies in and K reads
     out happen between the start and the end event of the timed region."""
 
-    def __init__(self, device, host_inputs, forward, result_of):
+    def __init__(self, device, host_inputs, forward, result_of, prefetch=None):
         import torch
 
         self.device, self.host_inputs, self.forward, self.result_of = device, host_inputs, forward, result_of
+        self.prefetch = prefetch        # optional: prefetch(ready_event, *next step's device inputs) after a step's launch
         self.copy_stream = torch.cuda.Stream(device=device)
         self.dev_in = [None, None]
         self.in_ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -235,6 +236,8 @@ class PipelinedE2E:
             self.prefetched = True
         cur.wait_event(self.in_ready[slot])
         res = self.result_of(self.forward(*self.dev_in[slot]))
+        if self.prefetch is not None and not last:
+            self.prefetch(self.in_ready[1 - slot], *self.dev_in[1 - slot])
         self.in_free[slot].record(cur)
         done = torch.cuda.Event()
         done.record(cur)
@@ -420,16 +423,41 @@ class DistillTrainStep:
         self.d2h = 4
         self.samples = BS_PER_GPU
         n_raw = len(self.raw.host)
-        self.pipe = PipelinedE2E(device, self.host,
-                                 lambda *t: self.step_fn(self._batch(self.raw.clouds(t[:n_raw]), *t[n_raw:])),
-                                 lambda terms: terms["loss"].reshape(1))
+        # The voxelization + rulebooks of the NEXT step are built on a side stream right after this step's launch, under its
+        # backward (DistillStep.prefetch_geometry): every timed step still does one full geometry phase -- the next one's.
+        self.prefetch_geometry = (os.environ.get("UD_PREFETCH_GEOMETRY", "1") != "0"
+                                  and (self.teacher_modalities["lidar"] or self.student_modalities["lidar"]))
+        self._n_raw = n_raw
+        self._next_clouds = {}
+        self.pipe = PipelinedE2E(device, self.host, self._e2e_forward, lambda terms: terms["loss"].reshape(1),
+                                 prefetch=self._e2e_prefetch if self.prefetch_geometry else None)
+
+    def _e2e_forward(self, *t):
+        clouds = self._next_clouds.pop(t[0].data_ptr(), None)
+        if clouds is None:
+            clouds = self.raw.clouds(t[:self._n_raw])
+        return self.step_fn(self._batch(clouds, *t[self._n_raw:]))
+
+    def _e2e_prefetch(self, ready_event, *t):
+        import torch
+
+        side = self.step_fn.geometry_stream()
+        side.wait_event(ready_event)                 # the next step's host -> device copies
+        with torch.cuda.stream(side):
+            clouds = self.raw.clouds(t[:self._n_raw])        # input-side kernel (sweep merge, range filter, ragged collate)
+        self._next_clouds.clear()
+        self._next_clouds[t[0].data_ptr()] = clouds
+        self.step_fn.prefetch_geometry(clouds)
 
     def _batch(self, clouds, imgs, gt_boxes, gt_labels, *mats):
         return {"points": clouds, "imgs": imgs, "gt_boxes": gt_boxes, "gt_labels": gt_labels,
                 "mats_dict": dict(zip(self._mat_keys, mats))}
 
     def step(self):
-        return self.step_fn(self.dev)
+        r = self.step_fn(self.dev)
+        if self.prefetch_geometry:
+            self.step_fn.prefetch_geometry(self.dev["points"])
+        return r
 
 
 class DistillLidarTrainStep(DistillTrainStep):
@@ -752,6 +780,7 @@ def measure(wl, args, world, rank, local, device, peaks, with_roofline=True):
         "step_ms_min_med_max": [round(min(step_ms), 3), round(sorted(step_ms)[len(step_ms) // 2], 3),
                                 round(max(step_ms), 3)],
         "rank_ms_per_step_min_med_max": [round(rank_ms[0], 3), round(rank_ms[len(rank_ms) // 2], 3), round(rank_ms[-1], 3)],
+        "step_ms": [round(v, 3) for v in step_ms],
     }
     if roof_all:
         res["roofline"] = _dominant(roof_all)

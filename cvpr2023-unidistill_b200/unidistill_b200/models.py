@@ -148,17 +148,28 @@ class LidarEncoder(BaseEncoder):
             if hit is not None and (hit["key"] != self._geometry_key() or hit["points"] is not lidar_points):
                 hit = None
         if hit is None:
-            voxels, coords, num = self.voxelizer(lidar_points)
-            feats = self.vfe(voxels, num)
-            indice_dict = {}
-            if geometry is not None:
-                geometry["lidar"] = dict(key=self._geometry_key(), points=lidar_points, feats=feats, coords=coords,
-                                         indice_dict=indice_dict)
-        else:
-            feats, coords, indice_dict = hit["feats"], hit["coords"], hit["indice_dict"]
+            hit = self.build_geometry(lidar_points, geometry if geometry is not None else {}, rulebooks=False)
+        feats, coords, indice_dict = hit["feats"], hit["coords"], hit["indice_dict"]
         sp, stride, _ = self.backbone_3d(feats, coords, len(lidar_points), indice_dict=indice_dict)
         bev, _ = self.map_to_bev(sp, stride)
         return bev
+
+    def build_geometry(self, lidar_points, geometry, rulebooks=True):
+        """Everything of the encoder that depends on the points only -- voxelization, mean VFE and (rulebooks=True) all
+        rulebooks of the backbone -- into geometry["lidar"]; forward() picks it up when it is handed the same `lidar_points`
+        object.  Runs on the current stream, so a trainer can call it for the NEXT batch on a side stream under the current
+        step's backward (DistillStep.prefetch_geometry): the host reads of this phase then stall nobody."""
+        voxels, coords, num = self.voxelizer(lidar_points)
+        feats = self.vfe(voxels, num)
+        indice_dict = {}
+        entry = dict(key=self._geometry_key(), points=lidar_points, feats=feats, coords=coords, indice_dict=indice_dict)
+        if rulebooks and coords.is_cuda and not getattr(self.backbone_3d, "morton_order", False):
+            import spconv.pytorch as spconv
+
+            spconv.prebuild_rulebooks(self.backbone_3d, coords.int().contiguous(),
+                                      [int(v) for v in self.backbone_3d.sparse_shape], len(lidar_points), indice_dict)
+        geometry["lidar"] = entry
+        return entry
 
 
 class CameraEncoder(BaseEncoder):

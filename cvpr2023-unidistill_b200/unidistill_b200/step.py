@@ -296,6 +296,25 @@ def fused_normalisers(ret, valid, mask_sum):
     return AsyncNormalisers(ret, valid, mask_sum).get()
 
 
+def _record_stream(obj, stream, _seen=None):
+    """tensor.record_stream(stream) for every tensor reachable from obj (dicts, sequences, objects with a __dict__)."""
+    seen = _seen if _seen is not None else set()
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream, seen)
+    elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.nn.Module, type)):
+        _record_stream(vars(obj), stream, seen)
+
+
 class DistillStep:
     """student / teacher: BEVFusionCenterHead models on the same device.  `geometry`: dict(pc_range, voxel_size,
     out_size_factor).  Call with a device-resident batch dict (points list | None, imgs | None, mats_dict | None,
@@ -319,6 +338,10 @@ class DistillStep:
         lr = float(lr if lr is not None else cfg["lr"])
         assert teacher_mode in ("eval", "train")
         self.teacher_mode = teacher_mode
+        self._geo_stream = None
+        self._geo_events = None
+        self._geo_turn = 0
+        self._prefetched = None
         self.student, self.teacher = student, teacher
         self.pc_range = list(geometry["pc_range"])
         self.voxel_size = list(geometry["voxel_size"])
@@ -403,6 +426,10 @@ class DistillStep:
             norm["n_valid"], norm["mask_sum"] = n_valid, mask_sum
 
         geometry = {}       # voxels + rulebooks of the step's clouds, shared by the two LiDAR encoders (if there are two)
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf[0] is points:          # built on the side stream under the previous step's backward
+            torch.cuda.current_stream().wait_event(pf[2])
+            geometry = pf[1]
         cam_future = None
         if (self.overlap_teacher_camera and imgs is not None and imgs.is_cuda and self.teacher.with_camera_encoder
                 and self.teacher.with_lidar_encoder):
@@ -430,6 +457,38 @@ class DistillStep:
             self.last = dict(feat_s=feat_s, bev_s=bev_s, resp_s=resp_s, feat_t=feat_t, bev_t=bev_t, resp_t=resp_t,
                              gt=gt, valid=valid, corners=corners, norm=dict(norm))
         return terms
+
+    def geometry_stream(self):
+        if self._geo_stream is None:
+            self._geo_stream = torch.cuda.Stream()
+        return self._geo_stream
+
+    def prefetch_geometry(self, points, ready_event=None):
+        """Voxelization + rulebooks of the NEXT step's clouds on a side stream.  Call it right after `step(batch)` returned
+        (the host has launched the whole step, the GPU is still in its backward): the five host reads of the geometry
+        phase then wait on the side stream only, and the next step finds its geometry ready (`points` must be the very
+        object the next batch carries; `ready_event`: recorded where the clouds were produced, if not on this stream)."""
+        enc = None
+        for net in (self.student, self.teacher):
+            if getattr(net, "with_lidar_encoder", False):
+                enc = net.lidar_encoder
+                break
+        if enc is None or not points or not points[0].is_cuda:
+            return
+        main = torch.cuda.current_stream()
+        side = self.geometry_stream()
+        if ready_event is not None:
+            side.wait_event(ready_event)
+        geometry = {}
+        if self._geo_events is None:         # two reusable events: creating one per step inside a timed region contends
+            self._geo_events = [torch.cuda.Event(), torch.cuda.Event()]      # with NVML clock sampling for a driver lock
+        self._geo_turn ^= 1
+        done = self._geo_events[self._geo_turn]
+        with torch.cuda.stream(side):
+            enc.build_geometry(points, geometry)
+            done.record(side)
+        _record_stream(geometry, main)      # allocated on the side stream, consumed (and freed) on the main one
+        self._prefetched = (points, geometry, done)
 
     def __call__(self, batch):
         self.bucket.zero()

@@ -198,3 +198,37 @@ def test_camera_branch_on_a_side_stream_gives_the_same_teacher(cuda, native_lib)
             for tg, tr in zip(got[2], ref[2]):
                 for k in tr:
                     assert torch.allclose(tg[k], tr[k], rtol=1e-4, atol=1e-5), k
+
+
+def test_prefetched_geometry_gives_identical_losses(cuda, native_lib):
+    """DistillStep.prefetch_geometry builds the next step's voxels and rulebooks on a side stream; the step that consumes
+    them must compute exactly what a step that builds them in line computes (LiDAR student and LiDAR teacher share them)."""
+    from unidistill_b200 import models
+    from unidistill_b200.step import DistillStep
+
+    torch.manual_seed(0)
+    cfg = models.make_model_cfg(bev=128, lidar=True, camera=False)
+    teacher = models.BEVFusionCenterHead(cfg).to(cuda)
+    student = models.BEVFusionCenterHead(cfg).to(cuda)
+    step = DistillStep(student, teacher, cfg["geometry"], optimizer=False, student_cuda_graph=False)
+    batch = _batch(cuda, bs=2)
+
+    def forward_terms():
+        step.bucket.zero()
+        with torch.no_grad():
+            t = step.losses(batch)
+        return {k: float(v) for k, v in t.items()}
+
+    ref = forward_terms()
+    assert step._prefetched is None
+    step.prefetch_geometry(batch["points"])
+    assert step._prefetched is not None and "lidar" in step._prefetched[1]
+    n_rulebooks = len([k for k in step._prefetched[1]["lidar"]["indice_dict"] if isinstance(k, str)])
+    assert n_rulebooks >= 8                       # 4 SubM keys + 4 strided keys of VoxelResBackBone8x
+    got = forward_terms()
+    assert step._prefetched is None               # consumed
+    assert got == ref, (got, ref)
+    # a prefetch for OTHER clouds is ignored (identity of the points object decides)
+    other = _batch(cuda, bs=2)
+    step.prefetch_geometry(other["points"])
+    assert forward_terms() == ref
