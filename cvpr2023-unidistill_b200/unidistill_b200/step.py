@@ -296,25 +296,6 @@ def fused_normalisers(ret, valid, mask_sum):
     return AsyncNormalisers(ret, valid, mask_sum).get()
 
 
-def _record_stream(obj, stream, _seen=None):
-    """tensor.record_stream(stream) for every tensor reachable from obj (dicts, sequences, objects with a __dict__)."""
-    seen = _seen if _seen is not None else set()
-    if id(obj) in seen:
-        return
-    seen.add(id(obj))
-    if isinstance(obj, torch.Tensor):
-        if obj.is_cuda:
-            obj.record_stream(stream)
-    elif isinstance(obj, dict):
-        for v in obj.values():
-            _record_stream(v, stream, seen)
-    elif isinstance(obj, (list, tuple)):
-        for v in obj:
-            _record_stream(v, stream, seen)
-    elif hasattr(obj, "__dict__") and not isinstance(obj, (torch.nn.Module, type)):
-        _record_stream(vars(obj), stream, seen)
-
-
 class DistillStep:
     """student / teacher: BEVFusionCenterHead models on the same device.  `geometry`: dict(pc_range, voxel_size,
     out_size_factor).  Call with a device-resident batch dict (points list | None, imgs | None, mats_dict | None,
@@ -342,6 +323,8 @@ class DistillStep:
         self._geo_events = None
         self._geo_turn = 0
         self._prefetched = None
+        self._geo_in_use = None
+        self._geo_prev = None
         self.student, self.teacher = student, teacher
         self.pc_range = list(geometry["pc_range"])
         self.voxel_size = list(geometry["voxel_size"])
@@ -430,6 +413,7 @@ class DistillStep:
         if pf is not None and pf[0] is points:          # built on the side stream under the previous step's backward
             torch.cuda.current_stream().wait_event(pf[2])
             geometry = pf[1]
+            self._geo_in_use = geometry                 # kept alive until the side stream may reuse its memory
         cam_future = None
         if (self.overlap_teacher_camera and imgs is not None and imgs.is_cuda and self.teacher.with_camera_encoder
                 and self.teacher.with_lidar_encoder):
@@ -477,17 +461,26 @@ class DistillStep:
             return
         main = torch.cuda.current_stream()
         side = self.geometry_stream()
+        if self._geo_events is None:         # reusable events: creating them per step inside a timed region contends with
+            self._geo_events = [torch.cuda.Event() for _ in range(4)]        # NVML clock sampling for a driver lock
+        self._geo_turn ^= 1
+        done, step_end = self._geo_events[self._geo_turn], self._geo_events[2 + self._geo_turn]
+        # Memory protocol (no record_stream: tensors parked by it made the allocator grow for several steps, each growth a
+        # device-wide stall).  The geometry tensors live in the side stream's pool but are read on the main stream, so they
+        # may only return to the pool once the main stream is past their step: the geometry consumed by the step BEFORE
+        # the one just launched is released here, after the side stream has been told to wait for that step's end.
+        if self._geo_prev is not None:
+            side.wait_event(self._geo_prev[1])
+            self._geo_prev = None
+        step_end.record(main)                # end of the step that has just been launched (it consumed _geo_in_use)
+        if self._geo_in_use is not None:
+            self._geo_prev, self._geo_in_use = (self._geo_in_use, step_end), None
         if ready_event is not None:
             side.wait_event(ready_event)
         geometry = {}
-        if self._geo_events is None:         # two reusable events: creating one per step inside a timed region contends
-            self._geo_events = [torch.cuda.Event(), torch.cuda.Event()]      # with NVML clock sampling for a driver lock
-        self._geo_turn ^= 1
-        done = self._geo_events[self._geo_turn]
         with torch.cuda.stream(side):
             enc.build_geometry(points, geometry)
             done.record(side)
-        _record_stream(geometry, main)      # allocated on the side stream, consumed (and freed) on the main one
         self._prefetched = (points, geometry, done)
 
     def __call__(self, batch):
