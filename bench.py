@@ -427,6 +427,9 @@ class DistillTrainStep:
         # backward (DistillStep.prefetch_geometry): every timed step still does one full geometry phase -- the next one's.
         self.prefetch_geometry = (os.environ.get("UD_PREFETCH_GEOMETRY", "1") != "0"
                                   and (self.teacher_modalities["lidar"] or self.student_modalities["lidar"]))
+        self.geometry_note = ("voxelization + rulebooks of step i+1 built on a side stream right after step i's launch, under its "
+                              "backward (one complete geometry phase per timed step; UD_PREFETCH_GEOMETRY=0: in line)"
+                              if self.prefetch_geometry else "voxelization and rulebooks built inside every step")
         self._n_raw = n_raw
         self._next_clouds = {}
         self.pipe = PipelinedE2E(device, self.host, self._e2e_forward, lambda terms: terms["loss"].reshape(1),
@@ -771,6 +774,7 @@ def measure(wl, args, world, rank, local, device, peaks, with_roofline=True):
         "config": {"workload": wl.name, "baseline_config": "configs[%d]" % wl.config_id,
                    "global_batch": wl.samples * world, "per_gpu_batch": wl.samples,
                    "bn": wl.bn_note, "weights": "random init, seed 0",
+                   "geometry": getattr(wl, "geometry_note", "voxelization and rulebooks built inside every step"),
                    "l2": "flushed (256 MiB fill) between timed steps; per-step CUDA events summed (e2e: one event pair "
                          "around the K steps, flushes included)",
                    "dense_convs": "cuDNN fp32 (torch default allow_tf32), NHWC memory format", "parallelism": "dp%d" % world},
