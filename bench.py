@@ -459,8 +459,8 @@ class DistillTrainStep:
     def step(self):
         r = self.step_fn(self.dev)
         if self.prefetch_geometry:
-            self.step_fn.prefetch_geometry(self.dev["points"])
-        return r
+            self.step_fn.prefetch_geometry(self.dev["points"])     # the NEXT step's geometry (here: the same resident clouds,
+        return r                                                   # recomputed every step like any other batch's would be)
 
 
 class DistillLidarTrainStep(DistillTrainStep):
