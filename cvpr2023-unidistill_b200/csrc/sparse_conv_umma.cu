@@ -34,7 +34,6 @@ constexpr int MAX_SCHED = MAX_TAPS * 4 * 8;   // >= taps * stages per tap * tile
 constexpr int TS_GROUP = 128;          // threads of one gather set
 constexpr int TS_ACC_COLS = 256;       // TMEM columns holding accumulators; the other 256 hold the A-operand ring
 
-__host__ __device__ constexpr int ts_tiles_max(int cout) { return TS_ACC_COLS / cout < 8 ? TS_ACC_COLS / cout : 8; }
 
 // taps that share one 64-channel stage (narrow layers)
 __host__ __device__ constexpr int ts_tapg(int cin) { return cin < 64 ? 64 / cin : 1; }
@@ -258,7 +257,6 @@ __device__ __forceinline__ void dg_set_arrive(uint32_t bar, int lane) {
 #else
 #define DG_MMA_WAIT mbar_wait
 #endif
-constexpr int DG_THREADS = 608;
 constexpr int DG_SETS = 4;
 // Per-CTA configuration of k_spconv_umma_dg, template parameter NSETS = gather sets = TMEM A slots:
 //   NSETS 4: one CTA per SM -- 512 TMEM columns (256 accumulators | 4 x 64 A ring), 16 gather warps + MMA + weights + indices warp
@@ -272,7 +270,6 @@ __host__ __device__ constexpr int dg_acc_cols(int nsets) { return 64 * nsets; }
 __host__ __device__ constexpr int dg_tiles_max(int nsets, int cout) { return dg_acc_cols(nsets) / cout < 8 ? dg_acc_cols(nsets) / cout : 8; }
 __host__ __device__ constexpr int dg_b_stages(int nsets, int cout) { return (nsets == 2 && cout >= 128) ? 2 : 4; }
 constexpr int DG_IDX_STAGES = 16;
-constexpr int DG_B_STAGES = 4;
 // statistics buffer: [0, 4096) final sums (2 * COUT doubles), then the workspace of det_reduce.cuh
 constexpr int DG_STAT_FINAL_BYTES = 4096;
 // Optional output transform of the forward kernels (inference: the eval-mode BatchNorm1d, residual add and ReLU that follow a
@@ -473,7 +470,6 @@ k_spconv_umma_dg(const __grid_constant__ CUtensorMap idx_map, const float* __res
     const int lane = tid & 31;
     const int row0 = blockIdx.x * tiles * TILE_M;
     const int rows_cta = min(tiles * TILE_M, n_out - row0);
-    const size_t ld_t = (size_t)((n_out + TILE_M - 1) / TILE_M) * TILE_M;
     if (stats != nullptr)
         for (int i = tid; i < GW * 2 * COUT; i += NTHREADS) wpart_s[i] = 0.f;
 
